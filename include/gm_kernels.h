@@ -1,0 +1,219 @@
+/*
+ * gm_kernels.h -- C-ABI of libgm_b200.so: the B200 (sm_100a) kernels behind the
+ * graphembed training hot path (pair distance + gradient, distortion loss,
+ * Riemannian optimizer step, BFS graph-distance targets).
+ *
+ * The reference (dalab/matrix-manifolds, `graphembed`) has no FFI: its "plugin
+ * API" for this path is the Python Manifold / optimizer interface.  Every entry
+ * point below therefore cites the reference *Python* function(s) it replaces
+ * (paths relative to /root/reference/graphembed/).  The Python drop-in package
+ * (matrix-manifolds_b200/graphembed) binds these with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless
+ *     the name ends in `_host`; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, a negative GM_E* code for bad
+ *     arguments (nothing launched) or a positive cudaError_t from the launch.
+ *   - kernels never allocate; outputs/workspaces are caller-owned.
+ *   - dtype selects the arithmetic AND storage type of all `void*` real arrays.
+ *   - re-entrant: no global mutable state; uses the caller's current device.
+ */
+#ifndef GM_KERNELS_H
+#define GM_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gm_stream_t; /* cudaStream_t */
+
+/* ---- error codes -------------------------------------------------------- */
+#define GM_OK 0
+#define GM_EINVAL (-1)       /* bad argument combination            */
+#define GM_EUNSUPPORTED (-2) /* (kind, n, p, dtype) not instantiated */
+#define GM_ENULL (-3)        /* required pointer is NULL            */
+
+/* ---- enums -------------------------------------------------------------- */
+enum gm_dtype { GM_F32 = 0, GM_F64 = 1 };
+
+enum gm_manifold_kind {
+  GM_SPD_AI = 0,    /* manifolds/spd.py:171-181  affine-invariant squared distance        */
+  GM_SPD_STEIN = 1, /* manifolds/spd.py:183-194,246-295  symmetric Stein divergence         */
+  GM_LORENTZ = 2,   /* manifolds/lorentz.py:72-77                                          */
+  GM_SPHERE = 3,    /* manifolds/sphere.py:68-74                                           */
+  GM_GRASSMANN = 4, /* manifolds/grassmann.py:91-96                                        */
+  GM_EUCLIDEAN = 5  /* manifolds/euclidean.py:46-50 via base.py:56-57                      */
+};
+
+/* gm_manifold_t.flags */
+#define GM_FAST_EIG 1u  /* SPD n=2,3: closed-form eigenvalues with the reference's eps terms (linalg/fast.py:53-91)   */
+#define GM_FAST_CHOL 2u /* SPD n=2: closed-form (inverse) Cholesky with eps terms (linalg/fast.py:94-134)             */
+#define GM_FAST_SVD 4u  /* Grassmann p=2: closed-form singular values (linalg/fast.py:138-159)                         */
+
+typedef struct gm_manifold {
+  int32_t kind;  /* gm_manifold_kind */
+  int32_t dtype; /* gm_dtype */
+  int32_t n;     /* SPD: matrix size; Lorentz: ambient dim; Sphere/Euclidean: #elements per point; Grassmann: rows */
+  int32_t p;     /* Grassmann: columns; otherwise 0 */
+  uint32_t flags;
+  int32_t reserved;
+  double wmin; /* SPD eigenvalue / distance clamp (spd.py:28-29), default 1e-8 */
+  double wmax; /* default 1e8 */
+} gm_manifold_t;
+
+/* How the P pairs of one launch are enumerated. */
+enum gm_pairs_mode {
+  GM_PAIRS_ELEMENTWISE = 0, /* pair k = (xa[k], xb[k])                       -- Manifold.dist(x, y)  (base.py:56-57)        */
+  GM_PAIRS_LIST = 1,        /* pair k = (xa[idx_i[k]], xb[idx_j[k]])         -- dist(x[I], x[J]) incl. the gather           */
+  GM_PAIRS_TRIU = 2         /* pair k = k-th (a<b) of triu_indices(B,B,1), rows
+                               xa[nodes[a]], xb[nodes[b]] (nodes NULL: a, b) -- Manifold.pdist (base.py:59-63) fused with
+                                                                                x[indices] (modules.py:84-88)              */
+};
+
+typedef struct gm_pairs {
+  int32_t mode;      /* gm_pairs_mode */
+  int32_t idx64;     /* 1: idx_i/idx_j/nodes are int64, 0: int32 */
+  int64_t P;         /* number of pairs (TRIU: must equal B(B-1)/2) */
+  const void* idx_i; /* LIST */
+  const void* idx_j; /* LIST */
+  int64_t B;         /* TRIU */
+  const void* nodes; /* TRIU, optional */
+} gm_pairs_t;
+
+/* Loss on (graph target g, manifold squared distance m) -- objectives.py:16-45. */
+enum gm_loss_kind { GM_LOSS_QUOTIENT = 0, GM_LOSS_STRESS = 1 };
+typedef struct gm_loss {
+  int32_t kind;
+  int32_t inc_l1; /* QuotientLoss(inc_l1) : sum |m/(alpha g) - 1|            */
+  int32_t inc_l2; /* QuotientLoss(inc_l2) : sum |alpha g/(m+eps) - 1|        */
+  int32_t reserved;
+  double alpha; /* objectives.py:25 (Stress ignores it)                    */
+  double eps;   /* 1/(epoch+1), objectives.py:30                           */
+} gm_loss_t;
+
+/* Where the per-pair target g comes from. */
+enum gm_target_mode {
+  GM_TGT_VECTOR = 0, /* data[k], same dtype as the manifold -- GraphDataset.__getitem__ result (data/dataset.py:19-27) */
+  GM_TGT_DENSE = 1,  /* data[u*ld + v], u,v = node ids of the pair -- GraphDataset.pdists, fuses the double gather +
+                        masked_select of data/dataset.py:23-27 (LIST/TRIU modes only)                               */
+  GM_TGT_HOPS_U8 = 2, /* uint8 BFS hop count h per pair; g = (h*h)/max_sq computed in the manifold dtype exactly as
+                        data/dataset.py:11-12 does (pow(2) then div_(max))                                           */
+  GM_TGT_HOPS_U16 = 3
+};
+typedef struct gm_targets {
+  int32_t mode;
+  int32_t reserved;
+  const void* data;
+  int64_t ld;    /* DENSE: row stride in elements */
+  double max_sq; /* HOPS: max over the graph of h*h */
+} gm_targets_t;
+
+/* ---- pair kernels -------------------------------------------------------- */
+
+/* out_d2[k] = squared manifold distance (Stein: divergence) of pair k, with the reference's value-only clamps.
+ * Replaces Manifold.dist/pdist(..., squared=True): spd.py:171-194, lorentz.py:72-77, sphere.py:68-74,
+ * grassmann.py:91-96, base.py:56-63 and the linalg they call (linalg/torch_batch.py, linalg/fast.py). */
+int gm_pairs_dist2(const gm_manifold_t* man, const void* xa, const void* xb, const gm_pairs_t* pairs,
+                   void* out_d2, gm_stream_t stream);
+
+/* Backward of gm_pairs_dist2: for every pair k adds coef*gout[k]*d(d2_k)/d(x) to the rows of ga / gb the pair
+ * touches (ELEMENTWISE: plain stores to row k; LIST/TRIU: atomic accumulation into row idx -- the fused
+ * index_put_(accumulate=True) of autograd).  ga/gb may alias.  SPD gradients are symmetric
+ * (what egrad2rgrad's sym() keeps, spd.py:134-135).  Straight-through clamps as in the reference. */
+int gm_pairs_grad(const gm_manifold_t* man, const void* xa, const void* xb, const gm_pairs_t* pairs,
+                  const void* gout, double coef, void* ga, void* gb, gm_stream_t stream);
+
+/* Single-factor fused hot path: distance, loss term and gradient in one pass.
+ *   m_k = scale_sp * d2_k;  loss += l(g_k, m_k);  grad[rows] += l'(g_k, m_k) * scale_sp * d(d2_k)/dx
+ *   acc[0] += sum_k l(g_k, m_k)          (double)
+ *   acc[1] += sum_k l'(g_k, m_k) * d2_k  (double; times sigmoid(scale) it is d loss / d scale, modules.py:84-88)
+ * out_d2 (optional, may be NULL) receives d2_k.  x is the (N, ...) parameter, grad the (N, ...) gradient to accumulate
+ * into (caller zeroes it).  Replaces BatchedObjective.forward + loss.backward() for one factor
+ * (modules.py:84-105, objectives.py:16-45, train.py:213-216). */
+int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_t* pairs,
+                        const gm_targets_t* targets, const gm_loss_t* loss, double scale_sp, void* out_d2,
+                        double* acc, void* grad, gm_stream_t stream);
+
+/* Product-manifold loss over F factor distance vectors (modules.py:84-88 + objectives.py):
+ *   m_k = sum_f sp[f]*d2[f][k];  acc[0] += sum_k l(g_k, m_k);  acc[1+f] += sum_k l'_k * d2[f][k];  out_g[k] = l'_k.
+ * d2_ptrs_host / sp_host are HOST arrays of length F (F <= 8). */
+int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
+                    const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc, void* out_g,
+                    gm_stream_t stream);
+
+/* ---- optimizer ---------------------------------------------------------- */
+enum gm_optim_kind { GM_OPT_RSGD = 0, GM_OPT_RADAM = 1 };
+typedef struct gm_optim {
+  int32_t kind;
+  int32_t exact;      /* 1: manifold.exp, 0: manifold.retr (radam.py:66, rsgd.py:60)              */
+  int32_t has_clip;   /* max_grad_norm is not None                                                 */
+  int32_t step;       /* RAdam: state['step'] BEFORE the update (starts at 1, radam.py:56)          */
+  int32_t has_momentum; /* RSGD: momentum > 0                                                      */
+  int32_t first_step; /* RSGD+momentum: buffer is initialised to the Euclidean grad (rsgd.py:53-54) */
+  int32_t grassmann_retr_qr; /* Grassmann(retr='qr')                                               */
+  int32_t reserved;
+  double lr, beta1, beta2, momentum, dampening, max_grad_norm, eps;
+} gm_optim_t;
+
+/* One fused in-place optimizer update over all N points (optim/radam.py:43-98, optim/rsgd.py:40-82 and the
+ * manifold callees egrad2rgrad / norm / exp|retr / transp of SURVEY 8a A14-A16).
+ *   RAdam: buf1 = exp_avg, buf2 = exp_avg_sq (both full parameter shape).  RSGD: buf1 = momentum buffer or NULL. */
+int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, const void* grad, void* buf1,
+                  void* buf2, int64_t N, gm_stream_t stream);
+
+/* ---- per-point manifold operations (Manifold API, manifolds/base.py:7-81) ----------------------------------- */
+enum gm_point_op {
+  GM_OP_EXP = 0,         /* out = exp_x(u)                      */
+  GM_OP_RETR = 1,        /* out = retr_x(u)                     */
+  GM_OP_LOG = 2,         /* out = log_x(u) with u := y          */
+  GM_OP_PROJU = 3,       /* out = proju(x, u)                   */
+  GM_OP_PROJX = 4,       /* out = projx(x)                      */
+  GM_OP_EGRAD2RGRAD = 5, /* out = egrad2rgrad(x, u)             */
+  GM_OP_INNER = 6,       /* out[k] = <u, v>_x (one scalar)      */
+  GM_OP_NORM2 = 7,       /* out[k] = manifold.norm(x,u)^2 with the reference's clamp (one scalar) */
+  GM_OP_TRANSP = 8,      /* out = transp(x, y := u, v)          */
+  GM_OP_RETR_QR = 9      /* Grassmann qr retraction             */
+};
+int gm_point_op(const gm_manifold_t* man, int32_t op, const void* x, const void* u, const void* v, void* out,
+                int64_t N, gm_stream_t stream);
+
+/* ---- graph-distance targets ---------------------------------------------------------------------------------- */
+
+/* Unweighted multi-source BFS on a CSR graph (both directions of every undirected edge present).
+ * levels[s*N + v] = hop count from sources[s] to v, GM_BFS_UNREACHED if not reachable.
+ * Replaces networkit APSP at data/graph.py:66-87; in-tree spec pyx/impl/precision.cpp:44-63.  Bit-exact.
+ * level_bytes: 1 (uint8, unreached = 255), 2 (uint16, 65535) or 4 (int32, -1).
+ * workspace: at least gm_bfs_workspace_bytes(N, S) bytes of device memory. */
+size_t gm_bfs_workspace_bytes(int32_t N, int32_t S);
+int gm_bfs_multi_source(const int32_t* rowptr, const int32_t* colidx, int32_t N, const int32_t* sources, int32_t S,
+                        int32_t level_bytes, void* levels, void* workspace, size_t workspace_bytes,
+                        gm_stream_t stream);
+
+/* Condensed (scipy.squareform order) float targets from a full S==N level matrix:
+ * out[k] = (float|double) levels[a*N+b] for the k-th a<b (data/graph.py:78-82). */
+int gm_levels_to_condensed(int32_t level_bytes, const void* levels, int32_t N, int32_t dtype, void* out,
+                           gm_stream_t stream);
+
+/* GraphDataset.__init__ (data/dataset.py:9-13): dense[u*N+v] = (h(u,v)^2)/max_sq in `dtype`, from a full level matrix. */
+int gm_levels_to_dense_targets(int32_t level_bytes, const void* levels, int32_t N, double max_sq, int32_t dtype,
+                               void* dense, gm_stream_t stream);
+
+/* Gather per-pair hop counts: out[k] = levels[row_of[k]*N + col[k]] (row_of indexes the S sources). */
+int gm_gather_levels(int32_t level_bytes, const void* levels, int32_t N, const int32_t* src_slot, const int32_t* col,
+                     int64_t P, void* out, gm_stream_t stream);
+
+/* ---- introspection ------------------------------------------------------------------------------------------- */
+const char* gm_version(void);
+/* 1 if (kind, n, p, dtype, flags) has a compiled kernel */
+int gm_supported(const gm_manifold_t* man);
+/* number of kernel launches issued by this library in this process (for bench.py's gpu_launches) */
+int64_t gm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GM_KERNELS_H */

@@ -1,0 +1,229 @@
+// C-ABI entry points of libgm_b200.so (declared in include/gm_kernels.h):
+// argument validation and dispatch to the templated kernel launchers.
+#include <atomic>
+#include <cuda_runtime.h>
+#include "gm_launch.cuh"
+
+namespace gm {
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int check_launch() { return (int)cudaGetLastError(); }
+
+int validate_pairs(const gm_pairs_t* p) {
+  if (!p) return GM_ENULL;
+  if (p->P < 0) return GM_EINVAL;
+  switch (p->mode) {
+    case GM_PAIRS_ELEMENTWISE:
+      return GM_OK;
+    case GM_PAIRS_LIST:
+      if (p->P > 0 && (!p->idx_i || !p->idx_j)) return GM_ENULL;
+      return GM_OK;
+    case GM_PAIRS_TRIU:
+      if (p->B < 0) return GM_EINVAL;
+      if (p->P != p->B * (p->B - 1) / 2) return GM_EINVAL;
+      return GM_OK;
+    default:
+      return GM_EINVAL;
+  }
+}
+
+#define GM_DECL_SPD(n) int spd_launch_##n(const PairArgs& a);
+GM_DECL_SPD(1) GM_DECL_SPD(2) GM_DECL_SPD(3) GM_DECL_SPD(4) GM_DECL_SPD(5)
+GM_DECL_SPD(6) GM_DECL_SPD(7) GM_DECL_SPD(8) GM_DECL_SPD(9) GM_DECL_SPD(10)
+int vec_launch(const PairArgs& a);
+
+static int spd_dispatch(const PairArgs& a) {
+  switch (a.n) {
+    case 1: return spd_launch_1(a);
+    case 2: return spd_launch_2(a);
+    case 3: return spd_launch_3(a);
+    case 4: return spd_launch_4(a);
+    case 5: return spd_launch_5(a);
+    case 6: return spd_launch_6(a);
+    case 7: return spd_launch_7(a);
+    case 8: return spd_launch_8(a);
+    case 9: return spd_launch_9(a);
+    case 10: return spd_launch_10(a);
+    default: return GM_EUNSUPPORTED;
+  }
+}
+
+static int manifold_ok(const gm_manifold_t* m) {
+  if (!m) return GM_ENULL;
+  if (m->dtype != GM_F32 && m->dtype != GM_F64) return GM_EINVAL;
+  switch (m->kind) {
+    case GM_SPD_AI:
+    case GM_SPD_STEIN:
+      if (m->n < 1 || m->n > 10) return GM_EUNSUPPORTED;
+      if ((m->flags & GM_FAST_CHOL) && m->n != 2) return GM_EINVAL;
+      if ((m->flags & GM_FAST_EIG) && m->n != 2 && m->n != 3) return GM_EINVAL;
+      return GM_OK;
+    case GM_LORENTZ:
+      return m->n >= 2 ? GM_OK : GM_EINVAL;
+    case GM_SPHERE:
+    case GM_EUCLIDEAN:
+      return m->n >= 1 ? GM_OK : GM_EINVAL;
+    case GM_GRASSMANN:
+      if (m->n < 1 || m->p < 1 || m->p > m->n) return GM_EINVAL;
+      if (m->p > 5) return GM_EUNSUPPORTED;
+      if ((m->flags & GM_FAST_SVD) && m->p != 2) return GM_EINVAL;
+      return GM_OK;
+    default:
+      return GM_EINVAL;
+  }
+}
+
+static void fill_manifold(PairArgs& a, const gm_manifold_t* m) {
+  a.kind = m->kind; a.dtype = m->dtype; a.n = m->n; a.p = m->p; a.flags = m->flags;
+  a.wmin = m->wmin; a.wmax = m->wmax;
+}
+
+static int pair_dispatch(const PairArgs& a) {
+  if (a.kind == GM_SPD_AI || a.kind == GM_SPD_STEIN) return spd_dispatch(a);
+  return vec_launch(a);
+}
+
+// ---------------------------------------------------------------------------
+// product-manifold loss over F distance vectors
+// ---------------------------------------------------------------------------
+struct FactorPtrs {
+  const void* d2[8];
+  double sp[8];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+product_loss_kernel(int F, FactorPtrs fp, TargetSpec tg, LossCfg lc, long long P, double* __restrict__ acc,
+                    T* __restrict__ out_g) {
+  __shared__ double red[8];
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = k < P;
+  double lv = 0.0;
+  double gd[8];
+  for (int f = 0; f < 8; ++f) gd[f] = 0.0;
+  if (active) {
+    // sum() of a Python list starts from int 0 and adds left to right (modules.py:84-88)
+    T m = (T)0;
+    T d2[8];
+    for (int f = 0; f < F; ++f) {
+      d2[f] = ((const T*)fp.d2[f])[k];
+      T term = (T)fp.sp[f] * d2[f];
+      m = (f == 0) ? term : m + term;
+    }
+    T g = fetch_target<T>(tg, k, 0, 0);
+    T dm;
+    lv = (double)loss_term<T>(lc, g, m, dm);
+    if (out_g) out_g[k] = dm;
+    for (int f = 0; f < F; ++f) gd[f] = (double)dm * (double)d2[f];
+  }
+  block_accumulate(lv, acc, red);
+  for (int f = 0; f < F; ++f) block_accumulate(gd[f], acc + 1 + f, red);
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* gm_version(void) { return "gm_b200 0.1 (sm_100a)"; }
+int64_t gm_launch_count(void) { return (int64_t)g_launches.load(); }
+int gm_supported(const gm_manifold_t* man) { return manifold_ok(man) == GM_OK; }
+
+int gm_pairs_dist2(const gm_manifold_t* man, const void* xa, const void* xb, const gm_pairs_t* pairs,
+                   void* out_d2, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  rc = validate_pairs(pairs);
+  if (rc) return rc;
+  if (pairs->P == 0) return GM_OK;
+  if (!xa || !xb || !out_d2) return GM_ENULL;
+  PairArgs a{};
+  fill_manifold(a, man);
+  a.kmode = K_FWD;
+  a.ps = make_pairs(pairs);
+  a.xa = xa; a.xb = xb; a.out_d2 = out_d2;
+  a.stream = (cudaStream_t)stream;
+  return pair_dispatch(a);
+}
+
+int gm_pairs_grad(const gm_manifold_t* man, const void* xa, const void* xb, const gm_pairs_t* pairs,
+                  const void* gout, double coef, void* ga, void* gb, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  rc = validate_pairs(pairs);
+  if (rc) return rc;
+  if (pairs->P == 0) return GM_OK;
+  if (!xa || !xb || !gout || !ga || !gb) return GM_ENULL;
+  if (pairs->mode == GM_PAIRS_ELEMENTWISE && ga == gb) return GM_EINVAL;
+  PairArgs a{};
+  fill_manifold(a, man);
+  a.kmode = K_BWD;
+  a.ps = make_pairs(pairs);
+  a.xa = xa; a.xb = xb; a.gout = gout; a.coef = coef; a.ga = ga; a.gb = gb;
+  a.stream = (cudaStream_t)stream;
+  return pair_dispatch(a);
+}
+
+int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_t* pairs,
+                        const gm_targets_t* targets, const gm_loss_t* loss, double scale_sp, void* out_d2,
+                        double* acc, void* grad, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  rc = validate_pairs(pairs);
+  if (rc) return rc;
+  if (!targets || !loss) return GM_ENULL;
+  if (pairs->mode == GM_PAIRS_ELEMENTWISE) return GM_EINVAL;
+  if (targets->mode < GM_TGT_VECTOR || targets->mode > GM_TGT_HOPS_U16) return GM_EINVAL;
+  if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
+  if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
+  if (pairs->P == 0) return GM_OK;
+  if (!x || !acc || !grad || !targets->data) return GM_ENULL;
+  PairArgs a{};
+  fill_manifold(a, man);
+  a.kmode = K_FUSED;
+  a.ps = make_pairs(pairs);
+  a.xa = x; a.xb = x; a.ga = grad; a.gb = grad; a.out_d2 = out_d2;
+  a.tg = make_targets(targets);
+  a.lc = make_loss(loss);
+  a.scale_sp = scale_sp;
+  a.acc = acc;
+  a.stream = (cudaStream_t)stream;
+  return pair_dispatch(a);
+}
+
+int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
+                    const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc, void* out_g,
+                    gm_stream_t stream) {
+  if (!d2_ptrs_host || !sp_host || !targets || !loss || !acc) return GM_ENULL;
+  if (F < 1 || F > 8 || P < 0) return GM_EINVAL;
+  if (dtype != GM_F32 && dtype != GM_F64) return GM_EINVAL;
+  if (targets->mode == GM_TGT_DENSE) return GM_EINVAL;
+  if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
+  if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
+  if (P == 0) return GM_OK;
+  FactorPtrs fp{};
+  for (int f = 0; f < F; ++f) {
+    if (!d2_ptrs_host[f]) return GM_ENULL;
+    fp.d2[f] = d2_ptrs_host[f];
+    fp.sp[f] = sp_host[f];
+  }
+  const int threads = 256;
+  long long blocks = (P + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return GM_EINVAL;
+  TargetSpec tg = make_targets(targets);
+  LossCfg lc = make_loss(loss);
+  if (dtype == GM_F32)
+    product_loss_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(F, fp, tg, lc, P, acc,
+                                                                                       (float*)out_g);
+  else
+    product_loss_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(F, fp, tg, lc, P, acc,
+                                                                                        (double*)out_g);
+  note_launch();
+  return check_launch();
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,192 @@
+// Kernel-side plumbing shared by all pair kernels: pair enumeration, target
+// fetch, vectorised row I/O, warp-aggregated gradient accumulation.
+#pragma once
+#include <stdint.h>
+#include "../../include/gm_kernels.h"
+#include "gm_manifolds.cuh"
+
+namespace gm {
+
+// ---- launch accounting (gm_launch_count) -----------------------------------
+void note_launch();
+int check_launch();  // returns cudaGetLastError() as int
+
+// ---- POD copies of the C-ABI structs, passed to kernels by value -------------
+struct PairSpec {
+  int mode, idx64;
+  long long P, B;
+  const void* idx_i;
+  const void* idx_j;
+  const void* nodes;
+};
+struct TargetSpec {
+  int mode;
+  const void* data;
+  long long ld;
+  double max_sq;
+};
+
+inline PairSpec make_pairs(const gm_pairs_t* p) {
+  PairSpec s;
+  s.mode = p->mode; s.idx64 = p->idx64; s.P = p->P; s.B = p->B;
+  s.idx_i = p->idx_i; s.idx_j = p->idx_j; s.nodes = p->nodes;
+  return s;
+}
+inline TargetSpec make_targets(const gm_targets_t* t) {
+  TargetSpec s;
+  s.mode = t->mode; s.data = t->data; s.ld = t->ld; s.max_sq = t->max_sq;
+  return s;
+}
+inline LossCfg make_loss(const gm_loss_t* l) {
+  LossCfg c;
+  c.kind = l->kind; c.inc_l1 = l->inc_l1; c.inc_l2 = l->inc_l2; c.alpha = l->alpha; c.eps = l->eps;
+  return c;
+}
+int validate_pairs(const gm_pairs_t* p);
+
+// ---- one pair-kernel launch request (filled by gm_api.cu) --------------------
+enum { K_FWD = 0, K_BWD = 1, K_FUSED = 2 };
+struct PairArgs {
+  int kind, dtype, n, p;
+  unsigned flags;
+  double wmin, wmax;
+  int kmode;
+  PairSpec ps;
+  const void* xa;
+  const void* xb;
+  const void* gout;
+  double coef;
+  void* ga;
+  void* gb;
+  void* out_d2;
+  TargetSpec tg;
+  LossCfg lc;
+  double scale_sp;
+  double* acc;
+  cudaStream_t stream;
+};
+
+// ---- pair enumeration --------------------------------------------------------
+__device__ __forceinline__ long long load_index(const void* p, long long k, int idx64) {
+  return idx64 ? ((const long long*)p)[k] : (long long)((const int*)p)[k];
+}
+
+// first pair index of row a in torch.triu_indices(B, B, 1) order (base.py:62)
+__device__ __forceinline__ long long triu_row_start(long long a, long long B) {
+  return a * (2 * B - a - 1) / 2;
+}
+
+// k -> (a, b), a < b, row-major upper triangle; exact for B up to 2^31
+__device__ __forceinline__ void triu_decode(long long k, long long B, long long& a, long long& b) {
+  double tb = (double)(2 * B - 1);
+  long long r = (long long)floor((tb - sqrt(tb * tb - 8.0 * (double)k)) * 0.5);
+  if (r < 0) r = 0;
+  if (r > B - 2) r = B - 2;
+  while (r + 1 <= B - 2 && triu_row_start(r + 1, B) <= k) ++r;
+  while (r > 0 && triu_row_start(r, B) > k) --r;
+  a = r;
+  b = k - triu_row_start(r, B) + r + 1;
+}
+
+// rows of xa / xb touched by pair k (also the rows gradients go to)
+__device__ __forceinline__ void decode_pair(const PairSpec& ps, long long k, long long& ra, long long& rb) {
+  if (ps.mode == GM_PAIRS_ELEMENTWISE) {
+    ra = k; rb = k;
+  } else if (ps.mode == GM_PAIRS_LIST) {
+    ra = load_index(ps.idx_i, k, ps.idx64);
+    rb = load_index(ps.idx_j, k, ps.idx64);
+  } else {
+    long long a, b;
+    triu_decode(k, ps.B, a, b);
+    if (ps.nodes) { ra = load_index(ps.nodes, a, ps.idx64); rb = load_index(ps.nodes, b, ps.idx64); }
+    else { ra = a; rb = b; }
+  }
+}
+
+// graph target of pair k (data/dataset.py:9-27)
+template <typename T>
+__device__ __forceinline__ T fetch_target(const TargetSpec& tg, long long k, long long ra, long long rb) {
+  if (tg.mode == GM_TGT_VECTOR) return ((const T*)tg.data)[k];
+  if (tg.mode == GM_TGT_DENSE) return ((const T*)tg.data)[ra * tg.ld + rb];
+  T h = (tg.mode == GM_TGT_HOPS_U8) ? (T)((const unsigned char*)tg.data)[k]
+                                    : (T)((const unsigned short*)tg.data)[k];
+  return (h * h) / (T)tg.max_sq;  // pow(2) then div_(max): dataset.py:11-12
+}
+
+// ---- row I/O ---------------------------------------------------------------
+template <typename T, int E>
+__device__ __forceinline__ void load_row(const T* __restrict__ base, long long row, T (&r)[E]) {
+  const T* p = base + row * E;
+  if constexpr ((E * sizeof(T)) % 16 == 0) {
+    constexpr int V = 16 / sizeof(T);
+    const float4* q = reinterpret_cast<const float4*>(p);
+    GM_UNROLL for (int k = 0; k < E / V; ++k) {
+      float4 t = __ldg(q + k);
+      const T* tt = reinterpret_cast<const T*>(&t);
+      GM_UNROLL for (int j = 0; j < V; ++j) r[k * V + j] = tt[j];
+    }
+  } else if constexpr ((E * sizeof(T)) % 8 == 0) {
+    constexpr int V = 8 / sizeof(T);
+    const float2* q = reinterpret_cast<const float2*>(p);
+    GM_UNROLL for (int k = 0; k < E / V; ++k) {
+      float2 t = __ldg(q + k);
+      const T* tt = reinterpret_cast<const T*>(&t);
+      GM_UNROLL for (int j = 0; j < V; ++j) r[k * V + j] = tt[j];
+    }
+  } else {
+    GM_UNROLL for (int k = 0; k < E; ++k) r[k] = __ldg(p + k);
+  }
+}
+
+template <typename T, int E>
+__device__ __forceinline__ void store_row(T* __restrict__ base, long long row, const T (&r)[E]) {
+  T* p = base + row * E;
+  if constexpr ((E * sizeof(T)) % 16 == 0) {
+    constexpr int V = 16 / sizeof(T);
+    float4* q = reinterpret_cast<float4*>(p);
+    GM_UNROLL for (int k = 0; k < E / V; ++k) {
+      float4 t;
+      T* tt = reinterpret_cast<T*>(&t);
+      GM_UNROLL for (int j = 0; j < V; ++j) tt[j] = r[k * V + j];
+      q[k] = t;
+    }
+  } else {
+    GM_UNROLL for (int k = 0; k < E; ++k) p[k] = r[k];
+  }
+}
+
+// red.global.add of one row; fp32 rows whose byte size is a multiple of 16 use the
+// sm_90+ 128-bit vector reduction (REDG.E.ADD.F32x4), fp64 uses scalar REDG.64.
+template <typename T, int E>
+__device__ __forceinline__ void atomic_add_row(T* __restrict__ base, long long row, const T (&r)[E]) {
+  T* p = base + row * E;
+  if constexpr (sizeof(T) == 4 && E % 4 == 0) {
+    GM_UNROLL for (int k = 0; k < E / 4; ++k)
+      atomicAdd(reinterpret_cast<float4*>(p) + k, make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
+  } else if constexpr (sizeof(T) == 4 && E % 2 == 0) {
+    GM_UNROLL for (int k = 0; k < E / 2; ++k)
+      atomicAdd(reinterpret_cast<float2*>(p) + k, make_float2(r[2 * k], r[2 * k + 1]));
+  } else {
+    GM_UNROLL for (int k = 0; k < E; ++k) atomicAdd(p + k, r[k]);
+  }
+}
+
+// Accumulate one gradient row per lane.  Lanes of a warp that target the same
+// row (the common case for the `a` side of TRIU / source-major pair lists) are
+// first summed with shuffles so that one lane issues the reduction.
+// Must be called by all 32 lanes; `row < 0` marks an idle lane.
+template <typename T, int E>
+__device__ __forceinline__ void warp_accumulate_row(T* __restrict__ base, long long row, T (&r)[E]) {
+  const unsigned full = 0xffffffffu;
+  long long row0 = __shfl_sync(full, row, 0);
+  bool uniform = __all_sync(full, row == row0);
+  if (uniform) {
+    if (row0 < 0) return;
+    GM_UNROLL for (int k = 0; k < E; ++k) r[k] = warp_sum(r[k]);
+    if ((threadIdx.x & 31) == 0) atomic_add_row<T, E>(base, row0, r);
+  } else if (row >= 0) {
+    atomic_add_row<T, E>(base, row, r);
+  }
+}
+
+}  // namespace gm

@@ -1,0 +1,352 @@
+// Register-resident small-matrix math for the pair / optimizer kernels (sm_100a).
+//
+// Everything here is templated on the scalar type T (float | double) and the
+// compile-time matrix size N so that every loop fully unrolls and every matrix
+// element lives in a register.  No shared memory, no local-memory arrays (as
+// long as N is small enough for ptxas to keep the working set in 255 regs).
+//
+// The functions are __host__ __device__ only so that tests/hostcheck can compile
+// the *same* arithmetic for x86 and compare it with the oracle in a container
+// that has no GPU; the shipped library never runs them on the host.
+//
+// Reference semantics being restated (never copied) are cited per function as
+// graphembed/<file>:<line> relative to /root/reference/graphembed/.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <float.h>
+
+#define GM_HD __host__ __device__ __forceinline__
+
+namespace gm {
+
+// ---------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static constexpr float eps = FLT_EPSILON;
+  static constexpr float tiny = FLT_MIN;
+  GM_HD static float sqrt(float x) { return sqrtf(x); }
+  GM_HD static float rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+  }
+  GM_HD static float log(float x) { return logf(x); }
+  GM_HD static float log1p(float x) { return log1pf(x); }
+  GM_HD static float exp(float x) { return expf(x); }
+  GM_HD static float acos(float x) { return acosf(x); }
+  GM_HD static float atan(float x) { return atanf(x); }
+  GM_HD static float cos(float x) { return cosf(x); }
+  GM_HD static float sin(float x) { return sinf(x); }
+  GM_HD static float cosh(float x) { return coshf(x); }
+  GM_HD static float sinh(float x) { return sinhf(x); }
+  GM_HD static float abs(float x) { return fabsf(x); }
+  GM_HD static float fma(float a, float b, float c) { return fmaf(a, b, c); }
+  GM_HD static float max(float a, float b) { return fmaxf(a, b); }
+  GM_HD static float min(float a, float b) { return fminf(a, b); }
+  GM_HD static float copysign(float a, float b) { return copysignf(a, b); }
+};
+template <> struct Num<double> {
+  static constexpr double eps = DBL_EPSILON;
+  static constexpr double tiny = DBL_MIN;
+  GM_HD static double sqrt(double x) { return ::sqrt(x); }
+  GM_HD static double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  GM_HD static double log(double x) { return ::log(x); }
+  GM_HD static double log1p(double x) { return ::log1p(x); }
+  GM_HD static double exp(double x) { return ::exp(x); }
+  GM_HD static double acos(double x) { return ::acos(x); }
+  GM_HD static double atan(double x) { return ::atan(x); }
+  GM_HD static double cos(double x) { return ::cos(x); }
+  GM_HD static double sin(double x) { return ::sin(x); }
+  GM_HD static double cosh(double x) { return ::cosh(x); }
+  GM_HD static double sinh(double x) { return ::sinh(x); }
+  GM_HD static double abs(double x) { return fabs(x); }
+  GM_HD static double fma(double a, double b, double c) { return ::fma(a, b, c); }
+  GM_HD static double max(double a, double b) { return fmax(a, b); }
+  GM_HD static double min(double a, double b) { return fmin(a, b); }
+  GM_HD static double copysign(double a, double b) { return ::copysign(a, b); }
+};
+
+// torch.clamp semantics on a *value* (NaN propagates like torch: clamp(NaN)=NaN)
+template <typename T>
+GM_HD T clampv(T x, T lo, T hi) {
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+template <typename T>
+GM_HD T clamp_min(T x, T lo) { return x < lo ? lo : x; }
+template <typename T>
+GM_HD T clamp_max(T x, T hi) { return x > hi ? hi : x; }
+// torch.sign / abs-backward convention: sign(0) == 0
+template <typename T>
+GM_HD T sgn0(T x) { return (T)((x > (T)0) - (x < (T)0)); }
+
+// ---------------------------------------------------------------------------
+// N x N matrices held as flat register arrays (row-major, index i*N+j)
+// ---------------------------------------------------------------------------
+#define GM_UNROLL _Pragma("unroll")
+
+// Lower Cholesky factor of a symmetric matrix (reads the lower triangle of x).
+// Non-PD input yields NaN (sqrt of a negative pivot), mirroring the reference's
+// "NaNs are not detected" behaviour (torch.cholesky would raise on CPU;
+// graphembed/linalg/torch_batch.py:43-67).
+template <typename T, int N>
+GM_HD void chol_lower(const T (&x)[N * N], T (&l)[N * N]) {
+  GM_UNROLL for (int j = 0; j < N; ++j) {
+    T s = x[j * N + j];
+    GM_UNROLL for (int k = 0; k < j; ++k) s -= l[j * N + k] * l[j * N + k];
+    T d = Num<T>::sqrt(s);
+    l[j * N + j] = d;
+    T inv = (T)1 / d;
+    GM_UNROLL for (int i = j + 1; i < N; ++i) {
+      T t = x[i * N + j];
+      GM_UNROLL for (int k = 0; k < j; ++k) t -= l[i * N + k] * l[j * N + k];
+      l[i * N + j] = t * inv;
+    }
+    GM_UNROLL for (int i = 0; i < j; ++i) l[i * N + j] = (T)0;
+  }
+}
+
+// a = l^{-1} for lower-triangular l (forward substitution against I;
+// graphembed/manifolds/spd.py:55-61).
+template <typename T, int N>
+GM_HD void tri_inv_lower(const T (&l)[N * N], T (&a)[N * N]) {
+  GM_UNROLL for (int j = 0; j < N; ++j) {
+    GM_UNROLL for (int i = 0; i < j; ++i) a[i * N + j] = (T)0;
+    a[j * N + j] = (T)1 / l[j * N + j];
+    GM_UNROLL for (int i = j + 1; i < N; ++i) {
+      T s = (T)0;
+      GM_UNROLL for (int k = j; k < i; ++k) s += l[i * N + k] * a[k * N + j];
+      a[i * N + j] = -s / l[i * N + i];
+    }
+  }
+}
+
+// m = a y a^T for lower-triangular a and symmetric y; m is produced exactly
+// symmetric (upper computed, mirrored).  graphembed/linalg/torch_batch.py:30-34.
+template <typename T, int N>
+GM_HD void congr_lower(const T (&a)[N * N], const T (&y)[N * N], T (&m)[N * N]) {
+  T t[N * N];
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = 0; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = 0; k <= i; ++k) s += a[i * N + k] * y[k * N + j];
+      t[i * N + j] = s;
+    }
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = i; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = 0; k <= j; ++k) s += t[i * N + k] * a[j * N + k];
+      m[i * N + j] = s;
+      m[j * N + i] = s;
+    }
+}
+
+// m = a y a^T for general (full) a and symmetric y.
+template <typename T, int N>
+GM_HD void congr_full(const T (&a)[N * N], const T (&y)[N * N], T (&m)[N * N]) {
+  T t[N * N];
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = 0; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = 0; k < N; ++k) s += a[i * N + k] * y[k * N + j];
+      t[i * N + j] = s;
+    }
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = i; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = 0; k < N; ++k) s += t[i * N + k] * a[j * N + k];
+      m[i * N + j] = s;
+      m[j * N + i] = s;
+    }
+}
+
+// w = a^T v for lower-triangular a.
+template <typename T, int N>
+GM_HD void lowerT_mul(const T (&a)[N * N], const T (&v)[N * N], T (&w)[N * N]) {
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = 0; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = i; k < N; ++k) s += a[k * N + i] * v[k * N + j];
+      w[i * N + j] = s;
+    }
+}
+
+// w = l v for lower-triangular l.
+template <typename T, int N>
+GM_HD void lower_mul(const T (&l)[N * N], const T (&v)[N * N], T (&w)[N * N]) {
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = 0; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = 0; k <= i; ++k) s += l[i * N + k] * v[k * N + j];
+      w[i * N + j] = s;
+    }
+}
+
+// g = w diag(c) w^T (symmetric; upper computed, mirrored).
+// graphembed/linalg/torch_batch.py:84-91,138-142 (mvmt / hgie).
+template <typename T, int N>
+GM_HD void wdwt(const T (&w)[N * N], const T (&c)[N], T (&g)[N * N]) {
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = i; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = 0; k < N; ++k) s += (w[i * N + k] * c[k]) * w[j * N + k];
+      g[i * N + j] = s;
+      g[j * N + i] = s;
+    }
+}
+
+template <typename T, int N>
+GM_HD void matmul(const T (&a)[N * N], const T (&b)[N * N], T (&c)[N * N]) {
+  GM_UNROLL for (int i = 0; i < N; ++i)
+    GM_UNROLL for (int j = 0; j < N; ++j) {
+      T s = (T)0;
+      GM_UNROLL for (int k = 0; k < N; ++k) s += a[i * N + k] * b[k * N + j];
+      c[i * N + j] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Cyclic Jacobi eigensolver for a symmetric N x N matrix held in registers.
+// On exit w[k] are the eigenvalues and the columns of v the eigenvectors
+// (a = v diag(w) v^T).  Replaces torch.symeig(eigenvectors=True), i.e. LAPACK
+// syevd, at graphembed/linalg/torch_batch.py:127-135 / manifolds/spd.py:63-64.
+// Order and sign of eigenpairs are unspecified; every caller uses only
+// permutation/sign-invariant combinations (sum f(w), v f(w) v^T).
+// ---------------------------------------------------------------------------
+template <typename T> struct JacobiCfg;
+template <> struct JacobiCfg<float> { static constexpr int max_sweeps = 10; };
+template <> struct JacobiCfg<double> { static constexpr int max_sweeps = 16; };
+
+template <typename T, int N, bool WANT_V = true>
+GM_HD void jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N]) {
+  if (WANT_V) {
+    GM_UNROLL for (int i = 0; i < N; ++i)
+      GM_UNROLL for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? (T)1 : (T)0;
+  }
+  if (N == 1) { w[0] = a[0]; return; }
+  for (int sweep = 0; sweep < JacobiCfg<T>::max_sweeps; ++sweep) {
+    T off = (T)0, dia = (T)0;
+    GM_UNROLL for (int i = 0; i < N; ++i) {
+      dia += a[i * N + i] * a[i * N + i];
+      GM_UNROLL for (int j = i + 1; j < N; ++j) off += a[i * N + j] * a[i * N + j];
+    }
+    // converged when the off-diagonal mass is below rounding level of the diagonal
+    if (off <= (Num<T>::eps * Num<T>::eps * (T)0.0625) * dia || off < Num<T>::tiny) break;
+    GM_UNROLL for (int p = 0; p < N - 1; ++p) {
+      GM_UNROLL for (int q = p + 1; q < N; ++q) {
+        T apq = a[p * N + q];
+        T d = a[q * N + q] - a[p * N + p];
+        // t = tan(theta), smaller root of t^2 + 2 t cot(2 theta) - 1 = 0, branch-free:
+        // t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)); apq == 0 -> t == 0.
+        T two_apq = apq + apq;
+        T den = Num<T>::abs(d) + Num<T>::sqrt(d * d + two_apq * two_apq);
+        T t = (den > (T)0) ? (d >= (T)0 ? two_apq : -two_apq) / den : (T)0;
+        T c = Num<T>::rsqrt(t * t + (T)1);
+        T s = t * c;
+        a[p * N + p] -= t * apq;
+        a[q * N + q] += t * apq;
+        a[p * N + q] = (T)0;
+        a[q * N + p] = (T)0;
+        GM_UNROLL for (int r = 0; r < N; ++r) {
+          if (r != p && r != q) {
+            T arp = a[r * N + p], arq = a[r * N + q];
+            T nrp = c * arp - s * arq;
+            T nrq = s * arp + c * arq;
+            a[r * N + p] = nrp; a[p * N + r] = nrp;
+            a[r * N + q] = nrq; a[q * N + r] = nrq;
+          }
+        }
+        if (WANT_V) {
+          GM_UNROLL for (int r = 0; r < N; ++r) {
+            T vrp = v[r * N + p], vrq = v[r * N + q];
+            v[r * N + p] = c * vrp - s * vrq;
+            v[r * N + q] = s * vrp + c * vrq;
+          }
+        }
+      }
+    }
+  }
+  GM_UNROLL for (int i = 0; i < N; ++i) w[i] = a[i * N + i];
+}
+
+// ---------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi SVD of an R x C matrix (R >= C) held in
+// registers: on exit the columns of `a` are u_k * s_k, `v` (C x C) holds the right
+// singular vectors and s[k] >= 0 the singular values (unsorted).  Replaces
+// torch.svd (LAPACK gesdd) at graphembed/linalg/torch_batch.py:109-112.
+// ---------------------------------------------------------------------------
+template <typename T, int R, int C>
+GM_HD void jacobi_svd(T (&a)[R * C], T (&v)[C * C], T (&s)[C]) {
+  GM_UNROLL for (int i = 0; i < C; ++i)
+    GM_UNROLL for (int j = 0; j < C; ++j) v[i * C + j] = (i == j) ? (T)1 : (T)0;
+  for (int sweep = 0; sweep < JacobiCfg<T>::max_sweeps + 4; ++sweep) {
+    bool rotated = false;
+    GM_UNROLL for (int p = 0; p < C - 1; ++p) {
+      GM_UNROLL for (int q = p + 1; q < C; ++q) {
+        T alpha = (T)0, beta = (T)0, gamma = (T)0;
+        GM_UNROLL for (int r = 0; r < R; ++r) {
+          alpha += a[r * C + p] * a[r * C + p];
+          beta += a[r * C + q] * a[r * C + q];
+          gamma += a[r * C + p] * a[r * C + q];
+        }
+        if (Num<T>::abs(gamma) > (Num<T>::eps * (T)0.25) * Num<T>::sqrt(alpha * beta) &&
+            Num<T>::abs(gamma) > Num<T>::tiny) {
+          rotated = true;
+          T d = beta - alpha;
+          T two_g = gamma + gamma;
+          T den = Num<T>::abs(d) + Num<T>::sqrt(d * d + two_g * two_g);
+          T t = (d >= (T)0 ? two_g : -two_g) / den;
+          T c = Num<T>::rsqrt(t * t + (T)1);
+          T sn = t * c;
+          GM_UNROLL for (int r = 0; r < R; ++r) {
+            T x = a[r * C + p], y = a[r * C + q];
+            a[r * C + p] = c * x - sn * y;
+            a[r * C + q] = sn * x + c * y;
+          }
+          GM_UNROLL for (int r = 0; r < C; ++r) {
+            T x = v[r * C + p], y = v[r * C + q];
+            v[r * C + p] = c * x - sn * y;
+            v[r * C + q] = sn * x + c * y;
+          }
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  GM_UNROLL for (int k = 0; k < C; ++k) {
+    T n2 = (T)0;
+    GM_UNROLL for (int r = 0; r < R; ++r) n2 += a[r * C + k] * a[r * C + k];
+    s[k] = Num<T>::sqrt(n2);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// warp / block reductions
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+  GM_UNROLL for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum `v` over the block and add it to *dst (one atomic per block).  `red` must
+// hold blockDim.x/32 doubles of shared memory.
+__device__ __forceinline__ void block_accumulate(double v, double* dst, double* red) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    double s = lane < nw ? red[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0 && dst != nullptr) atomicAdd(dst, s);
+  }
+  __syncthreads();
+}
+
+}  // namespace gm

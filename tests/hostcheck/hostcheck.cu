@@ -1,0 +1,128 @@
+// DEV/TEST HARNESS -- not part of the product.  Compiles the *device* math of
+// matrix-manifolds_b200/csrc/gm_manifolds.cuh for the host (all of it is
+// __host__ __device__) so that the per-pair arithmetic the CUDA kernels execute
+// can be compared with the oracle in a container without a GPU
+// (tests/test_hostcheck_math.py, `-m "not gpu"`).  The shipped library
+// (libgm_b200.so) never links or calls this file.
+#include "../../matrix-manifolds_b200/csrc/gm_manifolds.cuh"
+#include "../../include/gm_kernels.h"
+
+using namespace gm;
+
+template <class Op, typename T>
+static void run_rows(const Op& op, const T* x, const T* y, long P, T* d2, T* gx, T* gy) {
+  constexpr int E = Op::E;
+  for (long k = 0; k < P; ++k) {
+    T xr[E], yr[E], gxr[E], gyr[E];
+    for (int e = 0; e < E; ++e) { xr[e] = x[k * E + e]; yr[e] = y[k * E + e]; }
+    if (gx) {
+      d2[k] = op.dist2_grad(xr, yr, gxr, gyr);
+      for (int e = 0; e < E; ++e) { gx[k * E + e] = gxr[e]; gy[k * E + e] = gyr[e]; }
+    } else {
+      d2[k] = op.dist2(xr, yr);
+    }
+  }
+}
+
+template <typename T, int N>
+static int spd_n(int kind, unsigned flags, double wmin, double wmax, const T* x, const T* y, long P, T* d2, T* gx,
+                 T* gy) {
+  const bool fe = flags & GM_FAST_EIG, fc = flags & GM_FAST_CHOL;
+  if (kind == GM_SPD_AI) {
+    if constexpr (N == 2) {
+      if (fe && fc) { SpdAI<T, 2, true, true> op{(T)wmin, (T)wmax}; run_rows(op, x, y, P, d2, gx, gy); return 0; }
+      if (fe) { SpdAI<T, 2, true, false> op{(T)wmin, (T)wmax}; run_rows(op, x, y, P, d2, gx, gy); return 0; }
+      if (fc) { SpdAI<T, 2, false, true> op{(T)wmin, (T)wmax}; run_rows(op, x, y, P, d2, gx, gy); return 0; }
+    }
+    if constexpr (N == 3) {
+      if (fe) { SpdAI<T, 3, true, false> op{(T)wmin, (T)wmax}; run_rows(op, x, y, P, d2, gx, gy); return 0; }
+    }
+    SpdAI<T, N, false, false> op{(T)wmin, (T)wmax};
+    run_rows(op, x, y, P, d2, gx, gy);
+    return 0;
+  }
+  if constexpr (N == 2) {
+    if (fc) { SpdStein<T, 2, true> op{(T)wmin, (T)wmax}; run_rows(op, x, y, P, d2, gx, gy); return 0; }
+  }
+  SpdStein<T, N, false> op{(T)wmin, (T)wmax};
+  run_rows(op, x, y, P, d2, gx, gy);
+  return 0;
+}
+
+template <typename T>
+static int spd_t(int kind, int n, unsigned flags, double wmin, double wmax, const void* x, const void* y, long P,
+                 void* d2, void* gx, void* gy) {
+#define CASE(N) case N: return spd_n<T, N>(kind, flags, wmin, wmax, (const T*)x, (const T*)y, P, (T*)d2, (T*)gx, (T*)gy);
+  switch (n) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) default: return -2; }
+#undef CASE
+}
+
+template <typename T, int KIND>
+static void vec_rows(int n, const T* x, const T* y, long P, T* d2, T* gx, T* gy) {
+  VecMan<T, KIND> op{(T)1e-8, (T)(1.0 - 1e-16)};
+  for (long k = 0; k < P; ++k) {
+    T c;
+    d2[k] = op.value(x + k * n, y + k * n, n, c);
+    if (gx)
+      for (int e = 0; e < n; ++e) op.grad_elem(e, x[k * n + e], y[k * n + e], c, gx[k * n + e], gy[k * n + e]);
+  }
+}
+
+template <typename T, int P_, bool FAST>
+static void grass_rows(int n, const T* x, const T* y, long P, T* d2, T* gx, T* gy) {
+  GrassmannCore<T, P_, FAST> op{(T)(1.0 - 1e-16)};
+  for (long k = 0; k < P; ++k) {
+    const T* px = x + k * n * P_;
+    const T* py = y + k * n * P_;
+    T a[P_ * P_], ga[P_ * P_];
+    for (int i = 0; i < P_ * P_; ++i) a[i] = 0;
+    for (int r = 0; r < n; ++r)
+      for (int i = 0; i < P_; ++i)
+        for (int j = 0; j < P_; ++j) a[i * P_ + j] += px[r * P_ + i] * py[r * P_ + j];
+    d2[k] = op.run(a, gx != nullptr, ga);
+    if (gx)
+      for (int r = 0; r < n; ++r)
+        for (int i = 0; i < P_; ++i) {
+          T sx = 0, sy = 0;
+          for (int j = 0; j < P_; ++j) { sx += py[r * P_ + j] * ga[i * P_ + j]; sy += px[r * P_ + j] * ga[j * P_ + i]; }
+          gx[(k * n + r) * P_ + i] = sx;
+          gy[(k * n + r) * P_ + i] = sy;
+        }
+  }
+}
+
+template <typename T>
+static int any_t(int kind, int n, int p, unsigned flags, double wmin, double wmax, const void* x, const void* y,
+                 long P, void* d2, void* gx, void* gy) {
+  const T* X = (const T*)x; const T* Y = (const T*)y;
+  T* D = (T*)d2; T* GX = (T*)gx; T* GY = (T*)gy;
+  switch (kind) {
+    case GM_SPD_AI: case GM_SPD_STEIN: return spd_t<T>(kind, n, flags, wmin, wmax, x, y, P, d2, gx, gy);
+    case GM_LORENTZ: vec_rows<T, VEC_LORENTZ>(n, X, Y, P, D, GX, GY); return 0;
+    case GM_SPHERE: vec_rows<T, VEC_SPHERE>(n, X, Y, P, D, GX, GY); return 0;
+    case GM_EUCLIDEAN: vec_rows<T, VEC_EUCLIDEAN>(n, X, Y, P, D, GX, GY); return 0;
+    case GM_GRASSMANN:
+      if (p == 2 && (flags & GM_FAST_SVD)) { grass_rows<T, 2, true>(n, X, Y, P, D, GX, GY); return 0; }
+      if (p == 1) { grass_rows<T, 1, false>(n, X, Y, P, D, GX, GY); return 0; }
+      if (p == 2) { grass_rows<T, 2, false>(n, X, Y, P, D, GX, GY); return 0; }
+      if (p == 3) { grass_rows<T, 3, false>(n, X, Y, P, D, GX, GY); return 0; }
+      if (p == 4) { grass_rows<T, 4, false>(n, X, Y, P, D, GX, GY); return 0; }
+      return -2;
+  }
+  return -1;
+}
+
+extern "C" int hc_pairs(int kind, int dtype, int n, int p, unsigned flags, double wmin, double wmax, const void* x,
+                        const void* y, long P, void* d2, void* gx, void* gy) {
+  if (dtype == GM_F32) return any_t<float>(kind, n, p, flags, wmin, wmax, x, y, P, d2, gx, gy);
+  return any_t<double>(kind, n, p, flags, wmin, wmax, x, y, P, d2, gx, gy);
+}
+
+extern "C" void hc_loss(int dtype, int kind, int inc_l1, int inc_l2, double alpha, double eps, const void* g,
+                        const void* m, long P, void* val, void* dm) {
+  LossCfg c{kind, inc_l1, inc_l2, alpha, eps};
+  for (long k = 0; k < P; ++k) {
+    if (dtype == GM_F32) ((float*)val)[k] = loss_term<float>(c, ((const float*)g)[k], ((const float*)m)[k], ((float*)dm)[k]);
+    else ((double*)val)[k] = loss_term<double>(c, ((const double*)g)[k], ((const double*)m)[k], ((double*)dm)[k]);
+  }
+}
