@@ -2,7 +2,7 @@
 // argument validation and dispatch to the templated kernel launchers.
 #include <atomic>
 #include <cuda_runtime.h>
-#include "gm_launch.cuh"
+#include "gm_point_kernels.cuh"
 
 namespace gm {
 
@@ -28,24 +28,55 @@ int validate_pairs(const gm_pairs_t* p) {
   }
 }
 
-#define GM_DECL_SPD(n) int spd_launch_##n(const PairArgs& a);
-GM_DECL_SPD(1) GM_DECL_SPD(2) GM_DECL_SPD(3) GM_DECL_SPD(4) GM_DECL_SPD(5)
-GM_DECL_SPD(6) GM_DECL_SPD(7) GM_DECL_SPD(8) GM_DECL_SPD(9) GM_DECL_SPD(10)
+// the set of compiled SPD sizes comes from the Makefile (-DGM_SPD_LIST="X(1) X(2) ...")
+#ifndef GM_SPD_LIST
+#define GM_SPD_LIST X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
+#endif
+#define X(n) int spd_launch_##n(const PairArgs& a); int spd_point_##n(const PointArgs& a);
+GM_SPD_LIST
+#undef X
 int vec_launch(const PairArgs& a);
+int vec_point_0(const PointArgs& a);
+int vec_point_1(const PointArgs& a);
+int vec_point_2(const PointArgs& a);
+int vec_point_3(const PointArgs& a);
+static int vec_point(const PointArgs& a) {
+  switch (a.kind) {
+    case GM_LORENTZ: return vec_point_0(a);
+    case GM_SPHERE: return vec_point_1(a);
+    case GM_EUCLIDEAN: return vec_point_2(a);
+    case GM_GRASSMANN: return vec_point_3(a);
+    default: return GM_EINVAL;
+  }
+}
+
+static int point_dispatch(const PointArgs& a) {
+  if (a.kind == GM_SPD_AI || a.kind == GM_SPD_STEIN) {
+    switch (a.n) {
+#define X(n) case n: return spd_point_##n(a);
+      GM_SPD_LIST
+#undef X
+      default: return GM_EUNSUPPORTED;
+    }
+  }
+  return vec_point(a);
+}
 
 static int spd_dispatch(const PairArgs& a) {
   switch (a.n) {
-    case 1: return spd_launch_1(a);
-    case 2: return spd_launch_2(a);
-    case 3: return spd_launch_3(a);
-    case 4: return spd_launch_4(a);
-    case 5: return spd_launch_5(a);
-    case 6: return spd_launch_6(a);
-    case 7: return spd_launch_7(a);
-    case 8: return spd_launch_8(a);
-    case 9: return spd_launch_9(a);
-    case 10: return spd_launch_10(a);
+#define X(n) case n: return spd_launch_##n(a);
+    GM_SPD_LIST
+#undef X
     default: return GM_EUNSUPPORTED;
+  }
+}
+
+static bool spd_size_compiled(int n) {
+  switch (n) {
+#define X(n) case n: return true;
+    GM_SPD_LIST
+#undef X
+    default: return false;
   }
 }
 
@@ -55,7 +86,7 @@ static int manifold_ok(const gm_manifold_t* m) {
   switch (m->kind) {
     case GM_SPD_AI:
     case GM_SPD_STEIN:
-      if (m->n < 1 || m->n > 10) return GM_EUNSUPPORTED;
+      if (!spd_size_compiled(m->n)) return GM_EUNSUPPORTED;
       if ((m->flags & GM_FAST_CHOL) && m->n != 2) return GM_EINVAL;
       if ((m->flags & GM_FAST_EIG) && m->n != 2 && m->n != 3) return GM_EINVAL;
       return GM_OK;
@@ -223,6 +254,55 @@ int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, c
                                                                                         (double*)out_g);
   note_launch();
   return check_launch();
+}
+
+int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, const void* grad, void* buf1,
+                  void* buf2, int64_t N, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  if (!opt) return GM_ENULL;
+  if (N < 0) return GM_EINVAL;
+  if (opt->kind != GM_OPT_RSGD && opt->kind != GM_OPT_RADAM) return GM_EINVAL;
+  if (N == 0) return GM_OK;
+  if (!x || !grad) return GM_ENULL;
+  if (opt->kind == GM_OPT_RADAM && (!buf1 || !buf2 || opt->step < 1)) return GM_EINVAL;
+  if (opt->kind == GM_OPT_RSGD && opt->has_momentum && !buf1) return GM_ENULL;
+  PointArgs a{};
+  a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
+  a.wmin = man->wmin; a.wmax = man->wmax;
+  a.op = -1;
+  a.oc.kind = opt->kind; a.oc.exact = opt->exact; a.oc.has_clip = opt->has_clip; a.oc.step = opt->step;
+  a.oc.has_momentum = opt->has_momentum; a.oc.first_step = opt->first_step;
+  a.oc.lr = opt->lr; a.oc.beta1 = opt->beta1; a.oc.beta2 = opt->beta2; a.oc.momentum = opt->momentum;
+  a.oc.dampening = opt->dampening; a.oc.max_grad_norm = opt->max_grad_norm; a.oc.eps = opt->eps;
+  a.grassmann_retr_qr = opt->grassmann_retr_qr;
+  a.x = x; a.u = grad; a.buf1 = buf1; a.buf2 = (opt->kind == GM_OPT_RADAM) ? buf2 : nullptr;
+  if (opt->kind == GM_OPT_RSGD && !opt->has_momentum) a.buf1 = nullptr;
+  a.N = N;
+  a.stream = (cudaStream_t)stream;
+  return point_dispatch(a);
+}
+
+int gm_point_op(const gm_manifold_t* man, int32_t op, const void* x, const void* u, const void* v, void* out,
+                int64_t N, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  if (N < 0 || op < GM_OP_EXP || op > GM_OP_RETR_QR) return GM_EINVAL;
+  if (N == 0) return GM_OK;
+  if (!x || !out) return GM_ENULL;
+  const bool needs_u = op != GM_OP_PROJX;
+  const bool needs_v = op == GM_OP_INNER || op == GM_OP_TRANSP;
+  if ((needs_u && !u) || (needs_v && !v)) return GM_ENULL;
+  PointArgs a{};
+  a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
+  a.wmin = man->wmin; a.wmax = man->wmax;
+  a.op = op;
+  a.grassmann_retr_qr = 0;
+  if (op == GM_OP_RETR_QR) { a.op = GM_OP_RETR; a.grassmann_retr_qr = 1; }
+  a.x = const_cast<void*>(x); a.u = u; a.v = v; a.out = out;
+  a.N = N;
+  a.stream = (cudaStream_t)stream;
+  return point_dispatch(a);
 }
 
 #pragma GCC visibility pop

@@ -126,3 +126,111 @@ extern "C" void hc_loss(int dtype, int kind, int inc_l1, int inc_l2, double alph
     else ((double*)val)[k] = loss_term<double>(c, ((const double*)g)[k], ((const double*)m)[k], ((double*)dm)[k]);
   }
 }
+
+// ---------------------------------------------------------------------------
+// per-point ops and optimizer update (gm_pointops.cuh), same dispatch as
+// gm_point_spd.cu / gm_point_vec.cu but looping on the host
+// ---------------------------------------------------------------------------
+#include "../../matrix-manifolds_b200/csrc/gm_pointops.cuh"
+
+struct HcPoint {
+  int op;  // gm_point_op or -1 (optimizer)
+  OptimCfg oc;
+  void* x; const void* u; const void* v; void* out; void* b1; void* b2;
+  long N;
+};
+
+template <class Man, typename T>
+static int pt_rows(const Man& man, const HcPoint& a) {
+  constexpr int CAP = Man::CAP;
+  const int cnt = man.count();
+  for (long k = 0; k < a.N; ++k) {
+    T xs[CAP], us[CAP], vs[CAP], os[CAP], b1[CAP], b2[CAP];
+    for (int e = 0; e < cnt; ++e) {
+      xs[e] = ((T*)a.x)[k * cnt + e];
+      us[e] = a.u ? ((const T*)a.u)[k * cnt + e] : (T)0;
+      vs[e] = a.v ? ((const T*)a.v)[k * cnt + e] : (T)0;
+      b1[e] = a.b1 ? ((T*)a.b1)[k * cnt + e] : (T)0;
+      b2[e] = a.b2 ? ((T*)a.b2)[k * cnt + e] : (T)0;
+    }
+    if (a.op < 0) {
+      optim_update<Man, T>(man, a.oc, xs, us, b1, b2);
+      for (int e = 0; e < cnt; ++e) {
+        ((T*)a.x)[k * cnt + e] = xs[e];
+        if (a.b1) ((T*)a.b1)[k * cnt + e] = b1[e];
+        if (a.b2) ((T*)a.b2)[k * cnt + e] = b2[e];
+      }
+      continue;
+    }
+    bool scalar = false; T sval = 0;
+    switch (a.op) {
+      case GM_OP_EXP: man.exp(xs, us, os); break;
+      case GM_OP_RETR: man.retr(xs, us, os); break;
+      case GM_OP_LOG: man.log(xs, us, os); break;
+      case GM_OP_PROJU: man.proju(xs, us, os); break;
+      case GM_OP_PROJX: man.projx(xs, os); break;
+      case GM_OP_EGRAD2RGRAD: man.egrad2rgrad(xs, us, os); break;
+      case GM_OP_INNER: scalar = true; sval = man.inner(xs, us, vs); break;
+      case GM_OP_NORM2: scalar = true; sval = man.norm2(xs, us); break;
+      case GM_OP_TRANSP: man.transp(xs, us, vs, os); break;
+      default: return -1;
+    }
+    if (scalar) ((T*)a.out)[k] = sval;
+    else for (int e = 0; e < cnt; ++e) ((T*)a.out)[k * cnt + e] = os[e];
+  }
+  return 0;
+}
+
+template <typename T, int N>
+static int pt_spd(unsigned flags, double wmin, double wmax, const HcPoint& a) {
+  if constexpr (N == 2) {
+    if (flags & GM_FAST_CHOL) { SpdPt<T, 2, true> m{(T)wmin, (T)wmax}; return pt_rows<decltype(m), T>(m, a); }
+  }
+  SpdPt<T, N, false> m{(T)wmin, (T)wmax};
+  return pt_rows<decltype(m), T>(m, a);
+}
+
+template <typename T>
+static int pt_any(int kind, int n, int p, unsigned flags, double wmin, double wmax, int retr_qr, const HcPoint& a) {
+  const T eps = (T)1e-8;
+  switch (kind) {
+    case GM_SPD_AI: case GM_SPD_STEIN:
+      switch (n) {
+        case 1: return pt_spd<T, 1>(flags, wmin, wmax, a);
+        case 2: return pt_spd<T, 2>(flags, wmin, wmax, a);
+        case 3: return pt_spd<T, 3>(flags, wmin, wmax, a);
+        case 4: return pt_spd<T, 4>(flags, wmin, wmax, a);
+        case 5: return pt_spd<T, 5>(flags, wmin, wmax, a);
+        case 6: return pt_spd<T, 6>(flags, wmin, wmax, a);
+        default: return -2;
+      }
+    case GM_LORENTZ: { LorentzPt<T, 64> m{n, eps}; return pt_rows<decltype(m), T>(m, a); }
+    case GM_SPHERE: { SpherePt<T, 64> m{n, eps}; return pt_rows<decltype(m), T>(m, a); }
+    case GM_EUCLIDEAN: { EuclideanPt<T, 64> m{n, eps}; return pt_rows<decltype(m), T>(m, a); }
+    case GM_GRASSMANN:
+      switch (p) {
+        case 1: { GrassmannPt<T, 1, 16> m{n, eps, retr_qr}; return pt_rows<decltype(m), T>(m, a); }
+        case 2: { GrassmannPt<T, 2, 16> m{n, eps, retr_qr}; return pt_rows<decltype(m), T>(m, a); }
+        case 3: { GrassmannPt<T, 3, 16> m{n, eps, retr_qr}; return pt_rows<decltype(m), T>(m, a); }
+        case 4: { GrassmannPt<T, 4, 16> m{n, eps, retr_qr}; return pt_rows<decltype(m), T>(m, a); }
+        default: return -2;
+      }
+  }
+  return -1;
+}
+
+extern "C" int hc_point(int kind, int dtype, int n, int p, unsigned flags, double wmin, double wmax, int retr_qr,
+                        int op, const gm_optim_t* opt, void* x, const void* u, const void* v, void* out, void* b1,
+                        void* b2, long N) {
+  HcPoint a{};
+  a.op = op; a.x = x; a.u = u; a.v = v; a.out = out; a.b1 = b1; a.b2 = b2; a.N = N;
+  if (op < 0) {
+    a.oc.kind = opt->kind; a.oc.exact = opt->exact; a.oc.has_clip = opt->has_clip; a.oc.step = opt->step;
+    a.oc.has_momentum = opt->has_momentum; a.oc.first_step = opt->first_step;
+    a.oc.lr = opt->lr; a.oc.beta1 = opt->beta1; a.oc.beta2 = opt->beta2; a.oc.momentum = opt->momentum;
+    a.oc.dampening = opt->dampening; a.oc.max_grad_norm = opt->max_grad_norm; a.oc.eps = opt->eps;
+    retr_qr = opt->grassmann_retr_qr;
+  }
+  if (dtype == GM_F32) return pt_any<float>(kind, n, p, flags, wmin, wmax, retr_qr, a);
+  return pt_any<double>(kind, n, p, flags, wmin, wmax, retr_qr, a);
+}
