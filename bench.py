@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on its headline config, measured on B200.
+
+metric   : SPD pair dist+grad evals/sec (BASELINE.json), unit "pairs/s"
+workload : BASELINE config 5 -- synthetic 2M-node scale-free graph, SPD 4x4 affine-invariant embedding (fp32),
+           2^24 sampled pairs per step built as 1024 BFS sources x 16384 random targets, hop-count targets from the
+           multi-source BFS kernel, distortion loss (QuotientLoss, both terms), RiemannianAdam(lr .01, clip 100,
+           exact) -- graphembed/experiments/run_grid.py:24-36,108-138 hyper-parameters.
+step     : zero grad -> ONE fused pair kernel (gather + distance + loss + gradient + scatter-add) over the batch
+           -> [N>1: NCCL all-reduce of the dense gradient] -> ONE fused optimizer kernel over all 2M points.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs-log2 24] [--nodes 2000000]
+
+`value`  : whole-job pairs/s with the pair batches resident in HBM (CUDA events, max over ranks).
+`e2e`    : same metric through the public API (graphembed.engine.PairTrainer.step_host) from PINNED HOST buffers:
+           every step uploads its (i, j, hops) batch and reads the loss back.
+`roofline`: fused pair kernel, algorithmic bytes (268 B/pair) / its CUDA-event duration vs the
+           measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port (same torch/LAPACK calls as the reference) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'matrix-manifolds_b200'))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'spd4_pair_dist_grad_evals_per_sec'
+UNIT = 'pairs/s'
+BYTES_PER_PAIR = 4 * 16 * 4 + 4 + 8  # 2 endpoint reads + 2 gradient accumulations + target + 2 indices
+N_SOURCES = 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--pairs-log2', type=int, default=24)
+    ap.add_argument('--nodes', type=int, default=2_000_000)
+    ap.add_argument('--batches', type=int, default=3, help='distinct pre-generated pair batches cycled through')
+    ap.add_argument('--cpu-pairs-log2', type=int, default=17)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------------------------------
+def scale_free_edges(n, m, seed):
+    """Preferential-attachment graph (Barabasi-Albert style, m edges per new node), vectorised: every edge of node t
+    either copies the target of a uniformly chosen earlier edge (degree-proportional choice) or picks a uniform earlier
+    node; copy chains are resolved by pointer jumping.  Connected by construction (edge 0 of node t goes to t-1's
+    component)."""
+    rng = np.random.RandomState(seed)
+    t = np.repeat(np.arange(1, n, dtype=np.int64), m)  # source node of every edge
+    e = np.arange(t.size, dtype=np.int64)
+    first_edge_of_t = (t - 1) * m
+    uniform_target = (rng.random_sample(t.size) * t).astype(np.int64)
+    copy = (rng.random_sample(t.size) < 0.5) & (first_edge_of_t > 0)
+    parent = np.where(copy, (rng.random_sample(t.size) * np.maximum(first_edge_of_t, 1)).astype(np.int64), e)
+    for _ in range(64):  # pointer jumping until every chain ends in a non-copy edge
+        nxt = parent[parent]
+        if np.array_equal(nxt, parent):
+            break
+        parent = nxt
+    target = uniform_target[parent]
+    return np.stack([t, target], axis=1)
+
+
+def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
+    """[(I int32, J int32, hops uint8)] pinned host tensors + max hop^2, targets from the BFS kernel."""
+    from graphembed.data import bfs_levels, edges_to_csr
+    from graphembed import _lib as L
+    import ctypes
+    P = 1 << log2_pairs
+    per_src = max(1, P // N_SOURCES)
+    n_src = P // per_src
+    edges = scale_free_edges(n_nodes, 4, seed)
+    rowptr, colidx = edges_to_csr(n_nodes, edges)
+    rp = torch.as_tensor(rowptr, device=device)
+    ci = torch.as_tensor(colidx, device=device)
+    gen = torch.Generator(device='cpu').manual_seed(seed)
+    batches, max_h = [], 0
+    for b in range(n_batches):
+        src = torch.randperm(n_nodes, generator=gen)[:n_src].int()
+        levels = bfs_levels(rp, ci, sources=src.to(device), device=device, level_bytes=1)  # (n_src, N) uint8
+        slot = torch.arange(n_src, dtype=torch.int32).repeat_interleave(per_src)
+        I = src[slot.long()].contiguous()
+        J = torch.randint(n_nodes - 1, (n_src * per_src,), generator=gen, dtype=torch.int32)
+        J = torch.where(J >= I, J + 1, J).contiguous()  # uniform over nodes != i
+        hops = torch.empty(n_src * per_src, dtype=torch.uint8, device=device)
+        sd, jd = slot.to(device), J.to(device)
+        rc = L.lib().gm_gather_levels(1, L.ptr(levels), n_nodes, L.ptr(sd), L.ptr(jd), hops.numel(), L.ptr(hops),
+                                      L.stream_ptr(device))
+        L.check(rc, 'gm_gather_levels')
+        max_h = max(max_h, int(levels.max().item()))
+        assert int(hops.min().item()) >= 1 and int(hops.max().item()) < 255
+        batches.append((I.pin_memory(), J.pin_memory(), hops.cpu().pin_memory()))
+        del levels
+    return batches, float(max_h * max_h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].startswith('Active')})
+        return {'sm_mhz': int(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port): same step on a bounded sample of the workload
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_step_rate(log2_pairs, steps, warmup, seed=0):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import manifolds_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = 1 << log2_pairs
+    n = max(64, P // 8)  # same pairs-per-node ratio as the full workload (2^24 pairs / 2M nodes)
+    gen = torch.Generator().manual_seed(seed)
+    orc = O.SpdOracle(4)
+    x = orc.rand(n, ir=0.1, dtype=torch.float32, generator=gen)
+    I = torch.randint(n, (P,), generator=gen)
+    J = (I + 1 + torch.randint(n - 1, (P,), generator=gen)) % n
+    t = torch.randint(1, 9, (P,), generator=gen).float().pow(2) / 64.0
+    sp = torch.nn.functional.softplus(torch.tensor(0.5))
+    state = {}
+    times = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        xr = x.clone().requires_grad_()
+        loss = O.quotient_loss(t, sp * orc.dist2(xr[I], xr[J]), 1.0, 1)
+        loss.backward()
+        x = O.radam_step(orc, x, xr.grad, state, lr=0.01, max_grad_norm=100, exact=True).detach()
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+    med = float(np.median(times))
+    return P / med, med, cores, f'2^{log2_pairs} pairs over {n} points per step (pairs:points = 8:1 as the full workload), ' \
+                                f'fwd+bwd+RAdam step, median of {steps}'
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: identical torch/LAPACK calls;
+    the Python reference itself cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    rate, med, cores, sample = cpu_step_rate(args.cpu_pairs_log2, steps, warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE config 5 (SPD 4x4 affine-invariant, sampled pairs, QuotientLoss, RAdam exact '
+                               'clip 100), bounded CPU sample', 'pairs_per_step': 1 << args.cpu_pairs_log2},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+        pg = dist.group.WORLD
+
+    from graphembed import _lib
+    from graphembed.engine import PairTrainer
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+
+    torch.manual_seed(42)  # identical replicas on every rank
+    N, P = args.nodes, 1 << args.pairs_log2
+    man = SymmetricPositiveDefinite(4)
+    emb = ManifoldEmbedding(N, [man], device=dev, dtype=torch.float32)
+    opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
+    # weak scaling: every rank draws its own 2^24-pair batches (different seed), embeddings replicated
+    batches, max_sq = make_pair_batches(N, args.pairs_log2, args.batches, dev, seed=1234 + rank)
+    if pg is not None:
+        m = torch.tensor([max_sq], device=dev)
+        torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MAX)
+        max_sq = float(m.item())
+    trainer = PairTrainer(emb, opt, QuotientLoss(), max_hops_sq=max_sq, alpha=1.0, process_group=pg)
+    dev_batches = [tuple(t.to(dev) for t in b) for b in batches]
+
+    def barrier():
+        if pg is not None:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (value, roofline) ----------------------------------------------------------------
+    for k in range(args.warmup):
+        trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
+    # per-kernel events for the dominant (pair) kernel: bracket it inside the step by patching the trainer's call
+    from graphembed import _ops
+    pair_events = []
+    orig = _ops.pairs_loss_fused
+
+    def timed_pairs(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(*a, **kw)
+        e1.record()
+        pair_events.append((e0, e1))
+        return r
+
+    _ops.pairs_loss_fused = timed_pairs
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    loss = None
+    for k in range(args.steps):
+        loss = trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
+    t1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    _ops.pairs_loss_fused = orig
+    ms = t0.elapsed_time(t1)
+    pair_ms = float(np.mean([a.elapsed_time(b) for a, b in pair_events]))
+    final_loss = float(loss.item())
+
+    # ---- end-to-end timing from pinned host buffers ----------------------------------------------------------------
+    for k in range(2):
+        trainer.step_host(*batches[k % len(batches)], epoch=1, next_batch=batches[(k + 1) % len(batches)])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        trainer.step_host(*batches[k % len(batches)], epoch=1, next_batch=batches[(k + 1) % len(batches)])
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if pg is not None:
+        t = torch.tensor([ms, ms_e2e, pair_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, ms_e2e, pair_ms = (float(v) for v in t.tolist())
+    if rank != 0:
+        if pg is not None:
+            torch.distributed.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    achieved = P * BYTES_PER_PAIR / (pair_ms * 1e-3) / 1e9
+    total_pairs = P * world * args.steps
+    line = {
+        'metric': METRIC, 'value': total_pairs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {
+            'workload': 'BASELINE config 5: synthetic scale-free graph, SPD 4x4 affine-invariant, sampled pairs '
+                        '(1024 BFS sources x targets) per step, QuotientLoss, RiemannianAdam(lr .01, clip 100, exact)',
+            'nodes': N, 'pairs_per_step_per_gpu': P, 'parallelism': f'pair-sharded replicas x{world}'
+            + (' + NCCL all-reduce of the (N,4,4) gradient' if world > 1 else ''),
+            'l2_policy': f'inputs larger than L2: {len(batches)} distinct batches of {P * 9 / 1e6:.0f} MB cycled, '
+                         f'{N * 64 / 1e6:.0f} MB embedding + {N * 64 / 1e6:.0f} MB gradient touched at random',
+            'final_loss': final_loss,
+        },
+        'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': P * 9,
+                'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps,
+                'api': 'graphembed.engine.PairTrainer.step_host (pinned host int32 i, int32 j, uint8 hops)'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'kernel': 'spd_pair_kernel<SpdAI<float,4>,K_FUSED>',
+                     'kernel_ms': pair_ms, 'bytes_per_pair': BYTES_PER_PAIR, 'peak_source': peak_src},
+        'clocks': clock_info,
+    }
+    if not args.no_cpu_baseline:
+        rate, med, cores, sample = cpu_step_rate(args.cpu_pairs_log2, 3, 1)
+        line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+    print(json.dumps(line))
+    if pg is not None:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

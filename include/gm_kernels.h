@@ -176,7 +176,9 @@ enum gm_point_op {
   GM_OP_INNER = 6,       /* out[k] = <u, v>_x (one scalar)      */
   GM_OP_NORM2 = 7,       /* out[k] = manifold.norm(x,u)^2 with the reference's clamp (one scalar) */
   GM_OP_TRANSP = 8,      /* out = transp(x, y := u, v)          */
-  GM_OP_RETR_QR = 9      /* Grassmann qr retraction             */
+  GM_OP_RETR_QR = 9,     /* Grassmann qr retraction             */
+  GM_OP_SPD_SQRTM = 10   /* SPD only: out = x^{1/2} via eigendecomposition, eigenvalues clamped to [wmin, wmax]
+                            (tb.spdsqrtm, linalg/torch_batch.py:169-171; used by SPD.randvec, spd.py:210-221) */
 };
 int gm_point_op(const gm_manifold_t* man, int32_t op, const void* x, const void* u, const void* v, void* out,
                 int64_t N, gm_stream_t stream);

@@ -287,10 +287,11 @@ int gm_point_op(const gm_manifold_t* man, int32_t op, const void* x, const void*
                 int64_t N, gm_stream_t stream) {
   int rc = manifold_ok(man);
   if (rc) return rc;
-  if (N < 0 || op < GM_OP_EXP || op > GM_OP_RETR_QR) return GM_EINVAL;
+  if (N < 0 || op < GM_OP_EXP || op > GM_OP_SPD_SQRTM) return GM_EINVAL;
+  if (op == GM_OP_SPD_SQRTM && man->kind != GM_SPD_AI && man->kind != GM_SPD_STEIN) return GM_EINVAL;
   if (N == 0) return GM_OK;
   if (!x || !out) return GM_ENULL;
-  const bool needs_u = op != GM_OP_PROJX;
+  const bool needs_u = op != GM_OP_PROJX && op != GM_OP_SPD_SQRTM;
   const bool needs_v = op == GM_OP_INNER || op == GM_OP_TRANSP;
   if ((needs_u && !u) || (needs_v && !v)) return GM_ENULL;
   PointArgs a{};

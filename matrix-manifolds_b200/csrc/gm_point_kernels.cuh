@@ -95,6 +95,8 @@ point_op_kernel(Man man, int op, const T* __restrict__ x, const T* __restrict__ 
     case GM_OP_INNER: scalar = true; sval = man.inner(xs, us, vs); break;
     case GM_OP_NORM2: scalar = true; sval = man.norm2(xs, us); break;
     case GM_OP_TRANSP: man.transp(xs, us, vs, os); break;
+    case GM_OP_SPD_SQRTM:
+      if constexpr (Man::kStatic) { man.sqrtm(xs, os); break; } else { return; }
     default: return;
   }
   if (scalar) {

@@ -107,6 +107,13 @@ struct SpdPt {
     GM_UNROLL for (int k = 0; k < N; ++k) w[k] = clampv(w[k], wmin, wmax);
     wdwt<T, N>(v, w, out);
   }
+  GM_HD void sqrtm(const T (&x)[CAP], T (&out)[CAP]) const {  // tb.spdsqrtm, torch_batch.py:169-171
+    T s[CAP], v[CAP], w[N];
+    GM_UNROLL for (int k = 0; k < CAP; ++k) s[k] = x[k];
+    jacobi_eigh<T, N, true>(s, v, w);
+    GM_UNROLL for (int k = 0; k < N; ++k) w[k] = Num<T>::sqrt(clampv(w[k], wmin, wmax));
+    wdwt<T, N>(v, w, out);
+  }
   GM_HD T inner(const T (&x)[CAP], const T (&u)[CAP], const T (&v)[CAP]) const {  // :100-106
     InvChol<T, N, FAST_CHOL> ic;
     ic.run(x);

@@ -1,0 +1,137 @@
+"""ctypes binding of libgm_b200.so -- the C-ABI declared in include/gm_kernels.h.
+
+There is no CPU fallback: if the shared library is missing, or an op is handed a
+tensor that is not a contiguous CUDA float32/float64 tensor, a RuntimeError is
+raised.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libgm_b200.so')
+
+# ---- enums (include/gm_kernels.h) -------------------------------------------
+GM_F32, GM_F64 = 0, 1
+GM_SPD_AI, GM_SPD_STEIN, GM_LORENTZ, GM_SPHERE, GM_GRASSMANN, GM_EUCLIDEAN = range(6)
+GM_FAST_EIG, GM_FAST_CHOL, GM_FAST_SVD = 1, 2, 4
+GM_PAIRS_ELEMENTWISE, GM_PAIRS_LIST, GM_PAIRS_TRIU = 0, 1, 2
+GM_LOSS_QUOTIENT, GM_LOSS_STRESS = 0, 1
+GM_TGT_VECTOR, GM_TGT_DENSE, GM_TGT_HOPS_U8, GM_TGT_HOPS_U16 = 0, 1, 2, 3
+GM_OPT_RSGD, GM_OPT_RADAM = 0, 1
+(GM_OP_EXP, GM_OP_RETR, GM_OP_LOG, GM_OP_PROJU, GM_OP_PROJX, GM_OP_EGRAD2RGRAD, GM_OP_INNER, GM_OP_NORM2,
+ GM_OP_TRANSP, GM_OP_RETR_QR, GM_OP_SPD_SQRTM) = range(11)
+
+_ERRORS = {-1: 'GM_EINVAL (bad argument combination)', -2: 'GM_EUNSUPPORTED (no kernel compiled for this '
+           'manifold size / dtype)', -3: 'GM_ENULL (required pointer is NULL)'}
+
+
+class Manifold(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('dtype', ctypes.c_int32), ('n', ctypes.c_int32), ('p', ctypes.c_int32),
+                ('flags', ctypes.c_uint32), ('reserved', ctypes.c_int32), ('wmin', ctypes.c_double),
+                ('wmax', ctypes.c_double)]
+
+
+class Pairs(ctypes.Structure):
+    _fields_ = [('mode', ctypes.c_int32), ('idx64', ctypes.c_int32), ('P', ctypes.c_int64),
+                ('idx_i', ctypes.c_void_p), ('idx_j', ctypes.c_void_p), ('B', ctypes.c_int64),
+                ('nodes', ctypes.c_void_p)]
+
+
+class Loss(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('inc_l1', ctypes.c_int32), ('inc_l2', ctypes.c_int32),
+                ('reserved', ctypes.c_int32), ('alpha', ctypes.c_double), ('eps', ctypes.c_double)]
+
+
+class Targets(ctypes.Structure):
+    _fields_ = [('mode', ctypes.c_int32), ('reserved', ctypes.c_int32), ('data', ctypes.c_void_p),
+                ('ld', ctypes.c_int64), ('max_sq', ctypes.c_double)]
+
+
+class Optim(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('exact', ctypes.c_int32), ('has_clip', ctypes.c_int32),
+                ('step', ctypes.c_int32), ('has_momentum', ctypes.c_int32), ('first_step', ctypes.c_int32),
+                ('grassmann_retr_qr', ctypes.c_int32), ('reserved', ctypes.c_int32), ('lr', ctypes.c_double),
+                ('beta1', ctypes.c_double), ('beta2', ctypes.c_double), ('momentum', ctypes.c_double),
+                ('dampening', ctypes.c_double), ('max_grad_norm', ctypes.c_double), ('eps', ctypes.c_double)]
+
+
+_vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+_PROTOTYPES = {
+    'gm_version': (ctypes.c_char_p, []),
+    'gm_launch_count': (_i64, []),
+    'gm_supported': (ctypes.c_int, [ctypes.POINTER(Manifold)]),
+    'gm_pairs_dist2': (ctypes.c_int, [ctypes.POINTER(Manifold), _vp, _vp, ctypes.POINTER(Pairs), _vp, _vp]),
+    'gm_pairs_grad': (ctypes.c_int, [ctypes.POINTER(Manifold), _vp, _vp, ctypes.POINTER(Pairs), _vp, _dbl, _vp, _vp,
+                                     _vp]),
+    'gm_pairs_loss_fused': (ctypes.c_int, [ctypes.POINTER(Manifold), _vp, ctypes.POINTER(Pairs),
+                                           ctypes.POINTER(Targets), ctypes.POINTER(Loss), _dbl, _vp, _vp, _vp, _vp]),
+    'gm_product_loss': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl),
+                                       ctypes.POINTER(Targets), ctypes.POINTER(Loss), _i64, _vp, _vp, _vp]),
+    'gm_optim_step': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(Optim), _vp, _vp, _vp, _vp, _i64, _vp]),
+    'gm_point_op': (ctypes.c_int, [ctypes.POINTER(Manifold), _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
+    'gm_bfs_workspace_bytes': (ctypes.c_size_t, [_i32, _i32]),
+    'gm_bfs_multi_source': (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, ctypes.c_size_t, _vp]),
+    'gm_levels_to_condensed': (ctypes.c_int, [_i32, _vp, _i32, _i32, _vp, _vp]),
+    'gm_levels_to_dense_targets': (ctypes.c_int, [_i32, _vp, _i32, _dbl, _i32, _vp, _vp]),
+    'gm_gather_levels': (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (loads on first use; raises if it was not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build the sm_100a kernels first '
+                '(`python -c "import __graft_entry__ as g; g.build()"` or `make -C matrix-manifolds_b200`). '
+                'graphembed-b200 has no CPU / PyTorch fallback.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f'{what}: {_ERRORS.get(rc, rc)}')
+    raise RuntimeError(f'{what}: CUDA error {rc} ({torch.cuda.get_device_name() if torch.cuda.is_available() else "no device"})')
+
+
+def dtype_code(dtype):
+    if dtype == torch.float32:
+        return GM_F32
+    if dtype == torch.float64:
+        return GM_F64
+    raise RuntimeError(f'gm_b200 kernels support float32/float64 only, got {dtype}')
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('gm_b200 kernels need CUDA tensors (there is no CPU fallback); got a tensor on '
+                               f'{t.device}. Move the embedding to the GPU or set the default device to cuda.')
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count():
+    return int(lib().gm_launch_count())

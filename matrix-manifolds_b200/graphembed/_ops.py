@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C-ABI (include/gm_kernels.h) and the autograd
+Functions the manifold classes are built from.
+
+Every function here launches hand-written sm_100a kernels from libgm_b200.so on
+the current CUDA stream of the tensors' device.  Nothing falls back to PyTorch.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+class ManifoldSpec:
+    """(kind, n, p, flags, wmin, wmax) of one manifold; dtype is taken from the tensors."""
+
+    __slots__ = ('kind', 'n', 'p', 'flags', 'wmin', 'wmax', 'point_shape')
+
+    def __init__(self, kind, n, p=0, flags=0, wmin=1e-8, wmax=1e8, point_shape=None):
+        self.kind, self.n, self.p, self.flags, self.wmin, self.wmax = kind, n, p, flags, wmin, wmax
+        self.point_shape = tuple(point_shape)
+
+    def c_struct(self, dtype):
+        return L.Manifold(kind=self.kind, dtype=L.dtype_code(dtype), n=self.n, p=self.p, flags=self.flags,
+                          reserved=0, wmin=self.wmin, wmax=self.wmax)
+
+    @property
+    def numel(self):
+        k = 1
+        for s in self.point_shape:
+            k *= s
+        return k
+
+
+def _prep(t):
+    L.require_cuda(t)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _index_tensor(idx, device):
+    """int32/int64 contiguous index tensor on `device` and its idx64 flag."""
+    if idx.dtype not in (torch.int32, torch.int64):
+        idx = idx.long()
+    idx = idx.to(device)
+    return (idx if idx.is_contiguous() else idx.contiguous()), int(idx.dtype == torch.int64)
+
+
+class PairSet:
+    """Which pairs a launch covers (mirrors gm_pairs_t); keeps the index tensors alive."""
+
+    def __init__(self, mode, P, idx_i=None, idx_j=None, B=0, nodes=None, idx64=0):
+        self.mode, self.P, self.idx_i, self.idx_j, self.B, self.nodes, self.idx64 = mode, P, idx_i, idx_j, B, nodes, idx64
+
+    @staticmethod
+    def elementwise(P):
+        return PairSet(L.GM_PAIRS_ELEMENTWISE, P)
+
+    @staticmethod
+    def from_lists(idx_i, idx_j, device):
+        i, f64 = _index_tensor(idx_i, device)
+        j, g64 = _index_tensor(idx_j, device)
+        if f64 != g64:
+            i, j, f64 = i.long(), j.long(), 1
+        if i.shape != j.shape or i.ndim != 1:
+            raise ValueError('pair index lists must be 1-D tensors of the same length')
+        return PairSet(L.GM_PAIRS_LIST, i.numel(), idx_i=i, idx_j=j, idx64=f64)
+
+    @staticmethod
+    def triu(B, nodes=None, device=None):
+        """All a<b pairs of a batch of B rows in torch.triu_indices(B, B, 1) order; `nodes` maps batch position
+        to row of the parameter (None: the batch *is* the tensor)."""
+        f64 = 0
+        if nodes is not None:
+            nodes, f64 = _index_tensor(nodes, device)
+            if nodes.numel() != B:
+                raise ValueError('len(nodes) must equal B')
+        return PairSet(L.GM_PAIRS_TRIU, B * (B - 1) // 2, B=B, nodes=nodes, idx64=f64)
+
+    def c_struct(self):
+        return L.Pairs(mode=self.mode, idx64=self.idx64, P=self.P,
+                       idx_i=None if self.idx_i is None else self.idx_i.data_ptr(),
+                       idx_j=None if self.idx_j is None else self.idx_j.data_ptr(), B=self.B,
+                       nodes=None if self.nodes is None else self.nodes.data_ptr())
+
+
+def pairs_dist2(spec, xa, xb, pairs):
+    xa, xb = _prep(xa), _prep(xb)
+    if xa.dtype != xb.dtype:
+        raise RuntimeError('dtype mismatch between the two endpoint tensors')
+    out = torch.empty(pairs.P, dtype=xa.dtype, device=xa.device)
+    m, p = spec.c_struct(xa.dtype), pairs.c_struct()
+    with torch.cuda.device(xa.device):
+        rc = L.lib().gm_pairs_dist2(ctypes.byref(m), L.ptr(xa), L.ptr(xb), ctypes.byref(p), L.ptr(out),
+                                    L.stream_ptr(xa.device))
+    L.check(rc, 'gm_pairs_dist2')
+    return out
+
+
+def pairs_grad(spec, xa, xb, pairs, gout, ga, gb, coef=1.0):
+    """ga/gb += coef * gout[k] * d(d2_k)/d(rows) (ELEMENTWISE: plain stores)."""
+    xa, xb, gout = _prep(xa), _prep(xb), _prep(gout)
+    if gout.dtype != xa.dtype:
+        gout = gout.to(xa.dtype)
+    m, p = spec.c_struct(xa.dtype), pairs.c_struct()
+    with torch.cuda.device(xa.device):
+        rc = L.lib().gm_pairs_grad(ctypes.byref(m), L.ptr(xa), L.ptr(xb), ctypes.byref(p), L.ptr(gout), float(coef),
+                                   L.ptr(ga), L.ptr(gb), L.stream_ptr(xa.device))
+    L.check(rc, 'gm_pairs_grad')
+
+
+class LossSpec:
+    def __init__(self, kind, inc_l1=True, inc_l2=True, alpha=1.0, eps=1.0):
+        self.kind, self.inc_l1, self.inc_l2, self.alpha, self.eps = kind, inc_l1, inc_l2, alpha, eps
+
+    def c_struct(self):
+        return L.Loss(kind=self.kind, inc_l1=int(self.inc_l1), inc_l2=int(self.inc_l2), reserved=0,
+                      alpha=float(self.alpha), eps=float(self.eps))
+
+
+class TargetSpec:
+    def __init__(self, mode, data, ld=0, max_sq=1.0):
+        self.mode, self.data, self.ld, self.max_sq = mode, data, ld, max_sq
+
+    @staticmethod
+    def vector(t):
+        return TargetSpec(L.GM_TGT_VECTOR, _prep(t))
+
+    @staticmethod
+    def dense(mat):
+        mat = _prep(mat)
+        return TargetSpec(L.GM_TGT_DENSE, mat, ld=mat.shape[1])
+
+    @staticmethod
+    def hops(h, max_sq):
+        h = _prep(h)
+        if h.dtype == torch.uint8:
+            return TargetSpec(L.GM_TGT_HOPS_U8, h, max_sq=max_sq)
+        if h.dtype in (torch.uint16, torch.int16):
+            return TargetSpec(L.GM_TGT_HOPS_U16, h, max_sq=max_sq)
+        raise RuntimeError('hop-count targets must be uint8 or uint16')
+
+    def c_struct(self):
+        return L.Targets(mode=self.mode, reserved=0, data=self.data.data_ptr(), ld=self.ld, max_sq=float(self.max_sq))
+
+
+def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, want_d2=False):
+    """One kernel: distances, loss and gradient.  Returns (acc, d2 or None); acc is a 2-element float64 tensor
+    [sum loss, sum l'(m) * d2] that is accumulated into (pass a zeroed one or None)."""
+    x = _prep(x)
+    if targets.mode in (L.GM_TGT_VECTOR, L.GM_TGT_DENSE) and targets.data.dtype != x.dtype:
+        raise RuntimeError('targets must have the dtype of the embedding')
+    if acc is None:
+        acc = torch.zeros(2, dtype=torch.float64, device=x.device)
+    d2 = torch.empty(pairs.P, dtype=x.dtype, device=x.device) if want_d2 else None
+    m, p, t, l = spec.c_struct(x.dtype), pairs.c_struct(), targets.c_struct(), loss.c_struct()
+    with torch.cuda.device(x.device):
+        rc = L.lib().gm_pairs_loss_fused(ctypes.byref(m), L.ptr(x), ctypes.byref(p), ctypes.byref(t), ctypes.byref(l),
+                                         float(scale_sp), L.ptr(d2), L.ptr(acc), L.ptr(grad),
+                                         L.stream_ptr(x.device))
+    L.check(rc, 'gm_pairs_loss_fused')
+    return acc, d2
+
+
+def product_loss(d2_list, sp_list, targets, loss, want_g=True):
+    """Loss over the product distance m = sum_f sp_f * d2_f.  Returns (acc[1+F] float64, dL/dm per pair)."""
+    F = len(d2_list)
+    d2_list = [_prep(d) for d in d2_list]
+    dtype, device, P = d2_list[0].dtype, d2_list[0].device, d2_list[0].numel()
+    acc = torch.zeros(1 + F, dtype=torch.float64, device=device)
+    g = torch.empty(P, dtype=dtype, device=device) if want_g else None
+    ptrs = (ctypes.c_void_p * F)(*[d.data_ptr() for d in d2_list])
+    sps = (ctypes.c_double * F)(*[float(s) for s in sp_list])
+    t, l = targets.c_struct(), loss.c_struct()
+    with torch.cuda.device(device):
+        rc = L.lib().gm_product_loss(L.dtype_code(dtype), F, ptrs, sps, ctypes.byref(t), ctypes.byref(l), P,
+                                     L.ptr(acc), L.ptr(g), L.stream_ptr(device))
+    L.check(rc, 'gm_product_loss')
+    return acc, g
+
+
+def point_op(spec, op, x, u=None, v=None, scalar=False):
+    x = _prep(x)
+    u = None if u is None else _prep(u.to(x.dtype))
+    v = None if v is None else _prep(v.to(x.dtype))
+    nd = len(spec.point_shape)
+    if tuple(x.shape[x.ndim - nd:]) != spec.point_shape:
+        raise RuntimeError(f'expected points of shape (..., {spec.point_shape}), got {tuple(x.shape)}')
+    batch = x.shape[:x.ndim - nd]
+    N = 1
+    for b in batch:
+        N *= b
+    out = torch.empty(batch if scalar else x.shape, dtype=x.dtype, device=x.device)
+    m = spec.c_struct(x.dtype)
+    with torch.cuda.device(x.device):
+        rc = L.lib().gm_point_op(ctypes.byref(m), op, L.ptr(x), L.ptr(u), L.ptr(v), L.ptr(out), N,
+                                 L.stream_ptr(x.device))
+    L.check(rc, 'gm_point_op')
+    return out
+
+
+def optim_step(spec, cfg, x, grad, buf1=None, buf2=None):
+    """In-place fused optimizer update of the (N, ...) parameter `x`."""
+    L.require_cuda(x, grad, buf1, buf2)
+    if not x.is_contiguous():
+        raise RuntimeError('parameters must be contiguous')
+    grad = _prep(grad.to(x.dtype))
+    N = x.numel() // spec.numel
+    m = spec.c_struct(x.dtype)
+    with torch.cuda.device(x.device):
+        rc = L.lib().gm_optim_step(ctypes.byref(m), ctypes.byref(cfg), L.ptr(x), L.ptr(grad), L.ptr(buf1),
+                                   L.ptr(buf2), N, L.stream_ptr(x.device))
+    L.check(rc, 'gm_optim_step')
+
+
+# ----------------------------------------------------------------------------
+# autograd Functions
+# ----------------------------------------------------------------------------
+class _Dist2Elementwise(torch.autograd.Function):
+    """d2[k] = dist^2(x[k], y[k]); backward writes per-row gradients."""
+
+    @staticmethod
+    def forward(ctx, x, y, spec):
+        ctx.spec = spec
+        x, y = _prep(x), _prep(y)
+        ctx.save_for_backward(x, y)
+        nd = len(spec.point_shape)
+        ctx.batch_shape = x.shape[:x.ndim - nd]
+        d2 = pairs_dist2(spec, x, y, PairSet.elementwise(x.numel() // spec.numel))
+        return d2.view(ctx.batch_shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        pairs_grad(ctx.spec, x, y, PairSet.elementwise(x.numel() // ctx.spec.numel), g.reshape(-1), gx, gy)
+        return gx, gy, None
+
+
+class _Dist2Indexed(torch.autograd.Function):
+    """d2 over a PairSet (LIST or TRIU) of rows of one parameter tensor; backward accumulates into a dense
+    gradient of x's shape (the fused equivalent of x[I], x[J] gathers + index_put_ backward)."""
+
+    @staticmethod
+    def forward(ctx, x, spec, pairs):
+        ctx.spec, ctx.pairs = spec, pairs
+        x = _prep(x)
+        ctx.save_for_backward(x)
+        return pairs_dist2(spec, x, x, pairs)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        gx = torch.zeros_like(x)
+        pairs_grad(ctx.spec, x, x, ctx.pairs, g, gx, gx)
+        return gx, None, None
+
+
+def dist2_elementwise(spec, x, y):
+    return _Dist2Elementwise.apply(x, y, spec)
+
+
+def dist2_indexed(spec, x, pairs):
+    return _Dist2Indexed.apply(x, spec, pairs)

@@ -1,0 +1,160 @@
+"""Model glue: ManifoldParameter, ManifoldEmbedding, BatchedObjective -- the
+interface of the reference's graphembed/modules.py:9-105.
+
+What is different underneath: `compute_dists(indices)` never materialises
+x[indices] (the gather is fused into the pair kernel), and `BatchedObjective`
+runs distance + loss + gradient as ONE kernel per step for a single manifold
+(gm_pairs_loss_fused) or distance / loss / gradient kernels per factor for a
+product (gm_pairs_dist2 + gm_product_loss + gm_pairs_grad).
+"""
+import abc
+
+import torch
+from torch.nn.functional import softplus
+
+from . import _ops
+
+
+class ManifoldParameter(torch.nn.Parameter):
+
+    def __new__(cls, data=None, manifold=None, requires_grad=True):
+        if data is None:
+            data = torch.Tensor()
+        instance = torch.Tensor._make_subclass(cls, data, requires_grad)
+        instance.manifold = manifold
+        return instance
+
+    def proj_(self):
+        self.manifold.projx(self, inplace=True)
+
+    def __repr__(self):
+        return 'Parameter on {} containing:\n'.format(self.manifold) + torch.Tensor.__repr__(self)
+
+
+class EmbeddingBase(torch.nn.Module):
+
+    @property
+    @abc.abstractmethod
+    def device(self):
+        pass
+
+    @property
+    @abc.abstractmethod
+    def curvature_params(self):
+        pass
+
+    def burnin(self, value=True):
+        for p in self.curvature_params:  # no curvature learning during burn-in
+            p.requires_grad_(not value)
+
+
+class ManifoldEmbedding(EmbeddingBase):
+    """n points on each of the given manifolds; the product distance is
+    sum_f softplus(scale_f) * dist_f^2 (modules.py:84-88)."""
+
+    def __init__(self, n, manifolds, device=None, dtype=None):
+        super().__init__()
+        self.n = n
+        self.n_components = len(manifolds)
+        self.manifolds = manifolds
+        hint = None
+        if device is not None or dtype is not None:
+            hint = torch.empty(0, device=device, dtype=dtype or torch.get_default_dtype())
+        self.xs = torch.nn.ParameterList([
+            ManifoldParameter(data=(m.rand(n) if hint is None else m.rand(n, out=hint)).contiguous(), manifold=m)
+            for m in manifolds
+        ])
+        # softplus(0.5) ~ 0.97
+        self.scales = torch.nn.ParameterList(
+            [torch.nn.Parameter(torch.tensor(0.5, device=self.xs[0].device, dtype=self.xs[0].dtype))
+             for _ in manifolds])
+
+    @property
+    def device(self):
+        return self.xs[0].device
+
+    @property
+    def curvature_params(self):
+        return self.scales
+
+    @torch.no_grad()
+    def perturb(self, norm):
+        for x, man in zip(self.xs, self.manifolds):
+            x.copy_(man.retr(x, man.randvec(x, norm)))
+
+    @torch.no_grad()
+    def stabilize(self):
+        for x in self.xs:
+            x.proj_()
+
+    @torch.no_grad()
+    def add_stats(self, writer, epoch):
+        for i in range(self.n_components):
+            writer.add_scalar(f'scale{i}', self.scales[i], epoch)
+
+    def compute_dists(self, i=None):
+        terms = []
+        for x, s, man in zip(self.xs, self.scales, self.manifolds):
+            d2 = man.pdist(x, squared=True) if i is None else man.batch_pdist2(x, i)
+            terms.append(softplus(s) * d2)
+        return sum(terms)
+
+    def __len__(self):
+        return self.n
+
+
+class _FusedObjective(torch.autograd.Function):
+    """loss(targets(pairs), sum_f softplus(s_f) dist_f^2(pairs)) with the gradients w.r.t. every x_f and s_f
+    produced in the forward pass; backward only rescales them."""
+
+    @staticmethod
+    def forward(ctx, pairs, targets, loss_spec, manifolds, n_factors, *params):
+        xs, scales = params[:n_factors], params[n_factors:]
+        sps = [float(softplus(s.detach())) for s in scales]
+        grads = [torch.zeros_like(x, memory_format=torch.contiguous_format) for x in xs]
+        if n_factors == 1:
+            acc, _ = _ops.pairs_loss_fused(manifolds[0].spec, xs[0].detach(), pairs, targets, loss_spec, sps[0],
+                                           grads[0])
+        else:
+            d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs) for m, x in zip(manifolds, xs)]
+            acc, g = _ops.product_loss(d2s, sps, targets, loss_spec)
+            for m, x, gx, sp in zip(manifolds, xs, grads, sps):
+                _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, gx, gx, coef=sp)
+        dscale = [acc[1 + f] * torch.sigmoid(scales[f].detach().double()) for f in range(n_factors)]
+        ctx.save_for_backward(*grads, *dscale)
+        ctx.n_factors = n_factors
+        ctx.scale_dtypes = [s.dtype for s in scales]
+        return acc[0].to(xs[0].dtype)
+
+    @staticmethod
+    def backward(ctx, upstream):
+        saved = ctx.saved_tensors
+        F = ctx.n_factors
+        gx = [g * upstream for g in saved[:F]]
+        gs = [(d * upstream).to(dt) for d, dt in zip(saved[F:], ctx.scale_dtypes)]
+        return (None, None, None, None, None, *gx, *gs)
+
+
+class BatchedObjective(torch.nn.Module):
+
+    def __init__(self, objective_fn, dataset, embedding):
+        super().__init__()
+        self.objective_fn = objective_fn
+        self.dataset = dataset
+        self.embedding = embedding
+
+    def forward(self, indices, *args, **kwargs):
+        emb = self.embedding
+        spec_fn = getattr(self.objective_fn, 'loss_spec', None)
+        loss_spec = spec_fn(**kwargs) if (spec_fn is not None and not args) else None
+        fusable = (loss_spec is not None and isinstance(emb, ManifoldEmbedding)
+                   and getattr(self.dataset, 'pdists', None) is not None
+                   and self.dataset.pdists.device == emb.device and self.dataset.pdists.dtype == emb.xs[0].dtype)
+        if not fusable:
+            return self.objective_fn(self.dataset[indices].to(emb.device), emb.compute_dists(indices), *args, **kwargs)
+        if indices is None:
+            pairs = _ops.PairSet.triu(emb.n)
+        else:
+            pairs = _ops.PairSet.triu(len(indices), indices, emb.device)
+        targets = _ops.TargetSpec.dense(self.dataset.pdists)
+        return _FusedObjective.apply(pairs, targets, loss_spec, emb.manifolds, emb.n_components, *emb.xs, *emb.scales)

@@ -1,0 +1,24 @@
+"""Shared plumbing of the two Riemannian optimizers: resolve the manifold of a
+parameter and launch the fused in-place update kernel (gm_optim_step)."""
+import torch
+
+from .. import _lib as L
+from .. import _ops
+
+
+def spec_of(param):
+    """ManifoldSpec of a parameter.  Plain tensors are treated like the reference treats them, as
+    Euclidean(1): every op is elementwise except the norm, taken over the last axis
+    (optim/radam.py:62-65, optim/rsgd.py:56-59)."""
+    manifold = getattr(param, 'manifold', None)
+    if manifold is not None and hasattr(manifold, 'spec'):
+        return manifold.spec, manifold
+    last = param.shape[-1] if param.ndim > 0 else 1
+    return _ops.ManifoldSpec(L.GM_EUCLIDEAN, last, point_shape=(last,)), None
+
+
+def fused_step(param, grad, cfg, buf1=None, buf2=None):
+    spec, manifold = spec_of(param)
+    cfg.grassmann_retr_qr = int(getattr(manifold, 'retr_kind', 'svd') == 'qr')
+    with torch.no_grad():
+        _ops.optim_step(spec, cfg, param.data, grad, buf1, buf2)

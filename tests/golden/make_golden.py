@@ -1,0 +1,163 @@
+"""Generates tests/golden/*.npz by running the REAL reference (dalab/matrix-manifolds
+`graphembed`, imported from /root/reference via oracle/ref_import.py) on CPU.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The fixtures are small (a dozen points per case) and are committed; the GPU box has
+no /root/reference, so the parity tests read these files instead.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings('ignore')
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, '..', '..', 'oracle'))
+import ref_import  # noqa: E402
+
+ref_import.load()
+from graphembed.manifolds import (SymmetricPositiveDefinite, Lorentz, Sphere, Grassmann, Euclidean)  # noqa: E402
+from graphembed.modules import ManifoldParameter, ManifoldEmbedding, BatchedObjective  # noqa: E402
+from graphembed.objectives import QuotientLoss, StressLoss  # noqa: E402
+from graphembed.optim import RiemannianAdam, RiemannianSGD  # noqa: E402
+from graphembed.data.dataset import GraphDataset  # noqa: E402
+
+N = 12
+CASES = {
+    # name: (constructor, ctor kwargs, init fn name, init kwargs)
+    'spd2': (SymmetricPositiveDefinite, dict(n=2), 'rand', dict(ir=1.0)),
+    'spd2_exact': (SymmetricPositiveDefinite, dict(n=2, fast_symeig=False, fast_chol=False), 'rand', dict(ir=1.0)),
+    'spd3': (SymmetricPositiveDefinite, dict(n=3), 'rand', dict(ir=1.0)),
+    'spd3_default_init': (SymmetricPositiveDefinite, dict(n=3), 'rand', dict()),
+    'spd4': (SymmetricPositiveDefinite, dict(n=4), 'rand', dict(ir=1.0)),
+    'spd4_default_init': (SymmetricPositiveDefinite, dict(n=4), 'rand', dict()),
+    'spd6': (SymmetricPositiveDefinite, dict(n=6), 'rand', dict(ir=1.0)),
+    'stein2': (SymmetricPositiveDefinite, dict(n=2, use_stein_div=True), 'rand', dict(ir=1.0)),
+    'stein4': (SymmetricPositiveDefinite, dict(n=4, use_stein_div=True), 'rand', dict(ir=1.0)),
+    'lorentz11': (Lorentz, dict(n=11), 'rand', dict(ir=1.0)),
+    'lorentz5_default_init': (Lorentz, dict(n=5), 'rand', dict()),
+    'sphere5': (Sphere, (5,), 'rand_uniform', dict()),
+    'euclidean7': (Euclidean, (7,), 'rand', dict(ir=1.0)),
+    'grassmann6_2': (Grassmann, dict(n=6, p=2), 'rand_uniform', dict()),
+    'grassmann7_3': (Grassmann, dict(n=7, p=3), 'rand_uniform', dict()),
+}
+
+
+def build(ctor, kw):
+    return ctor(*kw) if isinstance(kw, tuple) else ctor(**kw)
+
+
+def make_case(name, dtype, seed):
+    ctor, kw, init, ikw = CASES[name]
+    torch.set_default_dtype(dtype)
+    torch.manual_seed(seed)
+    man = build(ctor, kw)
+    x = getattr(man, init)(N, **ikw).contiguous()
+    y = getattr(man, init)(N, **ikw).contiguous()
+    out = dict(x=x.numpy(), y=y.numpy())
+    # elementwise dist^2 + gradients of a weighted sum
+    w = torch.linspace(0.5, 1.5, N, dtype=dtype)
+    xr, yr = x.clone().requires_grad_(), y.clone().requires_grad_()
+    d2 = man.dist(xr, yr, squared=True)
+    (d2 * w).sum().backward()
+    out.update(dist2=d2.detach().numpy(), w=w.numpy(), gx=xr.grad.numpy(), gy=yr.grad.numpy())
+    # pdist^2, QuotientLoss (both terms) and Stress against synthetic targets, gradients
+    P = N * (N - 1) // 2
+    g = torch.rand(P, dtype=dtype) * 0.9 + 0.1
+    out['targets'] = g.numpy()
+    for lname, fn, kwargs in (('quot', QuotientLoss(), dict(epoch=3, alpha=1.7)),
+                              ('quot_l1', QuotientLoss(inc_l2=False), dict(epoch=3, alpha=1.7)),
+                              ('stress', StressLoss(), dict())):
+        xr = x.clone().requires_grad_()
+        pd2 = man.pdist(xr, squared=True)
+        loss = fn(g, 0.9 * pd2, **kwargs)
+        loss.backward()
+        out[f'pdist2'] = pd2.detach().numpy()
+        out[f'loss_{lname}'] = np.array(loss.item())
+        out[f'grad_{lname}'] = xr.grad.numpy()
+    # point ops
+    u = man.randvec(x, 0.7).contiguous()
+    v = man.randvec(x, 0.3).contiguous()
+    eg = torch.randn_like(x)
+    out.update(u=u.numpy(), v=v.numpy(), eg=eg.numpy(), exp=man.exp(x, u).numpy(), retr=man.retr(x, u).numpy(),
+               log=man.log(x, y).numpy(), proju=man.proju(x, eg.clone()).numpy(),
+               egrad2rgrad=man.egrad2rgrad(x, eg.clone()).numpy(), transp=man.transp(x, y, u).numpy(),
+               inner=man.inner(x, u, v).numpy(), norm2=man.norm(x, u, squared=True).numpy())
+    # optimizer trajectories: 3 steps with fixed Euclidean gradients (the 2nd one zero)
+    grads = [torch.randn_like(x), torch.zeros_like(x), torch.randn_like(x)]
+    out['opt_grads'] = np.stack([t.numpy() for t in grads])
+    for oname, mk in (('radam_clip', lambda ps: RiemannianAdam(ps, lr=0.05, max_grad_norm=1.5)),
+                      ('radam_exact', lambda ps: RiemannianAdam(ps, lr=0.05, exact=True)),
+                      ('rsgd_exact_clip', lambda ps: RiemannianSGD(ps, lr=0.05, max_grad_norm=0.5, exact=True)),
+                      ('rsgd_momentum', lambda ps: RiemannianSGD(ps, lr=0.05, momentum=0.9, dampening=0.1))):
+        p = ManifoldParameter(x.clone(), manifold=man)
+        opt = mk([p])
+        traj = []
+        for gk in grads:
+            p.grad = gk.clone()
+            opt.step()
+            traj.append(p.data.clone().numpy())
+        out[f'{oname}_x'] = np.stack(traj)
+        st = opt.state[p]
+        for key in ('exp_avg', 'exp_avg_sq', 'momentum_buffer'):
+            if key in st:
+                out[f'{oname}_{key}'] = st[key].numpy()
+    return out
+
+
+def make_training_run():
+    """BASELINE config-1-shaped run on a tiny tree: SPD 3x3, fp64, full-batch QuotientLoss, RSGD(exact, clip 20),
+    through the reference's own ManifoldEmbedding / BatchedObjective, 4 steps; plus a product
+    SPD3 x Lorentz(5) run with RAdam."""
+    import networkx as nx
+    from scipy.sparse.csgraph import shortest_path
+    torch.set_default_dtype(torch.float64)
+    g = nx.balanced_tree(2, 4)  # 31 nodes
+    n = g.number_of_nodes()
+    hops = shortest_path(nx.to_scipy_sparse_array(g), unweighted=True)
+    iu = np.triu_indices(n, 1)
+    cond = torch.tensor(hops[iu])
+    out = dict(edges=np.array(g.edges()), hops_condensed=cond.numpy())
+    for tag, mans, mkopt in (
+            ('spd3_rsgd', lambda: [SymmetricPositiveDefinite(3)],
+             lambda ps: RiemannianSGD(ps, lr=0.01, max_grad_norm=20, exact=True)),
+            ('prod_radam', lambda: [SymmetricPositiveDefinite(3), Lorentz(5)],
+             lambda ps: RiemannianAdam(ps, lr=0.01, max_grad_norm=100, exact=True))):
+        torch.manual_seed(42)
+        ds = GraphDataset(cond.clone())
+        emb = ManifoldEmbedding(n, mans())
+        for i, x in enumerate(emb.xs):
+            out[f'{tag}_x0_{i}'] = x.data.clone().numpy()
+        opt = mkopt(emb.xs)
+        bobj = BatchedObjective(QuotientLoss(), ds, emb)
+        losses = []
+        perm = torch.randperm(n)
+        out[f'{tag}_perm'] = perm.numpy()
+        for step in range(4):
+            idx = perm if step % 2 == 0 else perm[:20]  # full batch and a node mini-batch
+            loss = bobj(idx, alpha=1.0, epoch=step + 1).sum()
+            opt.zero_grad()
+            loss.backward()
+            if step == 0:
+                for i, x in enumerate(emb.xs):
+                    out[f'{tag}_grad0_{i}'] = x.grad.clone().numpy()
+            opt.step()
+            losses.append(loss.item())
+        out[f'{tag}_losses'] = np.array(losses)
+        for i, x in enumerate(emb.xs):
+            out[f'{tag}_xT_{i}'] = x.data.clone().numpy()
+    return out
+
+
+def main():
+    for name in CASES:
+        for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
+            np.savez_compressed(os.path.join(HERE, f'{name}_{tag}.npz'), **make_case(name, dtype, seed=7))
+    np.savez_compressed(os.path.join(HERE, 'training_run_f64.npz'), **make_training_run())
+    print('wrote', len(os.listdir(HERE)) - 1, 'fixtures to', HERE)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,290 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C-ABI of libgm_b200.so,
+against (a) golden vectors produced by the real reference and (b) the pinned oracle on fresh seeded inputs.
+
+Tolerances are the ones BASELINE.json's north_star states: 1e-10 relative (fp64), 1e-5 relative (fp32) on
+distances, gradients, losses; bit-exact for BFS / indexing.  See helpers.tol() for the (documented) fp32
+exceptions where the reference itself is ill-conditioned.
+"""
+import numpy as np
+import pytest
+import torch
+
+import manifolds_oracle as O
+from helpers import CASES, DTYPES, is_spd, load_golden, make_oracle, make_product, rel_err, sym, tol
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _fix(name):
+    return sym if is_spd(name) else (lambda t: t)
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_dist_elementwise_vs_golden(name, tag):
+    g = load_golden(name, tag)
+    man = make_product(name)
+    x, y = g['x'].to(DEV).requires_grad_(), g['y'].to(DEV).requires_grad_()
+    d2 = man.dist(x, y, squared=True)
+    (d2 * g['w'].to(DEV)).sum().backward()
+    t = tol(DTYPES[tag], name)
+    fix = _fix(name)
+    assert rel_err(d2.detach(), g['dist2']) < t
+    assert rel_err(fix(x.grad), fix(g['gx'])) < t * 10
+    assert rel_err(fix(y.grad), fix(g['gy'])) < t * 10
+    # non-squared distance and its gradient flow through torch's sqrt like the reference's
+    d = man.dist(g['x'].to(DEV), g['y'].to(DEV))
+    assert rel_err(d, g['dist2'].sqrt()) < t
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_pdist_and_losses_vs_golden(name, tag):
+    from graphembed.objectives import QuotientLoss, StressLoss
+    g = load_golden(name, tag)
+    man = make_product(name)
+    t = tol(DTYPES[tag], name)
+    fix = _fix(name)
+    targets = g['targets'].to(DEV)
+    for lname, fn, kw in (('quot', QuotientLoss(), dict(epoch=3, alpha=1.7)),
+                          ('quot_l1', QuotientLoss(inc_l2=False), dict(epoch=3, alpha=1.7)),
+                          ('stress', StressLoss(), dict())):
+        x = g['x'].to(DEV).requires_grad_()
+        pd2 = man.pdist(x, squared=True)
+        loss = fn(targets, 0.9 * pd2, **kw)
+        loss.backward()
+        assert rel_err(pd2.detach(), g['pdist2']) < t
+        assert abs(loss.item() - g[f'loss_{lname}'].item()) <= t * 10 * abs(g[f'loss_{lname}'].item())
+        assert rel_err(fix(x.grad), fix(g[f'grad_{lname}'])) < t * 50
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_fused_kernel_vs_golden(name, tag):
+    """gm_pairs_loss_fused (distance + loss + gradient in one launch) against the reference's autograd."""
+    from graphembed import _ops, _lib as L
+    g = load_golden(name, tag)
+    man = make_product(name)
+    t = tol(DTYPES[tag], name)
+    fix = _fix(name)
+    x = g['x'].to(DEV).contiguous()
+    n = x.shape[0]
+    for lname, spec in (('quot', _ops.LossSpec(L.GM_LOSS_QUOTIENT, True, True, alpha=1.7, eps=1 / 4)),
+                        ('quot_l1', _ops.LossSpec(L.GM_LOSS_QUOTIENT, True, False, alpha=1.7, eps=1 / 4)),
+                        ('stress', _ops.LossSpec(L.GM_LOSS_STRESS))):
+        grad = torch.zeros_like(x)
+        acc, d2 = _ops.pairs_loss_fused(man.spec, x, _ops.PairSet.triu(n), _ops.TargetSpec.vector(g['targets'].to(DEV)),
+                                        spec, 0.9, grad, want_d2=True)
+        assert rel_err(d2, g['pdist2']) < t
+        assert abs(acc[0].item() - g[f'loss_{lname}'].item()) <= t * 10 * abs(g[f'loss_{lname}'].item())
+        assert rel_err(fix(grad), fix(g[f'grad_{lname}'])) < t * 50
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_point_ops_vs_golden(name, tag):
+    g = load_golden(name, tag)
+    man = make_product(name)
+    x, y, u, v, eg = (g[k].to(DEV) for k in ('x', 'y', 'u', 'v', 'eg'))
+    t = tol(DTYPES[tag]) * 20 if tag == 'f32' else 1e-10
+    assert rel_err(man.exp(x, u), g['exp']) < t
+    assert rel_err(man.retr(x, u), g['retr']) < t
+    assert rel_err(man.log(x, y), g['log']) < t * 50
+    assert rel_err(man.proju(x, eg), g['proju']) < t
+    assert rel_err(man.egrad2rgrad(x, eg), g['egrad2rgrad']) < t
+    assert rel_err(man.transp(x, y, u), g['transp']) < t
+    assert rel_err(man.inner(x, u, v), g['inner']) < t
+    assert rel_err(man.norm(x, u, squared=True), g['norm2'].reshape(-1)) < t
+    assert man.norm(x, u, keepdim=True).shape == (x.shape[0],) + (1,) * man.ndim
+
+
+OPTS = {
+    'radam_clip': ('radam', dict(lr=0.05, max_grad_norm=1.5)),
+    'radam_exact': ('radam', dict(lr=0.05, exact=True)),
+    'rsgd_exact_clip': ('rsgd', dict(lr=0.05, max_grad_norm=0.5, exact=True)),
+    'rsgd_momentum': ('rsgd', dict(lr=0.05, momentum=0.9, dampening=0.1)),
+}
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('oname', sorted(OPTS))
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_optimizer_trajectories_vs_golden(name, oname, tag):
+    from graphembed.modules import ManifoldParameter
+    from graphembed.optim import RiemannianAdam, RiemannianSGD
+    g = load_golden(name, tag)
+    man = make_product(name)
+    kind, kw = OPTS[oname]
+    p = ManifoldParameter(g['x'].to(DEV).contiguous(), manifold=man)
+    opt = (RiemannianAdam if kind == 'radam' else RiemannianSGD)([p], **kw)
+    t = 1e-10 if tag == 'f64' else 5e-5
+    for k in range(3):
+        p.grad = g['opt_grads'][k].to(DEV)
+        opt.step()
+        assert rel_err(p.data, g[f'{oname}_x'][k]) < t
+    st = opt.state[p]
+    for key in ('exp_avg', 'exp_avg_sq', 'momentum_buffer'):
+        if f'{oname}_{key}' in g:
+            assert rel_err(st[key], g[f'{oname}_{key}']) < t * 10
+
+
+@pytest.mark.parametrize('tag', ['spd3_rsgd', 'prod_radam'])
+def test_training_run_vs_golden(tag):
+    """BASELINE config 1 in miniature (tree -> SPD 3x3, fp64, QuotientLoss, RSGD exact clip 20) and a product
+    SPD3 x Lorentz5 with RAdam, free-running for 4 steps through the drop-in modules; targets from the BFS kernel."""
+    from graphembed.data import GraphDataset, bfs_levels, edges_to_csr
+    from graphembed.data.graph import levels_to_condensed
+    from graphembed.manifolds import SymmetricPositiveDefinite, Lorentz
+    from graphembed.modules import ManifoldEmbedding, BatchedObjective
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam, RiemannianSGD
+    with np.load(f'{__import__("helpers").GOLDEN}/training_run_f64.npz') as z:
+        g = {k: torch.from_numpy(z[k]) for k in z.files}
+    n = 31
+    rowptr, colidx = edges_to_csr(n, g['edges'].numpy())
+    levels = bfs_levels(rowptr, colidx)
+    cond = levels_to_condensed(levels, torch.float64)
+    assert torch.equal(cond.cpu(), g['hops_condensed'])  # BFS targets bit-exact
+    ds = GraphDataset(cond)
+    mans = [SymmetricPositiveDefinite(3)] if tag == 'spd3_rsgd' else [SymmetricPositiveDefinite(3), Lorentz(5)]
+    emb = ManifoldEmbedding(n, mans, device=DEV, dtype=torch.float64)
+    with torch.no_grad():
+        for i, x in enumerate(emb.xs):
+            x.copy_(g[f'{tag}_x0_{i}'].to(DEV))
+    opt = (RiemannianSGD(emb.xs, lr=0.01, max_grad_norm=20, exact=True) if tag == 'spd3_rsgd' else
+           RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True))
+    bobj = BatchedObjective(QuotientLoss(), ds, emb)
+    perm = g[f'{tag}_perm'].to(DEV)
+    losses = []
+    for step in range(4):
+        idx = perm if step % 2 == 0 else perm[:20]
+        loss = bobj(idx, alpha=1.0, epoch=step + 1).sum()
+        opt.zero_grad()
+        loss.backward()
+        if step == 0:
+            for i, x in enumerate(emb.xs):
+                fix = sym if i == 0 else (lambda t: t)
+                assert rel_err(fix(x.grad), fix(g[f'{tag}_grad0_{i}'])) < 1e-10
+        opt.step()
+        losses.append(loss.item())
+    ref = g[f'{tag}_losses']
+    assert np.allclose(np.array(losses), ref.numpy(), rtol=1e-9, atol=0), (losses, ref)
+    for i, x in enumerate(emb.xs):
+        assert rel_err(x.data, g[f'{tag}_xT_{i}']) < 1e-9
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('name', ['spd3', 'spd4', 'spd6', 'stein4', 'lorentz11', 'sphere5', 'grassmann6_2', 'euclidean7'])
+def test_pair_list_and_batch_gather_vs_oracle(name, dtype):
+    """LIST pairs (random I, J incl. repeats) and TRIU-with-node-gather against the oracle on seeded inputs."""
+    gen = torch.Generator().manual_seed(5)
+    g = load_golden(name, 'f64')
+    man, orc = make_product(name), make_oracle(name)
+    xs = torch.cat([g['x'], g['y']]).to(dtype)  # 24 valid points
+    n = xs.shape[0]
+    P = 500
+    I = torch.randint(n, (P,), generator=gen)
+    J = (I + 1 + torch.randint(n - 1, (P,), generator=gen)) % n
+    w = torch.rand(P, generator=gen, dtype=dtype) + 0.5
+    xo = xs.clone().requires_grad_()
+    d2o = orc.dist2(xo[I], xo[J])
+    (d2o * w).sum().backward()
+    xg = xs.to(DEV).requires_grad_()
+    d2 = man.pair_dist2(xg, I.to(DEV), J.to(DEV))
+    (d2 * w.to(DEV)).sum().backward()
+    t = tol(dtype, name)
+    fix = _fix(name)
+    assert rel_err(d2.detach(), d2o.detach()) < t
+    assert rel_err(fix(xg.grad), fix(xo.grad)) < t * 20
+    # int32 indices take the same path
+    d2b = man.pair_dist2(xs.to(DEV), I.int().to(DEV), J.int().to(DEV))
+    assert torch.equal(d2b, d2.detach())
+    # pdist(x[nodes]) with the gather fused
+    nodes = torch.randperm(n, generator=gen)[:17]
+    xo = xs.clone().requires_grad_()
+    pdo = orc.pdist2(xo[nodes])
+    pdo.sum().backward()
+    xg = xs.to(DEV).requires_grad_()
+    pd = man.batch_pdist2(xg, nodes.to(DEV))
+    pd.sum().backward()
+    assert rel_err(pd.detach(), pdo.detach()) < t
+    assert rel_err(fix(xg.grad), fix(xo.grad)) < t * 20
+
+
+def test_bfs_bit_exact_random_graphs():
+    """Multi-source BFS against scipy's BFS-based shortest_path on random connected graphs, all level widths,
+    partial source sets, and a path graph deeper than 254 hops (forces the uint16 retry)."""
+    import networkx as nx
+    from scipy.sparse.csgraph import shortest_path
+    from graphembed.data import bfs_levels, edges_to_csr
+    for seed, (n, m) in enumerate([(50, 2), (333, 1), (1000, 3)]):
+        g = nx.barabasi_albert_graph(n, m, seed=seed)
+        ref = shortest_path(nx.to_scipy_sparse_array(g), unweighted=True).astype(np.int64)
+        rowptr, colidx = edges_to_csr(n, np.array(g.edges()))
+        lv = bfs_levels(rowptr, colidx)
+        assert lv.dtype == torch.uint8 and np.array_equal(lv.cpu().numpy().astype(np.int64), ref)
+        src = np.random.RandomState(seed).choice(n, size=70, replace=False)
+        lv = bfs_levels(rowptr, colidx, sources=src, level_bytes=4)
+        assert np.array_equal(lv.cpu().numpy().astype(np.int64), ref[src])
+    g = nx.path_graph(400)
+    rowptr, colidx = edges_to_csr(400, np.array(g.edges()))
+    lv = bfs_levels(rowptr, colidx)
+    assert lv.dtype == torch.int16
+    ref = np.abs(np.arange(400)[:, None] - np.arange(400)[None, :])
+    assert np.array_equal(lv.cpu().numpy().astype(np.int64), ref)
+    # disconnected: unreachable marker
+    rowptr, colidx = edges_to_csr(4, np.array([[0, 1], [2, 3]]))
+    lv = bfs_levels(rowptr, colidx).cpu().numpy()
+    assert lv[0, 1] == 1 and lv[0, 2] == 255 and lv[2, 3] == 1
+
+
+def test_dataset_targets_match_oracle():
+    from graphembed.data import GraphDataset
+    gen = torch.Generator().manual_seed(0)
+    hops = torch.randint(1, 12, (45,), generator=gen).double()
+    ds = GraphDataset(hops.to(DEV))
+    ref = O.dataset_targets(hops, torch.float64)
+    assert torch.equal(ds[None].cpu(), ref)
+    idx = torch.tensor([7, 2, 9, 0])
+    dense = torch.zeros(10, 10, dtype=torch.float64)
+    i, j = torch.triu_indices(10, 10, 1)
+    dense[i, j] = ref
+    dense = dense + dense.T
+    assert torch.equal(ds[idx.to(DEV)].cpu(), O.batch_targets(dense, idx))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_full_size_properties_spd4(dtype):
+    """BASELINE-sized invariants that need no oracle: symmetry, affine invariance, fused == unfused, the sum of
+    all gradient rows equals the gradient computed pair-by-pair."""
+    from graphembed import _ops, _lib as L
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    torch.manual_seed(0)
+    man = SymmetricPositiveDefinite(4)
+    N, P = 1 << 16, 1 << 20
+    x = man.rand(N, out=torch.empty(0, device=DEV, dtype=dtype), ir=1.0)
+    I = torch.randint(N, (P,), device=DEV, dtype=torch.int32)
+    J = (I + 1 + torch.randint(N - 1, (P,), device=DEV, dtype=torch.int32)) % N
+    d_ij = man.pair_dist2(x, I, J)
+    d_ji = man.pair_dist2(x, J, I)
+    rt = 5e-5 if dtype == torch.float32 else 1e-10
+    assert rel_err(d_ij, d_ji) < rt
+    a = torch.randn(4, 4, device=DEV, dtype=dtype) + 3 * torch.eye(4, device=DEV, dtype=dtype)
+    xa = a @ x @ a.T
+    xa = 0.5 * (xa + xa.transpose(-2, -1))
+    assert rel_err(man.pair_dist2(xa, I, J), d_ij) < rt * 20
+    hops = torch.randint(1, 9, (P,), device=DEV, dtype=torch.uint8)
+    tg = _ops.TargetSpec.hops(hops, 64.0)
+    spec = _ops.LossSpec(L.GM_LOSS_QUOTIENT, True, True, alpha=1.0, eps=0.5)
+    pairs = _ops.PairSet.from_lists(I, J, DEV)
+    grad = torch.zeros_like(x)
+    acc, d2 = _ops.pairs_loss_fused(man.spec, x, pairs, tg, spec, 0.97, grad, want_d2=True)
+    assert torch.equal(d2, d_ij)
+    t = (hops.to(dtype) ** 2) / 64.0
+    acc2, g = _ops.product_loss([d_ij], [0.97], _ops.TargetSpec.vector(t), spec)
+    assert abs(acc[0].item() - acc2[0].item()) <= 1e-9 * abs(acc2[0].item())
+    grad2 = torch.zeros_like(x)
+    _ops.pairs_grad(man.spec, x, x, pairs, g, grad2, grad2, coef=0.97)
+    assert rel_err(grad, grad2) < (1e-4 if dtype == torch.float32 else 1e-11)
+    assert torch.isfinite(grad).all()
