@@ -27,7 +27,9 @@ def edges_to_csr(n, edges, directed=False):
         src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
     keep = src != dst
     src, dst = src[keep], dst[keep]
-    key = np.unique(dst * n + src)  # row = dst (who can be reached), col = src
+    key = np.sort(dst * n + src)  # row = dst (who can be reached), col = src
+    if key.size:
+        key = key[np.concatenate(([True], key[1:] != key[:-1]))]  # drop duplicate edges
     rows, cols = key // n, key % n
     rowptr = np.zeros(n + 1, dtype=np.int64)
     rowptr[1:] = np.cumsum(np.bincount(rows, minlength=n))
