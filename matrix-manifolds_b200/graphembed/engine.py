@@ -15,6 +15,7 @@ import torch
 from torch.nn.functional import softplus
 
 from . import _ops
+from .parallel import allreduce_step_buffers
 
 
 class PairTrainer:
@@ -51,9 +52,7 @@ class PairTrainer:
         self.grad.zero_()
         self.acc.zero_()
         _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, self._sp, self.grad, self.acc)
-        if self.pg is not None:
-            torch.distributed.all_reduce(self.grad, group=self.pg)
-            torch.distributed.all_reduce(self.acc, group=self.pg)
+        allreduce_step_buffers(self.grad, self.acc, self.pg)
         self.opt.step()
         return self.acc[0]
 

@@ -156,5 +156,8 @@ class BatchedObjective(torch.nn.Module):
             pairs = _ops.PairSet.triu(emb.n)
         else:
             pairs = _ops.PairSet.triu(len(indices), indices, emb.device)
-        targets = _ops.TargetSpec.dense(self.dataset.pdists)
+        if emb.n_components == 1:
+            targets = _ops.TargetSpec.dense(self.dataset.pdists)  # target gather fused into the pair kernel
+        else:
+            targets = _ops.TargetSpec.vector(self.dataset[indices])
         return _FusedObjective.apply(pairs, targets, loss_spec, emb.manifolds, emb.n_components, *emb.xs, *emb.scales)

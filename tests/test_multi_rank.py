@@ -1,0 +1,55 @@
+"""World-size-2 gloo test (CPU) of the multi-rank host logic: pair-sharding of a batch across ranks and the gradient
+combine produce the single-rank result.  The per-rank 'kernel' here is the oracle's autograd (CPU); the GPU path
+uses the same sharding helper and NCCL instead of gloo."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, 'matrix-manifolds_b200'))
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import manifolds_oracle as O
+    from graphembed.parallel import shard_range, allreduce_step_buffers
+    torch.manual_seed(0)
+    orc = O.SpdOracle(3)
+    x = orc.rand(20, ir=1.0)
+    P = 101
+    I = torch.randint(20, (P,))
+    J = (I + 1 + torch.randint(19, (P,))) % 20
+    t = torch.rand(P, dtype=torch.float64) + 0.2
+    lo, hi = shard_range(P, rank, world)
+    xr = x.clone().requires_grad_()
+    loss = O.quotient_loss(t[lo:hi], orc.dist2(xr[I[lo:hi]], xr[J[lo:hi]]), 1.0, 1)
+    loss.backward()
+    grad, acc = xr.grad.clone(), torch.tensor([loss.item(), 0.0], dtype=torch.float64)
+    allreduce_step_buffers(grad, acc, dist.group.WORLD)
+    if rank == 0:
+        xs = x.clone().requires_grad_()
+        full = O.quotient_loss(t, orc.dist2(xs[I], xs[J]), 1.0, 1)
+        full.backward()
+        out.put((float((grad - xs.grad).abs().max()), abs(acc[0].item() - full.item()), [shard_range(7, r, 3) for r in range(3)]))
+    dist.destroy_process_group()
+
+
+def test_pair_sharding_and_gradient_combine_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gerr, lerr, ranges = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert gerr < 1e-12 and lerr < 1e-10
+    assert ranges == [(0, 3), (3, 5), (5, 7)]  # contiguous, balanced, covering
