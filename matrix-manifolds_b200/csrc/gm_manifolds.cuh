@@ -197,6 +197,39 @@ struct SpdAI {
     return clamp_min(phi, wmin);
   }
 
+  // The exact path (LAPACK-equivalent Cholesky + Jacobi) depends on x only through a = chol(x)^-1, which a
+  // caller that visits many pairs with the same first endpoint can compute once (spd.py:178 does the same per node).
+  static constexpr bool kCanPrep = !FAST_EIG && !FAST_CHOL;
+  static constexpr int kPrepSize = N * (N + 1) / 2;
+  GM_HD void prep(const T (&x)[E], T (&ap)[kPrepSize]) const {
+    InvChol<T, N, false> ic;
+    ic.run(x);
+    GM_UNROLL for (int i = 0; i < N; ++i)
+      GM_UNROLL for (int j = 0; j <= i; ++j) ap[i * (i + 1) / 2 + j] = ic.a[i * N + j];
+  }
+  GM_HD T dist2_grad_prepped(const T (&ap)[kPrepSize], const T (&y)[E], T (&gx)[E], T (&gy)[E]) const {
+    T a[E], m[E];
+    GM_UNROLL for (int i = 0; i < N; ++i)
+      GM_UNROLL for (int j = 0; j < N; ++j) a[i * N + j] = (j <= i) ? ap[i * (i + 1) / 2 + j] : (T)0;
+    congr_lower<T, N>(a, y, m);
+    T v[E], w[N], cx[N], cy[N];
+    jacobi_eigh<T, N, true>(m, v, w);
+    T phi = (T)0;
+    GM_UNROLL for (int k = 0; k < N; ++k) {
+      T wc = clampv(w[k], wmin, wmax);
+      T lg = Num<T>::log(wc);
+      phi += lg * lg;
+      T c = (T)2 * lg / wc;
+      cy[k] = c;
+      cx[k] = -c * w[k];
+    }
+    T wm[E];
+    lowerT_mul<T, N>(a, v, wm);
+    wdwt<T, N>(wm, cx, gx);
+    wdwt<T, N>(wm, cy, gy);
+    return clamp_min(phi, wmin);
+  }
+
   // Returns d2 and fills gx = d(d2)/dx, gy = d(d2)/dy (both symmetric).
   GM_HD T dist2_grad(const T (&x)[E], const T (&y)[E], T (&gx)[E], T (&gy)[E]) const {
     InvChol<T, N, FAST_CHOL> ic;
@@ -274,7 +307,11 @@ struct SpdAI {
 template <typename T, int N, bool FAST_CHOL>
 struct SpdStein {
   static constexpr int E = N * N;
+  static constexpr bool kCanPrep = false;
+  static constexpr int kPrepSize = 1;
   T wmin, wmax;
+  GM_HD void prep(const T (&)[E], T (&)[1]) const {}
+  GM_HD T dist2_grad_prepped(const T (&)[1], const T (&)[E], T (&)[E], T (&)[E]) const { return (T)0; }
 
   template <bool WANT_INV>
   GM_HD static T logdet_inv(const T (&x)[E], T (&inv)[E]) {

@@ -35,6 +35,31 @@ template <> struct Num<float> {
     return 1.0f / sqrtf(x);
 #endif
   }
+  // Rotation-parameter math for the Jacobi sweeps.  The rotation ANGLE may be inexact (it only affects the
+  // convergence rate), the pair (c, s) must be orthonormal to rounding: approximate sqrt / divide (MUFU.RSQ,
+  // MUFU.RCP, no IEEE slow paths) for tan(theta), one Newton step on rsqrt for c.
+  GM_HD static float rot_sqrt(float x) {
+#ifdef __CUDA_ARCH__
+    return x > 0.f ? x * rsqrtf(x) : 0.f;
+#else
+    return sqrtf(x);
+#endif
+  }
+  GM_HD static float rot_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+  }
+  GM_HD static float rot_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float r = rsqrtf(x);
+    return r * (1.5f - 0.5f * x * r * r);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+  }
   GM_HD static float log(float x) { return logf(x); }
   GM_HD static float log1p(float x) { return log1pf(x); }
   GM_HD static float exp(float x) { return expf(x); }
@@ -55,6 +80,9 @@ template <> struct Num<double> {
   static constexpr double tiny = DBL_MIN;
   GM_HD static double sqrt(double x) { return ::sqrt(x); }
   GM_HD static double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  GM_HD static double rot_sqrt(double x) { return ::sqrt(x); }
+  GM_HD static double rot_div(double a, double b) { return a / b; }
+  GM_HD static double rot_rsqrt(double x) { return 1.0 / ::sqrt(x); }
   GM_HD static double log(double x) { return ::log(x); }
   GM_HD static double log1p(double x) { return ::log1p(x); }
   GM_HD static double exp(double x) { return ::exp(x); }
@@ -243,9 +271,9 @@ GM_HD void jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N]) {
         // t = tan(theta), smaller root of t^2 + 2 t cot(2 theta) - 1 = 0, branch-free:
         // t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)); apq == 0 -> t == 0.
         T two_apq = apq + apq;
-        T den = Num<T>::abs(d) + Num<T>::sqrt(d * d + two_apq * two_apq);
-        T t = (den > (T)0) ? (d >= (T)0 ? two_apq : -two_apq) / den : (T)0;
-        T c = Num<T>::rsqrt(t * t + (T)1);
+        T den = Num<T>::abs(d) + Num<T>::rot_sqrt(d * d + two_apq * two_apq);
+        T t = (den > (T)0) ? Num<T>::rot_div(d >= (T)0 ? two_apq : -two_apq, den) : (T)0;
+        T c = Num<T>::rot_rsqrt(t * t + (T)1);
         T s = t * c;
         a[p * N + p] -= t * apq;
         a[q * N + q] += t * apq;
@@ -298,9 +326,9 @@ GM_HD void jacobi_svd(T (&a)[R * C], T (&v)[C * C], T (&s)[C]) {
           rotated = true;
           T d = beta - alpha;
           T two_g = gamma + gamma;
-          T den = Num<T>::abs(d) + Num<T>::sqrt(d * d + two_g * two_g);
-          T t = (d >= (T)0 ? two_g : -two_g) / den;
-          T c = Num<T>::rsqrt(t * t + (T)1);
+          T den = Num<T>::abs(d) + Num<T>::rot_sqrt(d * d + two_g * two_g);
+          T t = Num<T>::rot_div(d >= (T)0 ? two_g : -two_g, den);
+          T c = Num<T>::rot_rsqrt(t * t + (T)1);
           T sn = t * c;
           GM_UNROLL for (int r = 0; r < R; ++r) {
             T x = a[r * C + p], y = a[r * C + q];

@@ -69,6 +69,234 @@ spd_pair_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __restric
   }
 }
 
+// ---------------------------------------------------------------------------
+// Streaming variant for LIST / TRIU pair sets (the training hot path).
+//
+// Persistent grid; every warp owns a contiguous range of pairs and walks it 32
+// pairs at a time.  Per lane, a 3-deep software pipeline hides the gather:
+//   iteration it   : compute pair k(it) from rows staged in shared memory
+//   issued in `it` : cp.async (LDGSTS) of both endpoint rows + target of pair k(it+1)
+//                    index loads of pair k(it+2)
+// Each thread stages into its own slots (layout [stage][row][16B-chunk][thread],
+// bank-conflict free), so no block barrier is needed inside the loop.
+// Consecutive pairs of a warp usually share the first endpoint (TRIU order,
+// source-major pair lists): its inverse Cholesky factor is cached in registers
+// and its gradient is accumulated in registers across iterations, reduced over
+// the warp with shuffles and flushed with ONE vector reduction when the row
+// changes.  The loss is accumulated per thread and block-reduced once.
+// ---------------------------------------------------------------------------
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+  else if constexpr (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <typename T, int E>
+struct RowStage {
+  static constexpr int ROWB = E * (int)sizeof(T);
+  static constexpr int CPB = (ROWB % 16 == 0) ? 16 : ((ROWB % 8 == 0) ? 8 : 4);
+  static constexpr int NCH = ROWB / CPB;
+  static constexpr int THREADS = 128;
+  static constexpr int BYTES = 2 /*stages*/ * 2 /*rows*/ * ROWB * THREADS;
+  // slot of chunk c of row r (0: a side, 1: b side) of stage s for thread t
+  __device__ __forceinline__ static char* slot(char* base, int s, int r, int c, int t) {
+    return base + ((((s * 2 + r) * NCH + c) * THREADS + t) * CPB);
+  }
+  __device__ __forceinline__ static void issue(char* base, int s, int r, int t, const T* row) {
+    const char* g = reinterpret_cast<const char*>(row);
+    GM_UNROLL for (int c = 0; c < NCH; ++c) cp_async<CPB>(slot(base, s, r, c, t), g + c * CPB);
+  }
+  __device__ __forceinline__ static void read(char* base, int s, int r, int t, T (&out)[E]) {
+    GM_UNROLL for (int c = 0; c < NCH; ++c) {
+      if constexpr (CPB == 16) {
+        float4 v = *reinterpret_cast<const float4*>(slot(base, s, r, c, t));
+        const T* tv = reinterpret_cast<const T*>(&v);
+        GM_UNROLL for (int j = 0; j < 16 / (int)sizeof(T); ++j) out[c * (16 / (int)sizeof(T)) + j] = tv[j];
+      } else if constexpr (CPB == 8) {
+        float2 v = *reinterpret_cast<const float2*>(slot(base, s, r, c, t));
+        const T* tv = reinterpret_cast<const T*>(&v);
+        GM_UNROLL for (int j = 0; j < 8 / (int)sizeof(T); ++j) out[c * (8 / (int)sizeof(T)) + j] = tv[j];
+      } else {
+        out[c] = *reinterpret_cast<const T*>(slot(base, s, r, c, t));
+      }
+    }
+  }
+};
+
+// pair cursor of one lane: walks k, k+32, k+64, ... inside [k, kend)
+struct PairCursor {
+  long long k, a, pos;  // TRIU: row a, position inside the row
+  __device__ __forceinline__ void init(const PairSpec& ps, long long k0) {
+    k = k0;
+    if (ps.mode == GM_PAIRS_TRIU && k0 < ps.P) {
+      long long b;
+      triu_decode(k0, ps.B, a, b);
+      pos = b - a - 1;
+    } else {
+      a = 0; pos = 0;
+    }
+  }
+  __device__ __forceinline__ void rows(const PairSpec& ps, long long& ra, long long& rb) const {
+    if (ps.mode == GM_PAIRS_LIST) {
+      ra = load_index(ps.idx_i, k, ps.idx64);
+      rb = load_index(ps.idx_j, k, ps.idx64);
+    } else {
+      long long b = a + 1 + pos;
+      if (ps.nodes) { ra = load_index(ps.nodes, a, ps.idx64); rb = load_index(ps.nodes, b, ps.idx64); }
+      else { ra = a; rb = b; }
+    }
+  }
+  __device__ __forceinline__ void advance(const PairSpec& ps) {
+    k += 32;
+    if (ps.mode == GM_PAIRS_TRIU) {
+      pos += 32;
+      while (a < ps.B - 1 && pos >= ps.B - a - 1) { pos -= ps.B - a - 1; ++a; }
+    }
+  }
+};
+
+template <class Op, typename T, int KMODE, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __restrict__ xb,
+                       const T* __restrict__ gout, T coef, T* __restrict__ ga, T* __restrict__ gb,
+                       T* __restrict__ out_d2, TargetSpec tg, LossCfg lc, T scale_sp, double* __restrict__ acc,
+                       long long chunk) {
+  constexpr int E = Op::E;
+  using Stage = RowStage<T, E>;
+  extern __shared__ __align__(16) char stage_mem[];
+  __shared__ double red[2][4];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned full = 0xffffffffu;
+  const long long warp_id = (long long)blockIdx.x * 4 + (tid >> 5);
+  const long long k0 = warp_id * chunk;
+  const long long kend = (k0 + chunk < ps.P) ? k0 + chunk : ps.P;
+
+  // ---- pipeline registers -------------------------------------------------------------------------------------
+  PairCursor cur;            // pair being computed / staged
+  long long ra0 = -1, rb0 = -1;  // rows of the pair computed in this iteration (staged in `stage`)
+  long long ra1 = -1, rb1 = -1;  // rows of the next pair (indices loaded, rows not yet issued)
+  T tg0 = (T)0, tg1 = (T)0;      // target (K_FUSED) or upstream gradient (K_BWD) of those pairs
+  int stage = 0;
+
+  auto fetch_scalar = [&](long long k, long long ra, long long rb) -> T {
+    if constexpr (KMODE == K_BWD) return gout[k];
+    else return fetch_target<T>(tg, k, ra, rb);
+  };
+
+  cur.init(ps, k0 + lane);
+  bool v0 = cur.k < kend;
+  if (v0) {
+    cur.rows(ps, ra0, rb0);
+    Stage::issue(stage_mem, 0, 0, tid, xa + ra0 * E);
+    Stage::issue(stage_mem, 0, 1, tid, xb + rb0 * E);
+    tg0 = fetch_scalar(cur.k, ra0, rb0);
+  }
+  cp_async_commit();
+  PairCursor nxt = cur;
+  nxt.advance(ps);
+  bool v1 = nxt.k < kend;
+  if (v1) nxt.rows(ps, ra1, rb1);
+
+  // ---- per-lane running state -------------------------------------------------------------------------------------
+  double loss_v = 0.0, gd2_v = 0.0;
+  long long acc_row = -1;  // warp-uniform row whose gradient is being accumulated in gacc (or -1)
+  T gacc[E];
+  GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = (T)0;
+  long long prep_row = -1;
+  T ap[Op::kPrepSize];
+
+  auto flush = [&]() {
+    if (acc_row >= 0) {
+      GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = warp_sum(gacc[e]);
+      if (lane == 0) atomic_add_row<T, E>(ga, acc_row, gacc);
+      GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = (T)0;
+      acc_row = -1;
+    }
+  };
+
+  while (__any_sync(full, v0)) {
+    // (1) rows of the current pair have landed in my slots
+    cp_async_wait_all();
+    T x[E], y[E];
+    if (v0) {
+      Stage::read(stage_mem, stage, 1, tid, y);
+      if (!Op::kCanPrep || ra0 != prep_row) Stage::read(stage_mem, stage, 0, tid, x);
+    }
+    // (2) stage the next pair: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
+    T tgn = (T)0;
+    if (v1) {
+      Stage::issue(stage_mem, stage ^ 1, 0, tid, xa + ra1 * E);
+      Stage::issue(stage_mem, stage ^ 1, 1, tid, xb + rb1 * E);
+      tgn = fetch_scalar(nxt.k, ra1, rb1);
+    }
+    cp_async_commit();
+    PairCursor nn = nxt;
+    nn.advance(ps);
+    bool v2 = v1 && nn.k < kend;
+    long long ra2 = -1, rb2 = -1;
+    if (v2) nn.rows(ps, ra2, rb2);
+
+    // (4) the math
+    T gx[E], gy[E];
+    if (v0) {
+      T d2;
+      if constexpr (Op::kCanPrep) {
+        if (ra0 != prep_row) { op.prep(x, ap); prep_row = ra0; }
+        d2 = op.dist2_grad_prepped(ap, y, gx, gy);
+      } else {
+        d2 = op.dist2_grad(x, y, gx, gy);
+      }
+      T w;
+      if constexpr (KMODE == K_BWD) {
+        w = coef * tg0;
+      } else {
+        T m = scale_sp * d2;
+        T dm;
+        T lv = loss_term<T>(lc, tg0, m, dm);
+        loss_v += (double)lv;
+        gd2_v += (double)dm * (double)d2;
+        w = dm * scale_sp;
+        if (out_d2) out_d2[cur.k] = d2;
+      }
+      GM_UNROLL for (int e = 0; e < E; ++e) { gx[e] *= w; gy[e] *= w; }
+      atomic_add_row<T, E>(gb, rb0, gy);
+    }
+    // (5) first-endpoint gradient: run-length accumulation in registers
+    {
+      long long r0 = __shfl_sync(full, ra0, 0);
+      bool uniform = __all_sync(full, v0 && ra0 == r0);
+      if (uniform && r0 == acc_row) {
+        GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] += gx[e];
+      } else {
+        flush();
+        if (uniform) {
+          acc_row = r0;
+          GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = gx[e];
+        } else if (v0) {
+          atomic_add_row<T, E>(ga, ra0, gx);
+        }
+      }
+    }
+    // (6) rotate the pipeline
+    cur = nxt; nxt = nn;
+    ra0 = ra1; rb0 = rb1; tg0 = tgn; v0 = v1;
+    ra1 = ra2; rb1 = rb2; v1 = v2;
+    stage ^= 1;
+  }
+  flush();
+  if constexpr (KMODE == K_FUSED) {
+    block_accumulate(loss_v, acc, red[0]);
+    block_accumulate(gd2_v, acc + 1, red[1]);
+  }
+}
+
 template <class Op, typename T>
 static int launch_op(const Op& op, const PairArgs& a) {
   if (a.ps.P <= 0) return 0;
@@ -78,6 +306,32 @@ static int launch_op(const Op& op, const PairArgs& a) {
   dim3 grid((unsigned)blocks), block(threads);
   const T* xa = (const T*)a.xa;
   const T* xb = (const T*)a.xb;
+  using Stage = RowStage<T, Op::E>;
+  if (a.kmode != K_FWD && a.ps.mode != GM_PAIRS_ELEMENTWISE && Stage::BYTES <= 64 * 1024) {
+    constexpr int MINB = sizeof(T) == 4 ? 4 : 2;
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto launch_stream = [&](auto kern, const T* gout, T coef, T* out_d2, T scale, double* acc) -> int {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Stage::BYTES);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, Stage::BYTES);
+      if (occ < 1) occ = 1;
+      long long max_blocks = (long long)sms * occ;
+      long long want = (a.ps.P + threads - 1) / threads;
+      long long nb = want < max_blocks ? want : max_blocks;
+      long long warps = nb * (threads / 32);
+      long long chunk = ((a.ps.P + warps - 1) / warps + 31) / 32 * 32;
+      kern<<<(unsigned)nb, threads, Stage::BYTES, a.stream>>>(op, a.ps, xa, xb, gout, coef, (T*)a.ga, (T*)a.gb, out_d2,
+                                                             a.tg, a.lc, scale, acc, chunk);
+      note_launch();
+      return check_launch();
+    };
+    if (a.kmode == K_BWD)
+      return launch_stream(spd_pair_stream_kernel<Op, T, K_BWD, MINB>, (const T*)a.gout, (T)a.coef, nullptr, (T)0,
+                           nullptr);
+    return launch_stream(spd_pair_stream_kernel<Op, T, K_FUSED, MINB>, nullptr, (T)0, (T*)a.out_d2, (T)a.scale_sp,
+                         a.acc);
+  }
   switch (a.kmode) {
     case K_FWD:
       spd_pair_kernel<Op, T, K_FWD><<<grid, block, 0, a.stream>>>(
