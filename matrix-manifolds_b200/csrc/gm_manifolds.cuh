@@ -199,35 +199,51 @@ struct SpdAI {
 
   // The exact path (LAPACK-equivalent Cholesky + Jacobi) depends on x only through a = chol(x)^-1, which a
   // caller that visits many pairs with the same first endpoint can compute once (spd.py:178 does the same per node).
+  // It is split in two so that the caller can fold its loss weight into the N gradient coefficients instead of
+  // scaling 2 N^2 gradient entries afterwards:
+  //   eig_forward : m = a y a^T, Jacobi sweeps started from W0 = a^T so that W = L^-T V (which diagonalises both:
+  //                 W^T x W = I, W^T y W = diag(lambda)) comes out of the sweeps directly; returns phi = sum log^2.
+  //   eig_backward: gx = wgt * d(phi)/dx = W diag(-2 wgt log l_k) W^T,  gy = W diag(2 wgt log l_k / l_k) W^T.
   static constexpr bool kCanPrep = !FAST_EIG && !FAST_CHOL;
   static constexpr int kPrepSize = N * (N + 1) / 2;
+  struct EigState {
+    T wm[E];
+    T cx[N], cy[N];
+  };
   GM_HD void prep(const T (&x)[E], T (&ap)[kPrepSize]) const {
     InvChol<T, N, false> ic;
     ic.run(x);
     GM_UNROLL for (int i = 0; i < N; ++i)
       GM_UNROLL for (int j = 0; j <= i; ++j) ap[i * (i + 1) / 2 + j] = ic.a[i * N + j];
   }
-  GM_HD T dist2_grad_prepped(const T (&ap)[kPrepSize], const T (&y)[E], T (&gx)[E], T (&gy)[E]) const {
-    T a[E], m[E];
-    GM_UNROLL for (int i = 0; i < N; ++i)
-      GM_UNROLL for (int j = 0; j < N; ++j) a[i * N + j] = (j <= i) ? ap[i * (i + 1) / 2 + j] : (T)0;
+  GM_HD T eig_forward(const T (&a)[E], const T (&y)[E], EigState& st) const {
+    T m[E], w[N];
     congr_lower<T, N>(a, y, m);
-    T v[E], w[N], cx[N], cy[N];
-    jacobi_eigh<T, N, true>(m, v, w);
+    GM_UNROLL for (int i = 0; i < N; ++i)
+      GM_UNROLL for (int j = 0; j < N; ++j) st.wm[i * N + j] = (j >= i) ? a[j * N + i] : (T)0;
+    jacobi_eigh<T, N, true, false>(m, st.wm, w);
     T phi = (T)0;
     GM_UNROLL for (int k = 0; k < N; ++k) {
       T wc = clampv(w[k], wmin, wmax);
       T lg = Num<T>::log(wc);
       phi += lg * lg;
-      T c = (T)2 * lg / wc;
-      cy[k] = c;
-      cx[k] = -c * w[k];
+      T c = Num<T>::div_fast(lg + lg, wc);
+      st.cy[k] = c;
+      st.cx[k] = -c * w[k];
     }
-    T wm[E];
-    lowerT_mul<T, N>(a, v, wm);
-    wdwt<T, N>(wm, cx, gx);
-    wdwt<T, N>(wm, cy, gy);
     return clamp_min(phi, wmin);
+  }
+  GM_HD T eig_forward_prepped(const T (&ap)[kPrepSize], const T (&y)[E], EigState& st) const {
+    T a[E];
+    GM_UNROLL for (int i = 0; i < N; ++i)
+      GM_UNROLL for (int j = 0; j < N; ++j) a[i * N + j] = (j <= i) ? ap[i * (i + 1) / 2 + j] : (T)0;
+    return eig_forward(a, y, st);
+  }
+  GM_HD void eig_backward(const EigState& st, T wgt, T (&gx)[E], T (&gy)[E]) const {
+    T cx[N], cy[N];
+    GM_UNROLL for (int k = 0; k < N; ++k) { cx[k] = st.cx[k] * wgt; cy[k] = st.cy[k] * wgt; }
+    wdwt<T, N>(st.wm, cx, gx);
+    wdwt<T, N>(st.wm, cy, gy);
   }
 
   // Returns d2 and fills gx = d(d2)/dx, gy = d(d2)/dy (both symmetric).
@@ -238,22 +254,10 @@ struct SpdAI {
     congr_lower<T, N>(ic.a, y, m);
     T phi;
     if constexpr (!FAST_EIG && !FAST_CHOL) {
-      // W = L^-T V diagonalises both: W^T x W = I, W^T y W = diag(lambda).
-      T v[E], w[N], cx[N], cy[N];
-      jacobi_eigh<T, N, true>(m, v, w);
-      phi = (T)0;
-      GM_UNROLL for (int k = 0; k < N; ++k) {
-        T wc = clampv(w[k], wmin, wmax);
-        T lg = Num<T>::log(wc);
-        phi += lg * lg;
-        T c = (T)2 * lg / wc;
-        cy[k] = c;
-        cx[k] = -c * w[k];
-      }
-      T wm[E];
-      lowerT_mul<T, N>(ic.a, v, wm);
-      wdwt<T, N>(wm, cx, gx);
-      wdwt<T, N>(wm, cy, gy);
+      EigState st;
+      T d2 = eig_forward(ic.a, y, st);
+      eig_backward(st, (T)1, gx, gy);
+      return d2;
     } else {
       T g[E];  // sym(d phi / d m)
       if constexpr (FAST_EIG) {
@@ -310,8 +314,10 @@ struct SpdStein {
   static constexpr bool kCanPrep = false;
   static constexpr int kPrepSize = 1;
   T wmin, wmax;
+  struct EigState {};
   GM_HD void prep(const T (&)[E], T (&)[1]) const {}
-  GM_HD T dist2_grad_prepped(const T (&)[1], const T (&)[E], T (&)[E], T (&)[E]) const { return (T)0; }
+  GM_HD T eig_forward_prepped(const T (&)[1], const T (&)[E], EigState&) const { return (T)0; }
+  GM_HD void eig_backward(const EigState&, T, T (&)[E], T (&)[E]) const {}
 
   template <bool WANT_INV>
   GM_HD static T logdet_inv(const T (&x)[E], T (&inv)[E]) {
@@ -481,7 +487,9 @@ struct LossCfg {
   double alpha, eps;
 };
 
-template <typename T>
+// FAST: reciprocals through Num<T>::div_fast (fp32: MUFU.RCP, ~2 ulp) instead of IEEE division -- used by the
+// streaming training kernel, whose loss and gradient are checked at 1e-5 relative.
+template <typename T, bool FAST = false>
 GM_HD T loss_term(const LossCfg& c, T g, T m, T& dm) {
   if (c.kind == 1) {  // StressLoss: (m - g)^2
     T d = m - g;
@@ -492,15 +500,17 @@ GM_HD T loss_term(const LossCfg& c, T g, T m, T& dm) {
   T v = (T)0;
   dm = (T)0;
   if (c.inc_l1) {
-    T q = m / t - (T)1;
+    T rt = FAST ? Num<T>::div_fast((T)1, t) : (T)1 / t;
+    T q = FAST ? m * rt - (T)1 : m / t - (T)1;
     v += Num<T>::abs(q);
-    dm += sgn0(q) / t;
+    dm += sgn0(q) * rt;
   }
   if (c.inc_l2) {
     T den = m + (T)c.eps;
-    T q = t / den - (T)1;
+    T rd = FAST ? Num<T>::div_fast((T)1, den) : (T)1 / den;
+    T q = FAST ? t * rd - (T)1 : t / den - (T)1;
     v += Num<T>::abs(q);
-    dm -= sgn0(q) * t / (den * den);
+    dm -= FAST ? sgn0(q) * t * rd * rd : sgn0(q) * t / (den * den);
   }
   return v;
 }

@@ -35,30 +35,51 @@ template <> struct Num<float> {
     return 1.0f / sqrtf(x);
 #endif
   }
-  // Rotation-parameter math for the Jacobi sweeps.  The rotation ANGLE may be inexact (it only affects the
-  // convergence rate), the pair (c, s) must be orthonormal to rounding: approximate sqrt / divide (MUFU.RSQ,
-  // MUFU.RCP, no IEEE slow paths) for tan(theta), one Newton step on rsqrt for c.
-  GM_HD static float rot_sqrt(float x) {
+  // Raw special-function-unit approximations (MUFU.RSQ / MUFU.RCP, <= 2 ulp, flush-to-zero, no denormal or
+  // IEEE slow paths): one instruction each instead of the 4-10 the C library forms expand to.
+  GM_HD static float rsqrt_raw(float x) {
 #ifdef __CUDA_ARCH__
-    return x > 0.f ? x * rsqrtf(x) : 0.f;
-#else
-    return sqrtf(x);
-#endif
-  }
-  GM_HD static float rot_div(float a, float b) {
-#ifdef __CUDA_ARCH__
-    return __fdividef(a, b);
-#else
-    return a / b;
-#endif
-  }
-  GM_HD static float rot_rsqrt(float x) {
-#ifdef __CUDA_ARCH__
-    float r = rsqrtf(x);
-    return r * (1.5f - 0.5f * x * r * r);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / sqrtf(x);
 #endif
+  }
+  GM_HD static float rcp_raw(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+  }
+  // a / b to ~2 ulp; for coefficients whose consumers tolerate 1e-6 relative error (never for values the
+  // reference clamps or compares).
+  GM_HD static float div_fast(float a, float b) { return a * rcp_raw(b); }
+  // sign(d) * v with sign(+-0) = +-1: one LOP3
+  GM_HD static float mul_sign(float v, float d) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(d) & 0x80000000u));
+#else
+    return std::signbit(d) ? -v : v;
+#endif
+  }
+  // Jacobi rotation (c, s, t = s/c) annihilating a_pq given d = a_qq - a_pp.  The rotation ANGLE may be inexact
+  // (it only affects the convergence rate) but (c, s) must be orthonormal to rounding: approximate rsqrt / rcp for
+  // tan(theta), one Newton step on the rsqrt that normalises (c, s).
+  //   t = sgn(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2))   (smaller root; a_pq == 0 -> t == 0)
+  GM_HD static void rotation(float d, float apq, float& t, float& c, float& s) {
+    float two = apq + apq;
+    float h2 = fmaxf(fmaf(two, two, d * d), FLT_MIN);
+    float h = h2 * rsqrt_raw(h2);
+    float den = fabsf(d) + h;
+    t = mul_sign(two, d) * rcp_raw(den);
+    float x = fmaf(t, t, 1.0f);
+    float r = rsqrt_raw(x);
+    c = r * fmaf(-0.5f * x, r * r, 1.5f);
+    s = t * c;
   }
   GM_HD static float log(float x) { return logf(x); }
   GM_HD static float log1p(float x) { return log1pf(x); }
@@ -80,9 +101,14 @@ template <> struct Num<double> {
   static constexpr double tiny = DBL_MIN;
   GM_HD static double sqrt(double x) { return ::sqrt(x); }
   GM_HD static double rsqrt(double x) { return 1.0 / ::sqrt(x); }
-  GM_HD static double rot_sqrt(double x) { return ::sqrt(x); }
-  GM_HD static double rot_div(double a, double b) { return a / b; }
-  GM_HD static double rot_rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  GM_HD static double div_fast(double a, double b) { return a / b; }
+  GM_HD static void rotation(double d, double apq, double& t, double& c, double& s) {
+    double two = apq + apq;
+    double den = fabs(d) + ::sqrt(d * d + two * two);
+    t = (den > 0.0) ? (d >= 0.0 ? two : -two) / den : 0.0;
+    c = 1.0 / ::sqrt(t * t + 1.0);
+    s = t * c;
+  }
   GM_HD static double log(double x) { return ::log(x); }
   GM_HD static double log1p(double x) { return ::log1p(x); }
   GM_HD static double exp(double x) { return ::exp(x); }
@@ -249,53 +275,67 @@ template <typename T> struct JacobiCfg;
 template <> struct JacobiCfg<float> { static constexpr int max_sweeps = 10; };
 template <> struct JacobiCfg<double> { static constexpr int max_sweeps = 16; };
 
-template <typename T, int N, bool WANT_V = true>
+// Rotation schedule of one sweep (inside jacobi_eigh).  N == 4 uses the round-robin ("tournament") order (0,1)(2,3) (0,2)(1,3)
+// (0,3)(1,2): the two rotations of a round touch disjoint rows/columns, so their parameter chains are independent
+// (instruction-level parallelism 2), and it needs fewer sweeps than the row-cyclic order on the pair workload
+// (tools/eig_lab.cu: 92 % vs 52 % of 4x4 pair matrices done after 3 sweeps).  Other sizes: row-cyclic.
+// No sweep before this one is ever the last on non-trivial input (eig_lab: < 0.1 % of 4x4 matrices converge in
+// fewer than 3 sweeps), so the convergence test is skipped for them; an already diagonal matrix just sees identity
+// rotations.
+template <int N>
+struct JacobiFirstCheck { static constexpr int value = N >= 4 ? 3 : (N == 3 ? 2 : 1); };
+
+// INIT_V: start from v = I (eigenvectors).  With INIT_V == false the caller passes any matrix B in v and gets
+// B * V back -- the pair kernels pass L^-T so that W = L^-T V comes out of the sweeps directly.
+template <typename T, int N, bool WANT_V = true, bool INIT_V = true>
 GM_HD void jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N]) {
-  if (WANT_V) {
+  if (WANT_V && INIT_V) {
     GM_UNROLL for (int i = 0; i < N; ++i)
       GM_UNROLL for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? (T)1 : (T)0;
   }
   if (N == 1) { w[0] = a[0]; return; }
-  for (int sweep = 0; sweep < JacobiCfg<T>::max_sweeps; ++sweep) {
-    T off = (T)0, dia = (T)0;
-    GM_UNROLL for (int i = 0; i < N; ++i) {
-      dia += a[i * N + i] * a[i * N + i];
-      GM_UNROLL for (int j = i + 1; j < N; ++j) off += a[i * N + j] * a[i * N + j];
-    }
-    // converged when the off-diagonal mass is below rounding level of the diagonal
-    if (off <= (Num<T>::eps * Num<T>::eps * (T)0.0625) * dia || off < Num<T>::tiny) break;
-    GM_UNROLL for (int p = 0; p < N - 1; ++p) {
-      GM_UNROLL for (int q = p + 1; q < N; ++q) {
-        T apq = a[p * N + q];
-        T d = a[q * N + q] - a[p * N + p];
-        // t = tan(theta), smaller root of t^2 + 2 t cot(2 theta) - 1 = 0, branch-free:
-        // t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)); apq == 0 -> t == 0.
-        T two_apq = apq + apq;
-        T den = Num<T>::abs(d) + Num<T>::rot_sqrt(d * d + two_apq * two_apq);
-        T t = (den > (T)0) ? Num<T>::rot_div(d >= (T)0 ? two_apq : -two_apq, den) : (T)0;
-        T c = Num<T>::rot_rsqrt(t * t + (T)1);
-        T s = t * c;
-        a[p * N + p] -= t * apq;
-        a[q * N + q] += t * apq;
-        a[p * N + q] = (T)0;
-        a[q * N + p] = (T)0;
-        GM_UNROLL for (int r = 0; r < N; ++r) {
-          if (r != p && r != q) {
-            T arp = a[r * N + p], arq = a[r * N + q];
-            T nrp = c * arp - s * arq;
-            T nrq = s * arp + c * arq;
-            a[r * N + p] = nrp; a[p * N + r] = nrp;
-            a[r * N + q] = nrq; a[q * N + r] = nrq;
-          }
-        }
-        if (WANT_V) {
-          GM_UNROLL for (int r = 0; r < N; ++r) {
-            T vrp = v[r * N + p], vrq = v[r * N + q];
-            v[r * N + p] = c * vrp - s * vrq;
-            v[r * N + q] = s * vrp + c * vrq;
-          }
-        }
+  auto rotate = [&](const int p, const int q) {
+    T apq = a[p * N + q];
+    T t, c, s;
+    Num<T>::rotation(a[q * N + q] - a[p * N + p], apq, t, c, s);
+    a[p * N + p] -= t * apq;
+    a[q * N + q] += t * apq;
+    a[p * N + q] = (T)0;
+    a[q * N + p] = (T)0;
+    GM_UNROLL for (int r = 0; r < N; ++r) {
+      if (r != p && r != q) {
+        T arp = a[r * N + p], arq = a[r * N + q];
+        T nrp = c * arp - s * arq;
+        T nrq = s * arp + c * arq;
+        a[r * N + p] = nrp; a[p * N + r] = nrp;
+        a[r * N + q] = nrq; a[q * N + r] = nrq;
       }
+    }
+    if (WANT_V) {
+      GM_UNROLL for (int r = 0; r < N; ++r) {
+        T vrp = v[r * N + p], vrq = v[r * N + q];
+        v[r * N + p] = c * vrp - s * vrq;
+        v[r * N + q] = s * vrp + c * vrq;
+      }
+    }
+  };
+  for (int sweep = 0; sweep < JacobiCfg<T>::max_sweeps; ++sweep) {
+    if (sweep >= JacobiFirstCheck<N>::value) {
+      T off = (T)0, dia = (T)0;
+      GM_UNROLL for (int i = 0; i < N; ++i) {
+        dia += a[i * N + i] * a[i * N + i];
+        GM_UNROLL for (int j = i + 1; j < N; ++j) off += a[i * N + j] * a[i * N + j];
+      }
+      // converged when the off-diagonal mass is below rounding level of the diagonal
+      if (off <= (Num<T>::eps * Num<T>::eps * (T)0.0625) * dia || off < Num<T>::tiny) break;
+    }
+    if constexpr (N == 4) {
+      rotate(0, 1); rotate(2, 3);
+      rotate(0, 2); rotate(1, 3);
+      rotate(0, 3); rotate(1, 2);
+    } else {
+      GM_UNROLL for (int p = 0; p < N - 1; ++p)
+        GM_UNROLL for (int q = p + 1; q < N; ++q) rotate(p, q);
     }
   }
   GM_UNROLL for (int i = 0; i < N; ++i) w[i] = a[i * N + i];
@@ -324,12 +364,8 @@ GM_HD void jacobi_svd(T (&a)[R * C], T (&v)[C * C], T (&s)[C]) {
         if (Num<T>::abs(gamma) > (Num<T>::eps * (T)0.25) * Num<T>::sqrt(alpha * beta) &&
             Num<T>::abs(gamma) > Num<T>::tiny) {
           rotated = true;
-          T d = beta - alpha;
-          T two_g = gamma + gamma;
-          T den = Num<T>::abs(d) + Num<T>::rot_sqrt(d * d + two_g * two_g);
-          T t = Num<T>::rot_div(d >= (T)0 ? two_g : -two_g, den);
-          T c = Num<T>::rot_rsqrt(t * t + (T)1);
-          T sn = t * c;
+          T t, c, sn;
+          Num<T>::rotation(beta - alpha, gamma, t, c, sn);
           GM_UNROLL for (int r = 0; r < R; ++r) {
             T x = a[r * C + p], y = a[r * C + q];
             a[r * C + p] = c * x - sn * y;

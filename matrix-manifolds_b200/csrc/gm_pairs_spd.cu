@@ -162,6 +162,22 @@ struct PairCursor {
   }
 };
 
+// Raw per-pair scalar carried through the pipeline: the bits of a T (explicit target / upstream gradient) or, for
+// hop-count targets, the integer hop count.  Hop counts are mapped to (h^2)/max -- dataset.py:11-12, IEEE division so
+// that the value is bit-identical to the reference's -- through a 256-entry table built once per block (HOPS_U8) or
+// on the fly (HOPS_U16).
+template <typename T> struct RawScalar;
+template <> struct RawScalar<float> {
+  using type = unsigned;
+  __device__ __forceinline__ static unsigned pack(float v) { return __float_as_uint(v); }
+  __device__ __forceinline__ static float unpack(unsigned r) { return __uint_as_float(r); }
+};
+template <> struct RawScalar<double> {
+  using type = unsigned long long;
+  __device__ __forceinline__ static unsigned long long pack(double v) { return (unsigned long long)__double_as_longlong(v); }
+  __device__ __forceinline__ static double unpack(unsigned long long r) { return __longlong_as_double((long long)r); }
+};
+
 template <class Op, typename T, int KMODE, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __restrict__ xb,
@@ -169,25 +185,50 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
                        T* __restrict__ out_d2, TargetSpec tg, LossCfg lc, T scale_sp, double* __restrict__ acc,
                        long long chunk) {
   constexpr int E = Op::E;
+  constexpr int N = GM_N;
+  constexpr int EU = N * (N + 1) / 2;  // gradients are symmetric: the run-length accumulator keeps the upper triangle
   using Stage = RowStage<T, E>;
+  using Raw = RawScalar<T>;
+  using raw_t = typename Raw::type;
   extern __shared__ __align__(16) char stage_mem[];
   __shared__ double red[2][4];
+  __shared__ T hop_lut[256];
   const int tid = threadIdx.x, lane = tid & 31;
   const unsigned full = 0xffffffffu;
   const long long warp_id = (long long)blockIdx.x * 4 + (tid >> 5);
   const long long k0 = warp_id * chunk;
   const long long kend = (k0 + chunk < ps.P) ? k0 + chunk : ps.P;
+  const bool hops8 = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_U8;
+  const bool hops16 = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_U16;
+  if (hops8) {
+    for (int h = tid; h < 256; h += 128) hop_lut[h] = ((T)h * (T)h) / (T)tg.max_sq;
+    __syncthreads();
+  }
 
   // ---- pipeline registers -------------------------------------------------------------------------------------
   PairCursor cur;            // pair being computed / staged
   long long ra0 = -1, rb0 = -1;  // rows of the pair computed in this iteration (staged in `stage`)
   long long ra1 = -1, rb1 = -1;  // rows of the next pair (indices loaded, rows not yet issued)
-  T tg0 = (T)0, tg1 = (T)0;      // target (K_FUSED) or upstream gradient (K_BWD) of those pairs
+  raw_t tg0 = 0;                 // target (K_FUSED) or upstream gradient (K_BWD) of the current pair, raw
   int stage = 0;
 
-  auto fetch_scalar = [&](long long k, long long ra, long long rb) -> T {
-    if constexpr (KMODE == K_BWD) return gout[k];
-    else return fetch_target<T>(tg, k, ra, rb);
+  auto fetch_scalar = [&](long long k, long long ra, long long rb) -> raw_t {
+    if constexpr (KMODE == K_BWD) {
+      return Raw::pack(gout[k]);
+    } else {
+      if (hops8) return (raw_t)((const unsigned char*)tg.data)[k];
+      if (hops16) return (raw_t)((const unsigned short*)tg.data)[k];
+      return Raw::pack(fetch_target<T>(tg, k, ra, rb));
+    }
+  };
+  auto scalar_value = [&](raw_t r) -> T {
+    if constexpr (KMODE == K_BWD) {
+      return Raw::unpack(r);
+    } else {
+      if (hops8) return hop_lut[r];
+      if (hops16) { T h = (T)r; return (h * h) / (T)tg.max_sq; }
+      return Raw::unpack(r);
+    }
   };
 
   cur.init(ps, k0 + lane);
@@ -207,16 +248,24 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   // ---- per-lane running state -------------------------------------------------------------------------------------
   double loss_v = 0.0, gd2_v = 0.0;
   long long acc_row = -1;  // warp-uniform row whose gradient is being accumulated in gacc (or -1)
-  T gacc[E];
-  GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = (T)0;
+  T gacc[EU];
+  GM_UNROLL for (int e = 0; e < EU; ++e) gacc[e] = (T)0;
   long long prep_row = -1;
   T ap[Op::kPrepSize];
 
   auto flush = [&]() {
     if (acc_row >= 0) {
-      GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = warp_sum(gacc[e]);
-      if (lane == 0) atomic_add_row<T, E>(ga, acc_row, gacc);
-      GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = (T)0;
+      GM_UNROLL for (int e = 0; e < EU; ++e) gacc[e] = warp_sum(gacc[e]);
+      if (lane == 0) {
+        T gfull[E];
+        GM_UNROLL for (int i = 0; i < N; ++i)
+          GM_UNROLL for (int j = i; j < N; ++j) {
+            gfull[i * N + j] = gacc[i * N - i * (i - 1) / 2 + (j - i)];
+            gfull[j * N + i] = gfull[i * N + j];
+          }
+        atomic_add_row<T, E>(ga, acc_row, gfull);
+      }
+      GM_UNROLL for (int e = 0; e < EU; ++e) gacc[e] = (T)0;
       acc_row = -1;
     }
   };
@@ -230,7 +279,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
       if (!Op::kCanPrep || ra0 != prep_row) Stage::read(stage_mem, stage, 0, tid, x);
     }
     // (2) stage the next pair: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
-    T tgn = (T)0;
+    raw_t tgn = 0;
     if (v1) {
       Stage::issue(stage_mem, stage ^ 1, 0, tid, xa + ra1 * E);
       Stage::issue(stage_mem, stage ^ 1, 1, tid, xb + rb1 * E);
@@ -246,26 +295,30 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     // (4) the math
     T gx[E], gy[E];
     if (v0) {
-      T d2;
+      T d2, w;
+      [[maybe_unused]] typename Op::EigState st;
       if constexpr (Op::kCanPrep) {
         if (ra0 != prep_row) { op.prep(x, ap); prep_row = ra0; }
-        d2 = op.dist2_grad_prepped(ap, y, gx, gy);
+        d2 = op.eig_forward_prepped(ap, y, st);
       } else {
         d2 = op.dist2_grad(x, y, gx, gy);
       }
-      T w;
       if constexpr (KMODE == K_BWD) {
-        w = coef * tg0;
+        w = coef * scalar_value(tg0);
       } else {
         T m = scale_sp * d2;
         T dm;
-        T lv = loss_term<T>(lc, tg0, m, dm);
+        T lv = loss_term<T, true>(lc, scalar_value(tg0), m, dm);
         loss_v += (double)lv;
         gd2_v += (double)dm * (double)d2;
         w = dm * scale_sp;
         if (out_d2) out_d2[cur.k] = d2;
       }
-      GM_UNROLL for (int e = 0; e < E; ++e) { gx[e] *= w; gy[e] *= w; }
+      if constexpr (Op::kCanPrep) {
+        op.eig_backward(st, w, gx, gy);  // loss weight folded into the N eigen-coefficients
+      } else {
+        GM_UNROLL for (int e = 0; e < E; ++e) { gx[e] *= w; gy[e] *= w; }
+      }
       atomic_add_row<T, E>(gb, rb0, gy);
     }
     // (5) first-endpoint gradient: run-length accumulation in registers
@@ -273,12 +326,14 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
       long long r0 = __shfl_sync(full, ra0, 0);
       bool uniform = __all_sync(full, v0 && ra0 == r0);
       if (uniform && r0 == acc_row) {
-        GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] += gx[e];
+        GM_UNROLL for (int i = 0; i < N; ++i)
+          GM_UNROLL for (int j = i; j < N; ++j) gacc[i * N - i * (i - 1) / 2 + (j - i)] += gx[i * N + j];
       } else {
         flush();
         if (uniform) {
           acc_row = r0;
-          GM_UNROLL for (int e = 0; e < E; ++e) gacc[e] = gx[e];
+          GM_UNROLL for (int i = 0; i < N; ++i)
+            GM_UNROLL for (int j = i; j < N; ++j) gacc[i * N - i * (i - 1) / 2 + (j - i)] = gx[i * N + j];
         } else if (v0) {
           atomic_add_row<T, E>(ga, ra0, gx);
         }
