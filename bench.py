@@ -77,7 +77,8 @@ def scale_free_edges(n, m, seed):
 
 
 def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
-    """[(I int32, J int32, hops uint8)] pinned host tensors + max hop^2, targets from the BFS kernel."""
+    """[(I int32, J int32, hops uint8, sources int32, offsets int64)] pinned host tensors + max hop^2; hop targets
+    come from the multi-source BFS kernel.  (sources, offsets) is the source-grouped form of I."""
     from graphembed.data import bfs_levels, edges_to_csr
     from graphembed import _lib as L
     import ctypes
@@ -104,7 +105,9 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
         L.check(rc, 'gm_gather_levels')
         max_h = max(max_h, int(levels.max().item()))
         assert int(hops.min().item()) >= 1 and int(hops.max().item()) < 255
-        batches.append((I.pin_memory(), J.pin_memory(), hops.cpu().pin_memory()))
+        offsets = (torch.arange(n_src + 1, dtype=torch.int64) * per_src)
+        batches.append((I.pin_memory(), J.pin_memory(), hops.cpu().pin_memory(), src.contiguous().pin_memory(),
+                        offsets.pin_memory()))
         del levels
     return batches, float(max_h * max_h)
 
@@ -236,7 +239,7 @@ def main():
         torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MAX)
         max_sq = float(m.item())
     trainer = PairTrainer(emb, opt, QuotientLoss(), max_hops_sq=max_sq, alpha=1.0, process_group=pg)
-    dev_batches = [tuple(t.to(dev) for t in b) for b in batches]
+    dev_batches = [tuple(t.to(dev) for t in b[:3]) for b in batches]
 
     def barrier():
         if pg is not None:
@@ -280,16 +283,23 @@ def main():
     final_loss = float(loss.item())
 
     # ---- end-to-end timing from pinned host buffers ----------------------------------------------------------------
+    # source-grouped upload (sources, offsets, j, hops): 5 B/pair over PCIe; the next batch is uploaded on a second
+    # stream while this one computes; every step ends with a device->host read of the loss
+    def grouped(b):
+        return (b[3], b[4], b[1], b[2])
+
+    nb = len(batches)
     for k in range(2):
-        trainer.step_host(*batches[k % len(batches)], epoch=1, next_batch=batches[(k + 1) % len(batches)])
+        trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1, next_batch=grouped(batches[(k + 1) % nb]))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        trainer.step_host(*batches[k % len(batches)], epoch=1, next_batch=batches[(k + 1) % len(batches)])
+        trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1, next_batch=grouped(batches[(k + 1) % nb]))
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]))
 
     if pg is not None:
         t = torch.tensor([ms, ms_e2e, pair_ms], device=dev, dtype=torch.float64)
@@ -306,6 +316,10 @@ def main():
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     achieved = P * BYTES_PER_PAIR / (pair_ms * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json')
+    if os.path.isfile(tpath) and P == (1 << 24) and N == 2_000_000:
+        traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
     total_pairs = P * world * args.steps
     line = {
         'metric': METRIC, 'value': total_pairs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -314,18 +328,20 @@ def main():
         'config': {
             'workload': 'BASELINE config 5: synthetic scale-free graph, SPD 4x4 affine-invariant, sampled pairs '
                         '(1024 BFS sources x targets) per step, QuotientLoss, RiemannianAdam(lr .01, clip 100, exact)',
-            'nodes': N, 'pairs_per_step_per_gpu': P, 'parallelism': f'pair-sharded replicas x{world}'
-            + (' + NCCL all-reduce of the (N,4,4) gradient' if world > 1 else ''),
+            'nodes': N, 'pairs_per_step_per_gpu': P, 'parallelism': f'pair-sharded x{world}'
+            + (' + NCCL reduce-scatter of the (N,4,4) gradient, owner-rank optimizer update, all-gather of the points'
+               if trainer.shards is not None else (' + NCCL all-reduce of the (N,4,4) gradient' if world > 1 else '')),
             'l2_policy': f'inputs larger than L2: {len(batches)} distinct batches of {P * 9 / 1e6:.0f} MB cycled, '
                          f'{N * 64 / 1e6:.0f} MB embedding + {N * 64 / 1e6:.0f} MB gradient touched at random',
             'final_loss': final_loss,
         },
-        'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': P * 9,
+        'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps,
-                'api': 'graphembed.engine.PairTrainer.step_host (pinned host int32 i, int32 j, uint8 hops)'},
+                'api': 'graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
+                       'int32 j, uint8 hops; per rank)'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'kernel': 'spd_pair_kernel<SpdAI<float,4>,K_FUSED>',
+                     'traffic': traffic, 'kernel': 'spd_pair_stream_kernel<SpdAI<float,4>,K_FUSED>',
                      'kernel_ms': pair_ms, 'bytes_per_pair': BYTES_PER_PAIR, 'peak_source': peak_src},
         'clocks': clock_info,
     }

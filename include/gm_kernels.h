@@ -208,6 +208,13 @@ int gm_levels_to_dense_targets(int32_t level_bytes, const void* levels, int32_t 
 int gm_gather_levels(int32_t level_bytes, const void* levels, int32_t N, const int32_t* src_slot, const int32_t* col,
                      int64_t P, void* out, gm_stream_t stream);
 
+/* Source-grouped (CSR-like) pair lists -> explicit first-endpoint index vector for gm_pairs_t LIST mode:
+ * out_i[k] = group_row[g] for offsets[g] <= k < offsets[g+1], g < G; offsets[G] == P.  The grouped form is what a
+ * per-source sampler produces (BASELINE config 5: S BFS sources x targets) and is 4 bytes/pair cheaper to upload
+ * than the (i, j) lists base.py:62-63 builds with triu_indices. */
+int gm_expand_groups(const int32_t* group_row, const int64_t* offsets, int32_t G, int32_t* out_i, int64_t P,
+                     gm_stream_t stream);
+
 /* ---- introspection ------------------------------------------------------------------------------------------- */
 const char* gm_version(void);
 /* 1 if (kind, n, p, dtype, flags) has a compiled kernel */

@@ -271,10 +271,7 @@ int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, cons
   a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
   a.wmin = man->wmin; a.wmax = man->wmax;
   a.op = -1;
-  a.oc.kind = opt->kind; a.oc.exact = opt->exact; a.oc.has_clip = opt->has_clip; a.oc.step = opt->step;
-  a.oc.has_momentum = opt->has_momentum; a.oc.first_step = opt->first_step;
-  a.oc.lr = opt->lr; a.oc.beta1 = opt->beta1; a.oc.beta2 = opt->beta2; a.oc.momentum = opt->momentum;
-  a.oc.dampening = opt->dampening; a.oc.max_grad_norm = opt->max_grad_norm; a.oc.eps = opt->eps;
+  a.oc = make_optim_cfg(opt);
   a.grassmann_retr_qr = opt->grassmann_retr_qr;
   a.x = x; a.u = grad; a.buf1 = buf1; a.buf2 = (opt->kind == GM_OPT_RADAM) ? buf2 : nullptr;
   if (opt->kind == GM_OPT_RSGD && !opt->has_momentum) a.buf1 = nullptr;

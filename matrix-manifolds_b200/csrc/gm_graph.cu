@@ -157,6 +157,32 @@ __global__ void dense_targets_kernel(const L* __restrict__ levels, long long tot
   dense[k] = (h * h) / max_sq;  // pdists.pow(2) then div_(max): data/dataset.py:11-12
 }
 
+// out[k] = row[g] for offsets[g] <= k < offsets[g+1]: 4 consecutive k per thread (one 16-byte store), binary search
+// for the first, linear walk for the rest (empty groups are skipped).
+__global__ void expand_groups_kernel(const int* __restrict__ row, const long long* __restrict__ offsets, int G,
+                                     int* __restrict__ out, long long P) {
+  long long k = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  if (k >= P) return;
+  int lo = 0, hi = G;  // last g with offsets[g] <= k
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) <= k) lo = mid; else hi = mid;
+  }
+  int g = lo;
+  int v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    while (g + 1 < G && k + e >= __ldg(offsets + g + 1)) ++g;
+    v[e] = __ldg(row + g);
+  }
+  if (k + 3 < P && ((reinterpret_cast<size_t>(out + k) & 15) == 0)) {
+    *reinterpret_cast<int4*>(out + k) = make_int4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (k + e < P) out[k + e] = v[e];
+  }
+}
+
 template <typename L>
 __global__ void gather_levels_kernel(const L* __restrict__ levels, int N, const int* __restrict__ slot,
                                      const int* __restrict__ col, long long P, L* __restrict__ out) {
@@ -243,6 +269,20 @@ int gm_gather_levels(int32_t level_bytes, const void* levels, int32_t N, const i
   if (blocks > 0x7fffffffLL) return GM_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   GM_LEVEL_SWITCH(level_bytes, (gather_levels_kernel<L><<<(unsigned)blocks, 256, 0, st>>>((const L*)levels, N, src_slot, col, P, (L*)out)));
+  note_launch();
+  return check_launch();
+}
+
+int gm_expand_groups(const int32_t* group_row, const int64_t* offsets, int32_t G, int32_t* out_i, int64_t P,
+                     gm_stream_t stream) {
+  if (G < 0 || P < 0) return GM_EINVAL;
+  if (P == 0) return GM_OK;
+  if (G == 0) return GM_EINVAL;
+  if (!group_row || !offsets || !out_i) return GM_ENULL;
+  long long blocks = ((P + 3) / 4 + 255) / 256;
+  if (blocks > 0x7fffffffLL) return GM_EINVAL;
+  expand_groups_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(group_row, (const long long*)offsets, G,
+                                                                        out_i, P);
   note_launch();
   return check_launch();
 }

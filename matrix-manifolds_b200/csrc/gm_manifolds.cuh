@@ -189,9 +189,17 @@ struct SpdAI {
       T v[E], w[N];
       jacobi_eigh<T, N, false>(m, v, w);
       phi = (T)0;
-      GM_UNROLL for (int k = 0; k < N; ++k) {
-        T lg = Num<T>::log(clampv(w[k], wmin, wmax));
-        phi += lg * lg;
+      if constexpr (FAST_CHOL) {
+        GM_UNROLL for (int k = 0; k < N; ++k) {
+          T lg = Num<T>::log(clampv(w[k], wmin, wmax));
+          phi += lg * lg;
+        }
+      } else {  // same arithmetic as eig_forward, so that forward-only and fused launches agree bit for bit
+        const T lo = Num<T>::max(wmin, Num<T>::tiny), hi = Num<T>::min(wmax, Num<T>::huge);
+        GM_UNROLL for (int k = 0; k < N; ++k) {
+          T lg = Num<T>::log_pos(clampv(w[k], lo, hi));
+          phi += lg * lg;
+        }
       }
     }
     return clamp_min(phi, wmin);
@@ -223,9 +231,12 @@ struct SpdAI {
       GM_UNROLL for (int j = 0; j < N; ++j) st.wm[i * N + j] = (j >= i) ? a[j * N + i] : (T)0;
     jacobi_eigh<T, N, true, false>(m, st.wm, w);
     T phi = (T)0;
+    // log_pos needs a positive normal finite argument: guaranteed by the clamp for every sane [wmin, wmax]
+    // (default [1e-8, 1e8]); a caller-supplied wmin below the smallest normal is raised to it.
+    const T lo = Num<T>::max(wmin, Num<T>::tiny), hi = Num<T>::min(wmax, Num<T>::huge);
     GM_UNROLL for (int k = 0; k < N; ++k) {
-      T wc = clampv(w[k], wmin, wmax);
-      T lg = Num<T>::log(wc);
+      T wc = clampv(w[k], lo, hi);
+      T lg = Num<T>::log_pos(wc);
       phi += lg * lg;
       T c = Num<T>::div_fast(lg + lg, wc);
       st.cy[k] = c;
@@ -252,7 +263,7 @@ struct SpdAI {
     ic.run(x);
     T m[E];
     congr_lower<T, N>(ic.a, y, m);
-    T phi;
+    T phi = (T)0;
     if constexpr (!FAST_EIG && !FAST_CHOL) {
       EigState st;
       T d2 = eig_forward(ic.a, y, st);

@@ -17,6 +17,9 @@
 #include <float.h>
 
 #define GM_HD __host__ __device__ __forceinline__
+#ifndef GM_ROT_NEWTON
+#define GM_ROT_NEWTON 1
+#endif
 
 namespace gm {
 
@@ -27,6 +30,7 @@ template <typename T> struct Num;
 template <> struct Num<float> {
   static constexpr float eps = FLT_EPSILON;
   static constexpr float tiny = FLT_MIN;
+  static constexpr float huge = FLT_MAX;
   GM_HD static float sqrt(float x) { return sqrtf(x); }
   GM_HD static float rsqrt(float x) {
 #ifdef __CUDA_ARCH__
@@ -58,6 +62,15 @@ template <> struct Num<float> {
   // a / b to ~2 ulp; for coefficients whose consumers tolerate 1e-6 relative error (never for values the
   // reference clamps or compares).
   GM_HD static float div_fast(float a, float b) { return a * rcp_raw(b); }
+  // 1 / x to <= 1 ulp: MUFU.RCP + one Newton step (no IEEE slow path; x normal, finite, non-zero)
+  GM_HD static float recip(float x) {
+#ifdef __CUDA_ARCH__
+    float r = rcp_raw(x);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+  }
   // sign(d) * v with sign(+-0) = +-1: one LOP3
   GM_HD static float mul_sign(float v, float d) {
 #ifdef __CUDA_ARCH__
@@ -78,10 +91,39 @@ template <> struct Num<float> {
     t = mul_sign(two, d) * rcp_raw(den);
     float x = fmaf(t, t, 1.0f);
     float r = rsqrt_raw(x);
+#if GM_ROT_NEWTON
     c = r * fmaf(-0.5f * x, r * r, 1.5f);
+#else
+    c = r;
+#endif
     s = t * c;
   }
   GM_HD static float log(float x) { return logf(x); }
+  // log(x) for x that is positive, normal and finite or NaN -- what remains after the reference's eigenvalue clamp
+  // to [wmin, wmax] (spd.py:163-169).  Same scheme as logf (x = 2^e m, m in [2/3, 4/3), log m = f + f^2 g(f),
+  // f = m - 1, g a degree-8 near-minimax fit; <= 1.3 ulp over the range) minus the denormal / zero / infinity
+  // handling logf carries: 17 instructions instead of ~33.  NaN stays NaN.
+  GM_HD static float log_pos(float x) {
+#ifdef __CUDA_ARCH__
+    int ix = __float_as_int(x);
+    int e = (ix - 0x3f2aaaab) & 0xff800000;
+    float m = fmaf(x, 0.0f, __int_as_float(ix - e));  // x * 0 keeps a NaN input alive
+    float f = m - 1.0f;
+    float g = -0.12734152376651764f;
+    g = fmaf(g, f, 0.13756538927555084f);
+    g = fmaf(g, f, -0.12219617515802383f);
+    g = fmaf(g, f, 0.1405421793460846f);
+    g = fmaf(g, f, -0.16678093373775482f);
+    g = fmaf(g, f, 0.2000732272863388f);
+    g = fmaf(g, f, -0.24999839067459106f);
+    g = fmaf(g, f, 0.33333271741867065f);
+    g = fmaf(g, f, -0.5f);
+    float r = fmaf(f, f * g, f);
+    return fmaf((float)e, 1.1920928955078125e-07f * 0.693147180559945309f, r);
+#else
+    return logf(x);
+#endif
+  }
   GM_HD static float log1p(float x) { return log1pf(x); }
   GM_HD static float exp(float x) { return expf(x); }
   GM_HD static float acos(float x) { return acosf(x); }
@@ -99,9 +141,11 @@ template <> struct Num<float> {
 template <> struct Num<double> {
   static constexpr double eps = DBL_EPSILON;
   static constexpr double tiny = DBL_MIN;
+  static constexpr double huge = DBL_MAX;
   GM_HD static double sqrt(double x) { return ::sqrt(x); }
   GM_HD static double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   GM_HD static double div_fast(double a, double b) { return a / b; }
+  GM_HD static double recip(double x) { return 1.0 / x; }
   GM_HD static void rotation(double d, double apq, double& t, double& c, double& s) {
     double two = apq + apq;
     double den = fabs(d) + ::sqrt(d * d + two * two);
@@ -110,6 +154,7 @@ template <> struct Num<double> {
     s = t * c;
   }
   GM_HD static double log(double x) { return ::log(x); }
+  GM_HD static double log_pos(double x) { return ::log(x); }
   GM_HD static double log1p(double x) { return ::log1p(x); }
   GM_HD static double exp(double x) { return ::exp(x); }
   GM_HD static double acos(double x) { return ::acos(x); }

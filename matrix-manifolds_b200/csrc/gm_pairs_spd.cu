@@ -130,11 +130,10 @@ struct RowStage {
   }
 };
 
-// pair cursor of one lane: walks k, k+32, k+64, ... inside [k, kend)
+// TRIU position of one lane's look-ahead pair: walks k, k+32, k+64, ... (LIST pairs need no state beyond k)
 struct PairCursor {
-  long long k, a, pos;  // TRIU: row a, position inside the row
+  long long a, pos;  // TRIU: row a, position inside the row
   __device__ __forceinline__ void init(const PairSpec& ps, long long k0) {
-    k = k0;
     if (ps.mode == GM_PAIRS_TRIU && k0 < ps.P) {
       long long b;
       triu_decode(k0, ps.B, a, b);
@@ -143,7 +142,7 @@ struct PairCursor {
       a = 0; pos = 0;
     }
   }
-  __device__ __forceinline__ void rows(const PairSpec& ps, long long& ra, long long& rb) const {
+  __device__ __forceinline__ void rows(const PairSpec& ps, long long k, long long& ra, long long& rb) const {
     if (ps.mode == GM_PAIRS_LIST) {
       ra = load_index(ps.idx_i, k, ps.idx64);
       rb = load_index(ps.idx_j, k, ps.idx64);
@@ -154,13 +153,16 @@ struct PairCursor {
     }
   }
   __device__ __forceinline__ void advance(const PairSpec& ps) {
-    k += 32;
     if (ps.mode == GM_PAIRS_TRIU) {
       pos += 32;
       while (a < ps.B - 1 && pos >= ps.B - a - 1) { pos -= ps.B - a - 1; ++a; }
     }
   }
 };
+
+// Row ids are carried as 32-bit values when a table of 2^32 such rows cannot exist (>= 64-byte rows: 274 GB).
+template <int ROWBYTES, bool SMALL = (ROWBYTES >= 64)> struct RowId { using type = long long; };
+template <int ROWBYTES> struct RowId<ROWBYTES, true> { using type = unsigned; };
 
 // Raw per-pair scalar carried through the pipeline: the bits of a T (explicit target / upstream gradient) or, for
 // hop-count targets, the integer hop count.  Hop counts are mapped to (h^2)/max -- dataset.py:11-12, IEEE division so
@@ -206,19 +208,22 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   }
 
   // ---- pipeline registers -------------------------------------------------------------------------------------
-  PairCursor cur;            // pair being computed / staged
-  long long ra0 = -1, rb0 = -1;  // rows of the pair computed in this iteration (staged in `stage`)
-  long long ra1 = -1, rb1 = -1;  // rows of the next pair (indices loaded, rows not yet issued)
-  raw_t tg0 = 0;                 // target (K_FUSED) or upstream gradient (K_BWD) of the current pair, raw
+  using row_t = typename RowId<E * (int)sizeof(T)>::type;
+  const row_t kNoRow = (row_t)-1;
+  long long kc = k0 + lane;          // pair computed in this iteration (rows staged in `stage`)
+  PairCursor ahead;                  // TRIU position of the furthest pair whose indices have been loaded
+  row_t ra0 = kNoRow, rb0 = kNoRow;  // rows of pair kc
+  row_t ra1 = kNoRow, rb1 = kNoRow;  // rows of pair kc + 32 (indices loaded, rows not yet issued)
+  raw_t tg0 = 0;                     // target (K_FUSED) or upstream gradient (K_BWD) of pair kc, raw
   int stage = 0;
 
-  auto fetch_scalar = [&](long long k, long long ra, long long rb) -> raw_t {
+  auto fetch_scalar = [&](long long k, row_t ra, row_t rb) -> raw_t {
     if constexpr (KMODE == K_BWD) {
       return Raw::pack(gout[k]);
     } else {
       if (hops8) return (raw_t)((const unsigned char*)tg.data)[k];
       if (hops16) return (raw_t)((const unsigned short*)tg.data)[k];
-      return Raw::pack(fetch_target<T>(tg, k, ra, rb));
+      return Raw::pack(fetch_target<T>(tg, k, (long long)ra, (long long)rb));
     }
   };
   auto scalar_value = [&](raw_t r) -> T {
@@ -230,31 +235,35 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
       return Raw::unpack(r);
     }
   };
+  auto load_rows = [&](long long k, row_t& ra, row_t& rb) {
+    long long a, b;
+    ahead.rows(ps, k, a, b);
+    ra = (row_t)a; rb = (row_t)b;
+  };
 
-  cur.init(ps, k0 + lane);
-  bool v0 = cur.k < kend;
+  ahead.init(ps, kc);
+  bool v0 = kc < kend;
   if (v0) {
-    cur.rows(ps, ra0, rb0);
-    Stage::issue(stage_mem, 0, 0, tid, xa + ra0 * E);
-    Stage::issue(stage_mem, 0, 1, tid, xb + rb0 * E);
-    tg0 = fetch_scalar(cur.k, ra0, rb0);
+    load_rows(kc, ra0, rb0);
+    Stage::issue(stage_mem, 0, 0, tid, xa + (size_t)ra0 * E);
+    Stage::issue(stage_mem, 0, 1, tid, xb + (size_t)rb0 * E);
+    tg0 = fetch_scalar(kc, ra0, rb0);
   }
   cp_async_commit();
-  PairCursor nxt = cur;
-  nxt.advance(ps);
-  bool v1 = nxt.k < kend;
-  if (v1) nxt.rows(ps, ra1, rb1);
+  ahead.advance(ps);
+  bool v1 = kc + 32 < kend;
+  if (v1) load_rows(kc + 32, ra1, rb1);
 
   // ---- per-lane running state -------------------------------------------------------------------------------------
   double loss_v = 0.0, gd2_v = 0.0;
-  long long acc_row = -1;  // warp-uniform row whose gradient is being accumulated in gacc (or -1)
+  row_t acc_row = kNoRow;  // warp-uniform row whose gradient is being accumulated in gacc
   T gacc[EU];
   GM_UNROLL for (int e = 0; e < EU; ++e) gacc[e] = (T)0;
-  long long prep_row = -1;
+  row_t prep_row = kNoRow;
   T ap[Op::kPrepSize];
 
   auto flush = [&]() {
-    if (acc_row >= 0) {
+    if (acc_row != kNoRow) {
       GM_UNROLL for (int e = 0; e < EU; ++e) gacc[e] = warp_sum(gacc[e]);
       if (lane == 0) {
         T gfull[E];
@@ -263,10 +272,10 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
             gfull[i * N + j] = gacc[i * N - i * (i - 1) / 2 + (j - i)];
             gfull[j * N + i] = gfull[i * N + j];
           }
-        atomic_add_row<T, E>(ga, acc_row, gfull);
+        atomic_add_row<T, E>(ga, (long long)acc_row, gfull);
       }
       GM_UNROLL for (int e = 0; e < EU; ++e) gacc[e] = (T)0;
-      acc_row = -1;
+      acc_row = kNoRow;
     }
   };
 
@@ -281,16 +290,15 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     // (2) stage the next pair: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
     raw_t tgn = 0;
     if (v1) {
-      Stage::issue(stage_mem, stage ^ 1, 0, tid, xa + ra1 * E);
-      Stage::issue(stage_mem, stage ^ 1, 1, tid, xb + rb1 * E);
-      tgn = fetch_scalar(nxt.k, ra1, rb1);
+      Stage::issue(stage_mem, stage ^ 1, 0, tid, xa + (size_t)ra1 * E);
+      Stage::issue(stage_mem, stage ^ 1, 1, tid, xb + (size_t)rb1 * E);
+      tgn = fetch_scalar(kc + 32, ra1, rb1);
     }
     cp_async_commit();
-    PairCursor nn = nxt;
-    nn.advance(ps);
-    bool v2 = v1 && nn.k < kend;
-    long long ra2 = -1, rb2 = -1;
-    if (v2) nn.rows(ps, ra2, rb2);
+    ahead.advance(ps);
+    bool v2 = kc + 64 < kend;
+    row_t ra2 = kNoRow, rb2 = kNoRow;
+    if (v2) load_rows(kc + 64, ra2, rb2);
 
     // (4) the math
     T gx[E], gy[E];
@@ -312,18 +320,18 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
         loss_v += (double)lv;
         gd2_v += (double)dm * (double)d2;
         w = dm * scale_sp;
-        if (out_d2) out_d2[cur.k] = d2;
+        if (out_d2) out_d2[kc] = d2;
       }
       if constexpr (Op::kCanPrep) {
         op.eig_backward(st, w, gx, gy);  // loss weight folded into the N eigen-coefficients
       } else {
         GM_UNROLL for (int e = 0; e < E; ++e) { gx[e] *= w; gy[e] *= w; }
       }
-      atomic_add_row<T, E>(gb, rb0, gy);
+      atomic_add_row<T, E>(gb, (long long)rb0, gy);
     }
     // (5) first-endpoint gradient: run-length accumulation in registers
     {
-      long long r0 = __shfl_sync(full, ra0, 0);
+      row_t r0 = __shfl_sync(full, ra0, 0);
       bool uniform = __all_sync(full, v0 && ra0 == r0);
       if (uniform && r0 == acc_row) {
         GM_UNROLL for (int i = 0; i < N; ++i)
@@ -335,12 +343,12 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
           GM_UNROLL for (int i = 0; i < N; ++i)
             GM_UNROLL for (int j = i; j < N; ++j) gacc[i * N - i * (i - 1) / 2 + (j - i)] = gx[i * N + j];
         } else if (v0) {
-          atomic_add_row<T, E>(ga, ra0, gx);
+          atomic_add_row<T, E>(ga, (long long)ra0, gx);
         }
       }
     }
     // (6) rotate the pipeline
-    cur = nxt; nxt = nn;
+    kc += 32;
     ra0 = ra1; rb0 = rb1; tg0 = tgn; v0 = v1;
     ra1 = ra2; rb1 = rb2; v1 = v2;
     stage ^= 1;
@@ -363,7 +371,10 @@ static int launch_op(const Op& op, const PairArgs& a) {
   const T* xb = (const T*)a.xb;
   using Stage = RowStage<T, Op::E>;
   if (a.kmode != K_FWD && a.ps.mode != GM_PAIRS_ELEMENTWISE && Stage::BYTES <= 64 * 1024) {
-    constexpr int MINB = sizeof(T) == 4 ? 4 : 2;
+#ifndef GM_MINB_F32
+#define GM_MINB_F32 4
+#endif
+    constexpr int MINB = sizeof(T) == 4 ? GM_MINB_F32 : 2;
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

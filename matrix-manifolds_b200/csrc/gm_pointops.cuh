@@ -12,6 +12,7 @@
 //
 // Reference lines restated are cited per struct.
 #pragma once
+#include "../../include/gm_kernels.h"
 #include "gm_manifolds.cuh"
 
 namespace gm {
@@ -68,12 +69,11 @@ struct SpdPt {
   GM_HD void lfl(const T (&x)[CAP], const T (&u)[CAP], T (&out)[CAP]) const {
     InvChol<T, N, FAST_CHOL> ic;
     ic.run(x);
-    T m[CAP], v[CAP], w[N];
+    T m[CAP], lv[CAP], w[N];
     congr_lower<T, N>(ic.a, u, m);  // torch.symeig(upper=True) reads the upper triangle only
-    jacobi_eigh<T, N, true>(m, v, w);
+    GM_UNROLL for (int k = 0; k < CAP; ++k) lv[k] = ic.l[k];
+    jacobi_eigh<T, N, true, false>(m, lv, w);  // sweeps started from L: lv = L V on exit
     GM_UNROLL for (int k = 0; k < N; ++k) w[k] = (F == 0) ? Num<T>::exp(w[k]) : Num<T>::log(w[k]);
-    T lv[CAP];
-    lower_mul<T, N>(ic.l, v, lv);
     wdwt<T, N>(lv, w, out);
   }
   GM_HD void exp(const T (&x)[CAP], const T (&u)[CAP], T (&out)[CAP]) const { lfl<0>(x, u, out); }  // :137-144
@@ -464,7 +464,18 @@ struct GrassmannPt {
 struct OptimCfg {
   int kind, exact, has_clip, step, has_momentum, first_step;
   double lr, beta1, beta2, momentum, dampening, max_grad_norm, eps;
+  double alpha;  // RAdam step size lr * (1 - beta2^t)^0.5 / (1 - beta1^t), evaluated once on the host (radam.py:89-91)
 };
+
+inline OptimCfg make_optim_cfg(const gm_optim_t* opt) {
+  OptimCfg c;
+  c.kind = opt->kind; c.exact = opt->exact; c.has_clip = opt->has_clip; c.step = opt->step;
+  c.has_momentum = opt->has_momentum; c.first_step = opt->first_step;
+  c.lr = opt->lr; c.beta1 = opt->beta1; c.beta2 = opt->beta2; c.momentum = opt->momentum;
+  c.dampening = opt->dampening; c.max_grad_norm = opt->max_grad_norm; c.eps = opt->eps;
+  c.alpha = opt->lr * ::sqrt(1.0 - ::pow(opt->beta2, (double)opt->step)) / (1.0 - ::pow(opt->beta1, (double)opt->step));
+  return c;
+}
 
 // x, g: current point and Euclidean gradient.  b1/b2: optimizer buffers
 // (exp_avg / exp_avg_sq, or the momentum buffer in b1).  All updated in place.
@@ -482,14 +493,30 @@ GM_HD void optim_update(const Man& man, const OptimCfg& c, T* x, const T* g, T* 
     }
     T gn2 = gn * gn;  // grad_norm.pow_(2): the UNclipped norm (radam.py:87)
     // alpha = lr * (1 - beta2^t)^0.5 / (1 - beta1^t) in Python doubles, then applied in T (radam.py:89-91)
-    double alpha = c.lr * ::sqrt(1.0 - ::pow(c.beta2, (double)c.step)) / (1.0 - ::pow(c.beta1, (double)c.step));
-    for (int k = 0; k < cnt; ++k) {
-      T m = b1[k] * (T)c.beta1 + (T)(1.0 - c.beta1) * rg[k];
-      T v = b2[k] * (T)c.beta2 + (T)(1.0 - c.beta2) * gn2;
-      b1[k] = m;
-      b2[k] = v;
-      T denom = Num<T>::sqrt(v) + (T)c.eps;
-      dir[k] = ((T)1 / (denom / m)) * (T)(-alpha);  // denom.div_(exp_avg).reciprocal_().mul_(-alpha)
+    const T nalpha = (T)(-c.alpha), be1 = (T)c.beta1, om1 = (T)(1.0 - c.beta1), be2 = (T)c.beta2;
+    const T add2 = (T)(1.0 - c.beta2) * gn2;
+    // The second moment is one scalar per point stored at full parameter shape (radam.py:56-60,87), so all cnt
+    // entries normally agree: then one sqrt and one reciprocal serve the whole point.
+    bool same = true;
+    for (int k = 1; k < cnt; ++k) same = same && (b2[k] == b2[0]);
+    if (same) {
+      T v = b2[0] * be2 + add2;
+      T rden = Num<T>::recip(Num<T>::sqrt(v) + (T)c.eps);
+      for (int k = 0; k < cnt; ++k) {
+        T m = b1[k] * be1 + om1 * rg[k];
+        b1[k] = m;
+        b2[k] = v;
+        dir[k] = (m * rden) * nalpha;  // denom.div_(exp_avg).reciprocal_().mul_(-alpha)
+      }
+    } else {
+      for (int k = 0; k < cnt; ++k) {
+        T m = b1[k] * be1 + om1 * rg[k];
+        T v = b2[k] * be2 + add2;
+        b1[k] = m;
+        b2[k] = v;
+        T denom = Num<T>::sqrt(v) + (T)c.eps;
+        dir[k] = ((T)1 / (denom / m)) * nalpha;
+      }
     }
     if (c.exact) man.exp(*(T(*)[CAP])x, dir, nx); else man.retr(*(T(*)[CAP])x, dir, nx);
     T mt[CAP];

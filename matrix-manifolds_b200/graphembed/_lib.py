@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libgm_b200.so')
+# GM_B200_LIB lets an integrator (or an A/B experiment) point at another build of the same C-ABI
+LIB_PATH = os.environ.get('GM_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'lib', 'libgm_b200.so')
 
 # ---- enums (include/gm_kernels.h) -------------------------------------------
 GM_F32, GM_F64 = 0, 1
@@ -76,6 +77,7 @@ _PROTOTYPES = {
     'gm_levels_to_condensed': (ctypes.c_int, [_i32, _vp, _i32, _i32, _vp, _vp]),
     'gm_levels_to_dense_targets': (ctypes.c_int, [_i32, _vp, _i32, _dbl, _i32, _vp, _vp]),
     'gm_gather_levels': (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
+    'gm_expand_groups': (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

@@ -261,3 +261,15 @@ def dist2_elementwise(spec, x, y):
 
 def dist2_indexed(spec, x, pairs):
     return _Dist2Indexed.apply(x, spec, pairs)
+
+
+def expand_groups(group_rows, offsets, out):
+    """out[k] = group_rows[g] for offsets[g] <= k < offsets[g+1] (int32 rows, int64 offsets, int32 out; all CUDA)."""
+    L.require_cuda(group_rows, offsets, out)
+    G, P = group_rows.numel(), out.numel()
+    if offsets.numel() != G + 1 or group_rows.dtype != torch.int32 or out.dtype != torch.int32 or \
+            offsets.dtype != torch.int64:
+        raise ValueError('expand_groups: int32 rows (G,), int64 offsets (G+1,), int32 out (P,)')
+    rc = L.lib().gm_expand_groups(L.ptr(group_rows), L.ptr(offsets), G, L.ptr(out), P, L.stream_ptr(out.device))
+    L.check(rc, 'gm_expand_groups')
+    return out

@@ -15,7 +15,8 @@ import torch
 from torch.nn.functional import softplus
 
 from . import _ops
-from .parallel import allreduce_step_buffers
+from .modules import ManifoldParameter
+from .parallel import RowShards, allreduce_step_buffers
 
 
 class PairTrainer:
@@ -25,11 +26,14 @@ class PairTrainer:
     optimizer : RiemannianAdam / RiemannianSGD over embedding.xs
     objective : QuotientLoss / StressLoss
     max_hops_sq : max over the graph of hop^2 (GraphDataset normalisation, data/dataset.py:11-12)
-    process_group : optional torch.distributed group; gradients (and the loss) are summed over it, so that
-        every rank applies the same update to its replica of the embedding (pair-sharded data parallelism).
+    process_group : optional torch.distributed group; gradients (and the loss) are summed over it (pair-sharded data
+        parallelism).
+    owner_update : with a process group, reduce-scatter the gradient and let every rank update (and keep optimizer
+        state for) only the rows it owns, then all-gather the new points; otherwise all-reduce and update replicas.
+        Both give the same trajectory up to summation order.  Default: owner update whenever the rows split evenly.
     """
 
-    def __init__(self, embedding, optimizer, objective, max_hops_sq, alpha=1.0, process_group=None):
+    def __init__(self, embedding, optimizer, objective, max_hops_sq, alpha=1.0, process_group=None, owner_update=None):
         if embedding.n_components != 1:
             raise ValueError('PairTrainer drives a single-manifold embedding; use BatchedObjective for products')
         self.emb, self.opt, self.obj = embedding, optimizer, objective
@@ -42,6 +46,25 @@ class PairTrainer:
         self._sp = float(softplus(embedding.scales[0].detach()))
         self._staging = None
         self._copy_stream = None
+        self.shards = None
+        if process_group is not None and torch.distributed.get_world_size(process_group) > 1:
+            even = self.x.shape[0] % torch.distributed.get_world_size(process_group) == 0
+            if owner_update is None:
+                owner_update = even
+            if owner_update:
+                self.shards = RowShards(self.x.shape[0], process_group)
+                # the optimizer now drives a parameter that aliases the owned rows of x
+                own = ManifoldParameter(self.shards.own(self.x.data), manifold=self.man)
+                own.grad = torch.zeros_like(own.data)
+                self._own = own
+                replaced = False
+                for g in optimizer.param_groups:
+                    for k, prm in enumerate(g['params']):
+                        if prm is self.x:
+                            g['params'][k] = own
+                            replaced = True
+                if not replaced:
+                    raise ValueError('optimizer does not hold the embedding parameter')
 
     # ---- device-resident inputs ---------------------------------------------------------------------------------
     def step(self, idx_i, idx_j, hops, epoch=1):
@@ -52,16 +75,23 @@ class PairTrainer:
         self.grad.zero_()
         self.acc.zero_()
         _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, self._sp, self.grad, self.acc)
-        allreduce_step_buffers(self.grad, self.acc, self.pg)
-        self.opt.step()
+        if self.shards is None:
+            allreduce_step_buffers(self.grad, self.acc, self.pg)
+            self.opt.step()
+        else:
+            self.shards.reduce_scatter(self.grad, out=self._own.grad)
+            torch.distributed.all_reduce(self.acc, group=self.pg)
+            self.opt.step()
+            self.shards.all_gather(self.x.data)
         return self.acc[0]
 
     # ---- host-resident inputs (what a data loader hands over) ----------------------------------------------------------
-    def _ensure_staging(self, P, hop_dtype):
-        if self._staging is None or self._staging[0][0].numel() < P:
+    def _ensure_staging(self, P, hop_dtype, G=0):
+        if self._staging is None or self._staging[0][0].numel() < P or self._staging[0][3].numel() < G:
             dev = self.x.device
             self._staging = [(torch.empty(P, dtype=torch.int32, device=dev), torch.empty(P, dtype=torch.int32, device=dev),
-                              torch.empty(P, dtype=hop_dtype, device=dev)) for _ in range(2)]
+                              torch.empty(P, dtype=hop_dtype, device=dev), torch.empty(max(G, 1), dtype=torch.int32, device=dev),
+                              torch.empty(max(G, 1) + 1, dtype=torch.int64, device=dev)) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._slot = 0
             self._pending = None
@@ -78,15 +108,15 @@ class PairTrainer:
             cur.wait_event(ev)
         else:
             slot = self._slot
-            di, dj, dh = self._staging[slot]
+            di, dj, dh = self._staging[slot][:3]
             di[:P].copy_(idx_i, non_blocking=True)
             dj[:P].copy_(idx_j, non_blocking=True)
             dh[:P].copy_(hops, non_blocking=True)
-        di, dj, dh = self._staging[slot]
+        di, dj, dh = self._staging[slot][:3]
         self._pending = None
         if next_batch is not None:
             nslot = 1 - slot
-            ni, nj, nh = self._staging[nslot]
+            ni, nj, nh = self._staging[nslot][:3]
             n = next_batch[0].numel()
             self._copy_stream.wait_stream(cur)  # the other slot was consumed by the previous step
             with torch.cuda.stream(self._copy_stream):
@@ -97,5 +127,44 @@ class PairTrainer:
                 ev.record(self._copy_stream)
             self._pending = (next_batch[0], nslot, ev)
         self._slot = 1 - slot
+        loss = self.step(di[:P], dj[:P], dh[:P], epoch=epoch)
+        return loss.item()
+
+    def step_host_grouped(self, sources, offsets, idx_j, hops, epoch=1, next_batch=None):
+        """One step from PINNED host tensors in source-grouped (CSR-like) form, the natural output of a sampler that
+        draws targets per BFS source: pairs offsets[g] <= k < offsets[g+1] are (sources[g], idx_j[k]) with hop count
+        hops[k].  sources int32 (G,), offsets int64 (G+1,), idx_j int32 (P,), hops uint8/int16 (P,).  Uploads 5 bytes
+        per pair instead of 9; the first-endpoint index vector is expanded on the device (gm_expand_groups).
+        `next_batch` = the next step's (sources, offsets, idx_j, hops), uploaded on a second stream meanwhile."""
+        P, G = idx_j.numel(), sources.numel()
+        self._ensure_staging(P, hops.dtype, G)
+        cur = torch.cuda.current_stream(self.x.device)
+
+        def upload(slot, batch):
+            di, dj, dh, ds, do = self._staging[slot]
+            s_, o_, j_, h_ = batch
+            ds[:s_.numel()].copy_(s_, non_blocking=True)
+            do[:o_.numel()].copy_(o_, non_blocking=True)
+            dj[:j_.numel()].copy_(j_, non_blocking=True)
+            dh[:h_.numel()].copy_(h_, non_blocking=True)
+
+        if self._pending is not None and self._pending[0] is idx_j:
+            slot, ev = self._pending[1], self._pending[2]
+            cur.wait_event(ev)
+        else:
+            slot = self._slot
+            upload(slot, (sources, offsets, idx_j, hops))
+        di, dj, dh, ds, do = self._staging[slot]
+        self._pending = None
+        if next_batch is not None:
+            nslot = 1 - slot
+            self._copy_stream.wait_stream(cur)  # the other slot was consumed by the previous step
+            with torch.cuda.stream(self._copy_stream):
+                upload(nslot, next_batch)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._pending = (next_batch[2], nslot, ev)
+        self._slot = 1 - slot
+        _ops.expand_groups(ds[:G], do[:G + 1], di[:P])
         loss = self.step(di[:P], dj[:P], dh[:P], epoch=epoch)
         return loss.item()

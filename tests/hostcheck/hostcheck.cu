@@ -225,10 +225,7 @@ extern "C" int hc_point(int kind, int dtype, int n, int p, unsigned flags, doubl
   HcPoint a{};
   a.op = op; a.x = x; a.u = u; a.v = v; a.out = out; a.b1 = b1; a.b2 = b2; a.N = N;
   if (op < 0) {
-    a.oc.kind = opt->kind; a.oc.exact = opt->exact; a.oc.has_clip = opt->has_clip; a.oc.step = opt->step;
-    a.oc.has_momentum = opt->has_momentum; a.oc.first_step = opt->first_step;
-    a.oc.lr = opt->lr; a.oc.beta1 = opt->beta1; a.oc.beta2 = opt->beta2; a.oc.momentum = opt->momentum;
-    a.oc.dampening = opt->dampening; a.oc.max_grad_norm = opt->max_grad_norm; a.oc.eps = opt->eps;
+    a.oc = make_optim_cfg(opt);
     retr_qr = opt->grassmann_retr_qr;
   }
   if (dtype == GM_F32) return pt_any<float>(kind, n, p, flags, wmin, wmax, retr_qr, a);

@@ -53,3 +53,49 @@ def test_pair_sharding_and_gradient_combine_world2():
         assert p.exitcode == 0
     assert gerr < 1e-12 and lerr < 1e-10
     assert ranges == [(0, 3), (3, 5), (5, 7)]  # contiguous, balanced, covering
+
+
+def _shard_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, 'matrix-manifolds_b200'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from graphembed.parallel import RowShards
+    torch.manual_seed(rank)
+    n = 12
+    grad = torch.randn(n, 3, 3, dtype=torch.float64)
+    every = [None] * world
+    dist.all_gather_object(every, grad.clone())
+    total = sum(every)
+    sh = RowShards(n, dist.group.WORLD)
+    mine = sh.reduce_scatter(grad.clone())
+    ok_rs = torch.allclose(mine, total[sh.lo:sh.hi], atol=1e-14)
+    # owner update on the owned rows, then publish
+    x = torch.zeros(n, 3, 3, dtype=torch.float64)
+    sh.own(x).copy_(-0.1 * mine)
+    sh.all_gather(x)
+    ok_ag = torch.allclose(x, -0.1 * total, atol=1e-14)
+    bad = False
+    try:
+        RowShards(n + 1, dist.group.WORLD)
+    except ValueError:
+        bad = True
+    out.put((rank, ok_rs, ok_ag, bad, (sh.lo, sh.hi)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_shards_reduce_scatter_all_gather_world2():
+    """Owner-update plumbing (gloo, CPU): reduce-scatter hands every rank the summed rows it owns, all-gather
+    publishes the updated rows; uneven row counts are rejected."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [g[4] for g in got] == [(0, 6), (6, 12)]
+    assert all(g[1] and g[2] and g[3] for g in got)

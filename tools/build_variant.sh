@@ -1,0 +1,11 @@
+#!/bin/bash
+# DEV TOOL: A/B variants of the SPD 4x4 pair kernel.  tools/build_variant.sh <name> <extra nvcc flags...>
+# -> matrix-manifolds_b200/lib/libgm_b200_<name>.so (select with GM_B200_LIB=<path>)
+set -e
+cd "$(dirname "$0")/../matrix-manifolds_b200"
+name=$1; shift
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
+  --expt-relaxed-constexpr -DGM_N=4 "$@" -Xptxas -v -c csrc/gm_pairs_spd.cu -o build/var_$name.o 2> build/var_$name.ptxas.log
+objs=$(ls build/*.o | grep -v "build/var_" | grep -v "gm_pairs_spd_4.o")
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/libgm_b200_$name.so $objs build/var_$name.o -lcudart
+grep -A3 "spd_pair_stream_kernelINS_5SpdAIIfLi4ELb0ELb0EEEfLi2" build/var_$name.ptxas.log | grep -E "Used|spill"
