@@ -12,8 +12,9 @@ step     : zero grad -> ONE fused pair kernel (gather + distance + loss + gradie
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs-log2 24] [--nodes 2000000]
 
 `value`  : whole-job pairs/s with the pair batches resident in HBM (CUDA events, max over ranks).
-`e2e`    : same metric through the public API (graphembed.engine.PairTrainer.step_host) from PINNED HOST buffers:
-           every step uploads its (i, j, hops) batch and reads the loss back.
+`e2e`    : same metric through the public API (graphembed.engine.PairTrainer.step_host_grouped) from PINNED HOST
+           buffers: every step uploads its source-grouped (sources, offsets, j | hops << 24) batch -- 4 bytes per
+           pair -- and reads the loss back.
 `roofline`: fused pair kernel, algorithmic bytes (268 B/pair) / its CUDA-event duration vs the
            measured HBM copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline`: the oracle port (same torch/LAPACK calls as the reference) on the host cores, bounded sample.
@@ -49,6 +50,8 @@ def parse():
     ap.add_argument('--batches', type=int, default=3, help='distinct pre-generated pair batches cycled through')
     ap.add_argument('--cpu-pairs-log2', type=int, default=17)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--unpacked', action='store_true', help='separate uint8 hop-count vector instead of the packed '
+                    '(j | hops << 24) pair format')
     return ap.parse_args()
 
 
@@ -77,11 +80,12 @@ def scale_free_edges(n, m, seed):
 
 
 def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
-    """[(I int32, J int32, hops uint8, sources int32, offsets int64)] pinned host tensors + max hop^2; hop targets
-    come from the multi-source BFS kernel.  (sources, offsets) is the source-grouped form of I."""
+    """[(I int32, J int32, hops uint8, sources int32, offsets int64, J|hops<<24 int32)] pinned host tensors + max
+    hop^2; hop targets come from the multi-source BFS kernel.  (sources, offsets) is the source-grouped form of I, the
+    last entry the packed 4-byte-per-pair form of (J, hops)."""
     from graphembed.data import bfs_levels, edges_to_csr
+    from graphembed.engine import pack_hops
     from graphembed import _lib as L
-    import ctypes
     P = 1 << log2_pairs
     per_src = max(1, P // N_SOURCES)
     n_src = P // per_src
@@ -106,8 +110,9 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
         max_h = max(max_h, int(levels.max().item()))
         assert int(hops.min().item()) >= 1 and int(hops.max().item()) < 255
         offsets = (torch.arange(n_src + 1, dtype=torch.int64) * per_src)
-        batches.append((I.pin_memory(), J.pin_memory(), hops.cpu().pin_memory(), src.contiguous().pin_memory(),
-                        offsets.pin_memory()))
+        hops_h = hops.cpu()
+        batches.append((I.pin_memory(), J.pin_memory(), hops_h.pin_memory(), src.contiguous().pin_memory(),
+                        offsets.pin_memory(), pack_hops(J, hops_h).pin_memory()))
         del levels
     return batches, float(max_h * max_h)
 
@@ -239,7 +244,10 @@ def main():
         torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MAX)
         max_sq = float(m.item())
     trainer = PairTrainer(emb, opt, QuotientLoss(), max_hops_sq=max_sq, alpha=1.0, process_group=pg)
-    dev_batches = [tuple(t.to(dev) for t in b[:3]) for b in batches]
+    if args.unpacked:
+        dev_batches = [tuple(t.to(dev) for t in b[:3]) for b in batches]
+    else:  # (i, j | hops << 24): the hop count rides in the top byte of the second index
+        dev_batches = [(b[0].to(dev), b[5].to(dev), None) for b in batches]
 
     def barrier():
         if pg is not None:
@@ -286,7 +294,7 @@ def main():
     # source-grouped upload (sources, offsets, j, hops): 5 B/pair over PCIe; the next batch is uploaded on a second
     # stream while this one computes; every step ends with a device->host read of the loss
     def grouped(b):
-        return (b[3], b[4], b[1], b[2])
+        return (b[3], b[4], b[1], b[2]) if args.unpacked else (b[3], b[4], b[5], None)
 
     nb = len(batches)
     for k in range(2):
@@ -299,7 +307,7 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]))
+    h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
 
     if pg is not None:
         t = torch.tensor([ms, ms_e2e, pair_ms], device=dev, dtype=torch.float64)
@@ -331,14 +339,15 @@ def main():
             'nodes': N, 'pairs_per_step_per_gpu': P, 'parallelism': f'pair-sharded x{world}'
             + (' + NCCL reduce-scatter of the (N,4,4) gradient, owner-rank optimizer update, all-gather of the points'
                if trainer.shards is not None else (' + NCCL all-reduce of the (N,4,4) gradient' if world > 1 else '')),
-            'l2_policy': f'inputs larger than L2: {len(batches)} distinct batches of {P * 9 / 1e6:.0f} MB cycled, '
+            'l2_policy': f'inputs larger than L2: {len(batches)} distinct batches of '
+                         f'{P * (9 if args.unpacked else 8) / 1e6:.0f} MB cycled, '
                          f'{N * 64 / 1e6:.0f} MB embedding + {N * 64 / 1e6:.0f} MB gradient touched at random',
             'final_loss': final_loss,
         },
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps,
                 'api': 'graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
-                       'int32 j, uint8 hops; per rank)'},
+                       + ('int32 j, uint8 hops' if args.unpacked else 'int32 j | hops << 24') + '; per rank)'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': 'spd_pair_stream_kernel<SpdAI<float,4>,K_FUSED>',

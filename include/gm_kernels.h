@@ -69,7 +69,7 @@ typedef struct gm_manifold {
 enum gm_pairs_mode {
   GM_PAIRS_ELEMENTWISE = 0, /* pair k = (xa[k], xb[k])                       -- Manifold.dist(x, y)  (base.py:56-57)        */
   GM_PAIRS_LIST = 1,        /* pair k = (xa[idx_i[k]], xb[idx_j[k]])         -- dist(x[I], x[J]) incl. the gather           */
-  GM_PAIRS_TRIU = 2         /* pair k = k-th (a<b) of triu_indices(B,B,1), rows
+  GM_PAIRS_TRIU = 2         /* pair k = (k0+k)-th (a<b) of triu_indices(B,B,1), rows
                                xa[nodes[a]], xb[nodes[b]] (nodes NULL: a, b) -- Manifold.pdist (base.py:59-63) fused with
                                                                                 x[indices] (modules.py:84-88)              */
 };
@@ -77,11 +77,14 @@ enum gm_pairs_mode {
 typedef struct gm_pairs {
   int32_t mode;      /* gm_pairs_mode */
   int32_t idx64;     /* 1: idx_i/idx_j/nodes are int64, 0: int32 */
-  int64_t P;         /* number of pairs (TRIU: must equal B(B-1)/2) */
+  int64_t P;         /* number of pairs (TRIU: k0 + P <= B(B-1)/2) */
   const void* idx_i; /* LIST */
   const void* idx_j; /* LIST */
   int64_t B;         /* TRIU */
   const void* nodes; /* TRIU, optional */
+  int64_t k0;        /* TRIU: first pair of the triangle covered by this launch (0 for the whole triangle); per-pair
+                        vectors (out_d2, gout, VECTOR / HOPS targets) are indexed by the LOCAL pair number 0..P-1.
+                        A rank of a pair-sharded job passes its slice [k0, k0+P) */
 } gm_pairs_t;
 
 /* Loss on (graph target g, manifold squared distance m) -- objectives.py:16-45. */
@@ -102,7 +105,10 @@ enum gm_target_mode {
                         masked_select of data/dataset.py:23-27 (LIST/TRIU modes only)                               */
   GM_TGT_HOPS_U8 = 2, /* uint8 BFS hop count h per pair; g = (h*h)/max_sq computed in the manifold dtype exactly as
                         data/dataset.py:11-12 does (pow(2) then div_(max))                                           */
-  GM_TGT_HOPS_U16 = 3
+  GM_TGT_HOPS_U16 = 3,
+  GM_TGT_HOPS_PACKED = 4 /* LIST pairs with int32 indices only: the hop count rides in the top 8 bits of idx_j[k]
+                            (row = idx_j[k] & 0xFFFFFF, h = idx_j[k] >> 24; needs < 2^24 rows); `data` is ignored.
+                            One 4-byte word per pair instead of 5 bytes to upload and read (gm_pairs_loss_fused only) */
 };
 typedef struct gm_targets {
   int32_t mode;
@@ -144,6 +150,33 @@ int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_
 int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
                     const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc, void* out_g,
                     gm_stream_t stream);
+
+/* Validation metrics over a pair set, streamed (TrainingEngine._validate, train.py:230-265; metrics.average_distortion
+ * and metrics.pearsonr, metrics.py:13-17,46-56) without materialising the N(N-1)/2 distance vectors:
+ *   squared_inputs != 0:  m_k = sqrt(sum_f sp[f]*d2[f][k]),  g_k = sqrt(target_k)   (train.py:231-232)
+ *   squared_inputs == 0:  m_k = d2[0][k] (F must be 1),      g_k = target_k         (plain metrics.py call)
+ *   acc[0] += #pairs           acc[1] += sum |m-g|/g     acc[2] += sum m     acc[3] += sum g
+ *   acc[4] += sum m*m          acc[5] += sum g*g         acc[6] += sum m*g   (all double; acc has 8 slots)
+ * d2[f] are per-pair vectors of this launch (local index); targets may be VECTOR / DENSE / HOPS_*; `pairs` gives the
+ * node ids for DENSE targets (may be NULL otherwise; pairs->P is the number of pairs). */
+int gm_pairs_metrics(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
+                     const gm_pairs_t* pairs, const gm_targets_t* targets, int32_t squared_inputs, double* acc,
+                     gm_stream_t stream);
+
+/* KL-divergence objective with the stochastic-neighbour inference model (objectives.py:48-76,
+ * inference/stochastic_neighbors.py:8-24) over ALL pairs of a batch of B nodes, condensed triu order.
+ *   m_k = sum_f sp[f]*d2[f][k];  inclusive: theta_x = -alpha*g, theta_z = -m;  else theta_x = -m, theta_z = -alpha*g
+ *   KL = A_z - A_x - margs_x . (theta_z - theta_x),  A = sum_rows logsumexp_{j != i} theta_ij
+ * gm_sne_row_stats: one pass per row i over its B-1 entries (online softmax):
+ *   row_stats[0*B+i] = logsumexp theta_x row i;  row_stats[1*B+i] = logsumexp theta_z row i;
+ *   row_stats[2*B+i] = E_{p_x(i,.)}[theta_z - theta_x]
+ * gm_sne_pair_terms: acc[0] += KL, out_g[k] = dKL/dm_k, acc[1+f] += sum_k out_g[k]*d2[f][k] (scale gradients).
+ * g is a VECTOR target (condensed, dtype of the manifold).  row_stats: 3*B elements of `dtype`. */
+int gm_sne_row_stats(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
+                     const void* g, int64_t B, double alpha, int32_t inclusive, void* row_stats, gm_stream_t stream);
+int gm_sne_pair_terms(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
+                      const void* g, int64_t B, double alpha, int32_t inclusive, const void* row_stats, double* acc,
+                      void* out_g, gm_stream_t stream);
 
 /* ---- optimizer ---------------------------------------------------------- */
 enum gm_optim_kind { GM_OPT_RSGD = 0, GM_OPT_RADAM = 1 };

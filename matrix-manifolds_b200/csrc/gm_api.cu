@@ -20,8 +20,8 @@ int validate_pairs(const gm_pairs_t* p) {
       if (p->P > 0 && (!p->idx_i || !p->idx_j)) return GM_ENULL;
       return GM_OK;
     case GM_PAIRS_TRIU:
-      if (p->B < 0) return GM_EINVAL;
-      if (p->P != p->B * (p->B - 1) / 2) return GM_EINVAL;
+      if (p->B < 0 || p->k0 < 0) return GM_EINVAL;
+      if (p->k0 + p->P > p->B * (p->B - 1) / 2) return GM_EINVAL;
       return GM_OK;
     default:
       return GM_EINVAL;
@@ -118,11 +118,6 @@ static int pair_dispatch(const PairArgs& a) {
 // ---------------------------------------------------------------------------
 // product-manifold loss over F distance vectors
 // ---------------------------------------------------------------------------
-struct FactorPtrs {
-  const void* d2[8];
-  double sp[8];
-};
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 product_loss_kernel(int F, FactorPtrs fp, TargetSpec tg, LossCfg lc, long long P, double* __restrict__ acc,
@@ -207,17 +202,20 @@ int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_
   if (rc) return rc;
   if (!targets || !loss) return GM_ENULL;
   if (pairs->mode == GM_PAIRS_ELEMENTWISE) return GM_EINVAL;
-  if (targets->mode < GM_TGT_VECTOR || targets->mode > GM_TGT_HOPS_U16) return GM_EINVAL;
+  if (targets->mode < GM_TGT_VECTOR || targets->mode > GM_TGT_HOPS_PACKED) return GM_EINVAL;
+  const bool packed = targets->mode == GM_TGT_HOPS_PACKED;
+  if (packed && (pairs->mode != GM_PAIRS_LIST || pairs->idx64)) return GM_EINVAL;
   if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
   if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
   if (pairs->P == 0) return GM_OK;
-  if (!x || !acc || !grad || !targets->data) return GM_ENULL;
+  if (!x || !acc || !grad || (!packed && !targets->data)) return GM_ENULL;
   PairArgs a{};
   fill_manifold(a, man);
   a.kmode = K_FUSED;
   a.ps = make_pairs(pairs);
   a.xa = x; a.xb = x; a.ga = grad; a.gb = grad; a.out_d2 = out_d2;
   a.tg = make_targets(targets);
+  if (packed) { a.tg.data = pairs->idx_j; a.ps.jmask = 0x00ffffffu; }
   a.lc = make_loss(loss);
   a.scale_sp = scale_sp;
   a.acc = acc;

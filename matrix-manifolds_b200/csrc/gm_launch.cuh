@@ -18,6 +18,8 @@ struct PairSpec {
   const void* idx_i;
   const void* idx_j;
   const void* nodes;
+  long long k0;    // TRIU: triangle index of local pair 0
+  unsigned jmask;  // LIST + int32: row = idx_j[k] & jmask (0xFFFFFF when hop counts ride in the top byte)
 };
 struct TargetSpec {
   int mode;
@@ -30,6 +32,8 @@ inline PairSpec make_pairs(const gm_pairs_t* p) {
   PairSpec s;
   s.mode = p->mode; s.idx64 = p->idx64; s.P = p->P; s.B = p->B;
   s.idx_i = p->idx_i; s.idx_j = p->idx_j; s.nodes = p->nodes;
+  s.k0 = (p->mode == GM_PAIRS_TRIU) ? p->k0 : 0;
+  s.jmask = 0xffffffffu;
   return s;
 }
 inline TargetSpec make_targets(const gm_targets_t* t) {
@@ -43,6 +47,12 @@ inline LossCfg make_loss(const gm_loss_t* l) {
   return c;
 }
 int validate_pairs(const gm_pairs_t* p);
+
+// factor distance vectors of a product manifold and their softplus(scale) weights (modules.py:84-88)
+struct FactorPtrs {
+  const void* d2[8];
+  double sp[8];
+};
 
 // ---- one pair-kernel launch request (filled by gm_api.cu) --------------------
 enum { K_FWD = 0, K_BWD = 1, K_FUSED = 2 };
@@ -94,10 +104,10 @@ __device__ __forceinline__ void decode_pair(const PairSpec& ps, long long k, lon
     ra = k; rb = k;
   } else if (ps.mode == GM_PAIRS_LIST) {
     ra = load_index(ps.idx_i, k, ps.idx64);
-    rb = load_index(ps.idx_j, k, ps.idx64);
+    rb = ps.idx64 ? ((const long long*)ps.idx_j)[k] : (long long)(((const unsigned*)ps.idx_j)[k] & ps.jmask);
   } else {
     long long a, b;
-    triu_decode(k, ps.B, a, b);
+    triu_decode(k + ps.k0, ps.B, a, b);
     if (ps.nodes) { ra = load_index(ps.nodes, a, ps.idx64); rb = load_index(ps.nodes, b, ps.idx64); }
     else { ra = a; rb = b; }
   }
@@ -109,8 +119,20 @@ __device__ __forceinline__ T fetch_target(const TargetSpec& tg, long long k, lon
   if (tg.mode == GM_TGT_VECTOR) return ((const T*)tg.data)[k];
   if (tg.mode == GM_TGT_DENSE) return ((const T*)tg.data)[ra * tg.ld + rb];
   T h = (tg.mode == GM_TGT_HOPS_U8) ? (T)((const unsigned char*)tg.data)[k]
-                                    : (T)((const unsigned short*)tg.data)[k];
+        : (tg.mode == GM_TGT_HOPS_U16) ? (T)((const unsigned short*)tg.data)[k]
+                                       : (T)(((const unsigned*)tg.data)[k] >> 24);  // HOPS_PACKED: data == idx_j
   return (h * h) / (T)tg.max_sq;  // pow(2) then div_(max): dataset.py:11-12
+}
+
+// m_k = sum_f sp_f * d2_f[k]: sum() of a Python list starts from int 0 and adds left to right (modules.py:84-88)
+template <typename T>
+__device__ __forceinline__ T product_dist2(int F, const FactorPtrs& fp, long long k) {
+  T m = (T)0;
+  for (int f = 0; f < F; ++f) {
+    T term = (T)fp.sp[f] * ((const T*)fp.d2[f])[k];
+    m = (f == 0) ? term : m + term;
+  }
+  return m;
 }
 
 // ---- row I/O ---------------------------------------------------------------

@@ -136,7 +136,7 @@ struct PairCursor {
   __device__ __forceinline__ void init(const PairSpec& ps, long long k0) {
     if (ps.mode == GM_PAIRS_TRIU && k0 < ps.P) {
       long long b;
-      triu_decode(k0, ps.B, a, b);
+      triu_decode(k0 + ps.k0, ps.B, a, b);
       pos = b - a - 1;
     } else {
       a = 0; pos = 0;
@@ -145,7 +145,7 @@ struct PairCursor {
   __device__ __forceinline__ void rows(const PairSpec& ps, long long k, long long& ra, long long& rb) const {
     if (ps.mode == GM_PAIRS_LIST) {
       ra = load_index(ps.idx_i, k, ps.idx64);
-      rb = load_index(ps.idx_j, k, ps.idx64);
+      rb = load_index(ps.idx_j, k, ps.idx64);  // raw word: HOPS_PACKED callers split off the top byte
     } else {
       long long b = a + 1 + pos;
       if (ps.nodes) { ra = load_index(ps.nodes, a, ps.idx64); rb = load_index(ps.nodes, b, ps.idx64); }
@@ -200,7 +200,8 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   const long long warp_id = (long long)blockIdx.x * 4 + (tid >> 5);
   const long long k0 = warp_id * chunk;
   const long long kend = (k0 + chunk < ps.P) ? k0 + chunk : ps.P;
-  const bool hops8 = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_U8;
+  const bool hopsP = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_PACKED;  // hop count in the top byte of idx_j
+  const bool hops8 = (KMODE == K_FUSED) && (tg.mode == GM_TGT_HOPS_U8 || hopsP);
   const bool hops16 = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_U16;
   if (hops8) {
     for (int h = tid; h < 256; h += 128) hop_lut[h] = ((T)h * (T)h) / (T)tg.max_sq;
@@ -221,6 +222,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     if constexpr (KMODE == K_BWD) {
       return Raw::pack(gout[k]);
     } else {
+      if (hopsP) return (raw_t)(((unsigned)rb) >> 24);
       if (hops8) return (raw_t)((const unsigned char*)tg.data)[k];
       if (hops16) return (raw_t)((const unsigned short*)tg.data)[k];
       return Raw::pack(fetch_target<T>(tg, k, (long long)ra, (long long)rb));
@@ -245,9 +247,10 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   bool v0 = kc < kend;
   if (v0) {
     load_rows(kc, ra0, rb0);
+    tg0 = fetch_scalar(kc, ra0, rb0);
+    if (hopsP) rb0 &= (row_t)0x00ffffffu;
     Stage::issue(stage_mem, 0, 0, tid, xa + (size_t)ra0 * E);
     Stage::issue(stage_mem, 0, 1, tid, xb + (size_t)rb0 * E);
-    tg0 = fetch_scalar(kc, ra0, rb0);
   }
   cp_async_commit();
   ahead.advance(ps);
@@ -290,9 +293,10 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     // (2) stage the next pair: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
     raw_t tgn = 0;
     if (v1) {
+      tgn = fetch_scalar(kc + 32, ra1, rb1);
+      if (hopsP) rb1 &= (row_t)0x00ffffffu;
       Stage::issue(stage_mem, stage ^ 1, 0, tid, xa + (size_t)ra1 * E);
       Stage::issue(stage_mem, stage ^ 1, 1, tid, xb + (size_t)rb1 * E);
-      tgn = fetch_scalar(kc + 32, ra1, rb1);
     }
     cp_async_commit();
     ahead.advance(ps);

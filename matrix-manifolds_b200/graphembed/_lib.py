@@ -19,7 +19,7 @@ GM_SPD_AI, GM_SPD_STEIN, GM_LORENTZ, GM_SPHERE, GM_GRASSMANN, GM_EUCLIDEAN = ran
 GM_FAST_EIG, GM_FAST_CHOL, GM_FAST_SVD = 1, 2, 4
 GM_PAIRS_ELEMENTWISE, GM_PAIRS_LIST, GM_PAIRS_TRIU = 0, 1, 2
 GM_LOSS_QUOTIENT, GM_LOSS_STRESS = 0, 1
-GM_TGT_VECTOR, GM_TGT_DENSE, GM_TGT_HOPS_U8, GM_TGT_HOPS_U16 = 0, 1, 2, 3
+GM_TGT_VECTOR, GM_TGT_DENSE, GM_TGT_HOPS_U8, GM_TGT_HOPS_U16, GM_TGT_HOPS_PACKED = 0, 1, 2, 3, 4
 GM_OPT_RSGD, GM_OPT_RADAM = 0, 1
 (GM_OP_EXP, GM_OP_RETR, GM_OP_LOG, GM_OP_PROJU, GM_OP_PROJX, GM_OP_EGRAD2RGRAD, GM_OP_INNER, GM_OP_NORM2,
  GM_OP_TRANSP, GM_OP_RETR_QR, GM_OP_SPD_SQRTM) = range(11)
@@ -37,7 +37,7 @@ class Manifold(ctypes.Structure):
 class Pairs(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('idx64', ctypes.c_int32), ('P', ctypes.c_int64),
                 ('idx_i', ctypes.c_void_p), ('idx_j', ctypes.c_void_p), ('B', ctypes.c_int64),
-                ('nodes', ctypes.c_void_p)]
+                ('nodes', ctypes.c_void_p), ('k0', ctypes.c_int64)]
 
 
 class Loss(ctypes.Structure):
@@ -70,6 +70,12 @@ _PROTOTYPES = {
                                            ctypes.POINTER(Targets), ctypes.POINTER(Loss), _dbl, _vp, _vp, _vp, _vp]),
     'gm_product_loss': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl),
                                        ctypes.POINTER(Targets), ctypes.POINTER(Loss), _i64, _vp, _vp, _vp]),
+    'gm_pairs_metrics': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl), ctypes.POINTER(Pairs),
+                                        ctypes.POINTER(Targets), _i32, _vp, _vp]),
+    'gm_sne_row_stats': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl), _vp, _i64, _dbl, _i32,
+                                        _vp, _vp]),
+    'gm_sne_pair_terms': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl), _vp, _i64, _dbl, _i32,
+                                         _vp, _vp, _vp, _vp]),
     'gm_optim_step': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(Optim), _vp, _vp, _vp, _vp, _i64, _vp]),
     'gm_point_op': (ctypes.c_int, [ctypes.POINTER(Manifold), _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     'gm_bfs_workspace_bytes': (ctypes.c_size_t, [_i32, _i32]),

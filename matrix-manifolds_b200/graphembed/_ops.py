@@ -48,8 +48,9 @@ def _index_tensor(idx, device):
 class PairSet:
     """Which pairs a launch covers (mirrors gm_pairs_t); keeps the index tensors alive."""
 
-    def __init__(self, mode, P, idx_i=None, idx_j=None, B=0, nodes=None, idx64=0):
+    def __init__(self, mode, P, idx_i=None, idx_j=None, B=0, nodes=None, idx64=0, k0=0):
         self.mode, self.P, self.idx_i, self.idx_j, self.B, self.nodes, self.idx64 = mode, P, idx_i, idx_j, B, nodes, idx64
+        self.k0 = k0
 
     @staticmethod
     def elementwise(P):
@@ -66,21 +67,38 @@ class PairSet:
         return PairSet(L.GM_PAIRS_LIST, i.numel(), idx_i=i, idx_j=j, idx64=f64)
 
     @staticmethod
-    def triu(B, nodes=None, device=None):
+    def triu(B, nodes=None, device=None, k0=0, P=None):
         """All a<b pairs of a batch of B rows in torch.triu_indices(B, B, 1) order; `nodes` maps batch position
-        to row of the parameter (None: the batch *is* the tensor)."""
+        to row of the parameter (None: the batch *is* the tensor).  (k0, P) restricts the launch to pairs
+        [k0, k0+P) of the triangle (chunked validation, pair-sharded ranks)."""
         f64 = 0
         if nodes is not None:
             nodes, f64 = _index_tensor(nodes, device)
             if nodes.numel() != B:
                 raise ValueError('len(nodes) must equal B')
-        return PairSet(L.GM_PAIRS_TRIU, B * (B - 1) // 2, B=B, nodes=nodes, idx64=f64)
+        total = B * (B - 1) // 2
+        if P is None:
+            P = total - k0
+        if k0 < 0 or P < 0 or k0 + P > total:
+            raise ValueError(f'pair range [{k0}, {k0 + P}) outside the triangle of {total} pairs')
+        return PairSet(L.GM_PAIRS_TRIU, P, B=B, nodes=nodes, idx64=f64, k0=k0)
+
+    def slice(self, rank, world):
+        """The contiguous share of this pair set that `rank` of `world` ranks evaluates (sizes differ by <= 1)."""
+        base, extra = divmod(self.P, world)
+        lo = rank * base + min(rank, extra)
+        n = base + (1 if rank < extra else 0)
+        if self.mode == L.GM_PAIRS_TRIU:
+            return PairSet(self.mode, n, B=self.B, nodes=self.nodes, idx64=self.idx64, k0=self.k0 + lo)
+        if self.mode == L.GM_PAIRS_LIST:
+            return PairSet(self.mode, n, idx_i=self.idx_i[lo:lo + n], idx_j=self.idx_j[lo:lo + n], idx64=self.idx64)
+        raise ValueError('elementwise pair sets are not sharded')
 
     def c_struct(self):
         return L.Pairs(mode=self.mode, idx64=self.idx64, P=self.P,
                        idx_i=None if self.idx_i is None else self.idx_i.data_ptr(),
                        idx_j=None if self.idx_j is None else self.idx_j.data_ptr(), B=self.B,
-                       nodes=None if self.nodes is None else self.nodes.data_ptr())
+                       nodes=None if self.nodes is None else self.nodes.data_ptr(), k0=self.k0)
 
 
 def pairs_dist2(spec, xa, xb, pairs):
@@ -139,8 +157,14 @@ class TargetSpec:
             return TargetSpec(L.GM_TGT_HOPS_U16, h, max_sq=max_sq)
         raise RuntimeError('hop-count targets must be uint8 or uint16')
 
+    @staticmethod
+    def hops_packed(max_sq):
+        """Hop count in the top byte of the int32 second-endpoint index (LIST pairs, < 2^24 rows)."""
+        return TargetSpec(L.GM_TGT_HOPS_PACKED, None, max_sq=max_sq)
+
     def c_struct(self):
-        return L.Targets(mode=self.mode, reserved=0, data=self.data.data_ptr(), ld=self.ld, max_sq=float(self.max_sq))
+        return L.Targets(mode=self.mode, reserved=0, data=None if self.data is None else self.data.data_ptr(),
+                         ld=self.ld, max_sq=float(self.max_sq))
 
 
 def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, want_d2=False):
@@ -175,6 +199,59 @@ def product_loss(d2_list, sp_list, targets, loss, want_g=True):
         rc = L.lib().gm_product_loss(L.dtype_code(dtype), F, ptrs, sps, ctypes.byref(t), ctypes.byref(l), P,
                                      L.ptr(acc), L.ptr(g), L.stream_ptr(device))
     L.check(rc, 'gm_product_loss')
+    return acc, g
+
+
+def _factor_args(d2_list, sp_list):
+    F = len(d2_list)
+    ptrs = (ctypes.c_void_p * F)(*[d.data_ptr() for d in d2_list])
+    sps = (ctypes.c_double * F)(*[float(s) for s in sp_list])
+    return F, ptrs, sps
+
+
+def pairs_metrics(d2_list, sp_list, pairs, targets, squared=True, acc=None):
+    """Adds the validation-metric moments of the given pairs to `acc` (8 float64 slots):
+    [count, sum |m-g|/g, sum m, sum g, sum m^2, sum g^2, sum m g] with m = sqrt(sum_f sp_f d2_f), g = sqrt(target)
+    (squared=True) or m = d2_list[0], g = target (squared=False)."""
+    d2_list = [_prep(d) for d in d2_list]
+    dtype, device = d2_list[0].dtype, d2_list[0].device
+    if acc is None:
+        acc = torch.zeros(8, dtype=torch.float64, device=device)
+    if targets.mode in (L.GM_TGT_VECTOR, L.GM_TGT_DENSE) and targets.data.dtype != dtype:
+        raise RuntimeError('targets must have the dtype of the distances')
+    F, ptrs, sps = _factor_args(d2_list, sp_list)
+    p, t = pairs.c_struct(), targets.c_struct()
+    with torch.cuda.device(device):
+        rc = L.lib().gm_pairs_metrics(L.dtype_code(dtype), F, ptrs, sps, ctypes.byref(p), ctypes.byref(t),
+                                      int(bool(squared)), L.ptr(acc), L.stream_ptr(device))
+    L.check(rc, 'gm_pairs_metrics')
+    return acc
+
+
+def sne_kl(d2_list, sp_list, gdists, alpha, inclusive, want_g=True):
+    """KL objective with the stochastic-neighbour model over all pairs of a batch (condensed vectors).
+    Returns (acc[1+F] float64: [KL, sum_k g_k d2_f[k] ...], dKL/dm per pair)."""
+    d2_list = [_prep(d) for d in d2_list]
+    dtype, device, P = d2_list[0].dtype, d2_list[0].device, d2_list[0].numel()
+    gdists = _prep(gdists.to(dtype))
+    if gdists.numel() != P:
+        raise ValueError('graph and manifold distance vectors differ in length')
+    import math
+    B = math.ceil(math.sqrt(2 * P))
+    if B * (B - 1) // 2 != P:
+        raise ValueError(f'{P} is not the number of pairs of a batch')
+    F, ptrs, sps = _factor_args(d2_list, sp_list)
+    acc = torch.zeros(1 + F, dtype=torch.float64, device=device)
+    stats = torch.empty(3 * B, dtype=dtype, device=device)
+    g = torch.empty(P, dtype=dtype, device=device) if want_g else None
+    with torch.cuda.device(device):
+        st = L.stream_ptr(device)
+        rc = L.lib().gm_sne_row_stats(L.dtype_code(dtype), F, ptrs, sps, L.ptr(gdists), B, float(alpha),
+                                      int(bool(inclusive)), L.ptr(stats), st)
+        L.check(rc, 'gm_sne_row_stats')
+        rc = L.lib().gm_sne_pair_terms(L.dtype_code(dtype), F, ptrs, sps, L.ptr(gdists), B, float(alpha),
+                                       int(bool(inclusive)), L.ptr(stats), L.ptr(acc), L.ptr(g), st)
+        L.check(rc, 'gm_sne_pair_terms')
     return acc, g
 
 

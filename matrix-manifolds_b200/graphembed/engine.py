@@ -19,6 +19,17 @@ from .modules import ManifoldParameter
 from .parallel import RowShards, allreduce_step_buffers
 
 
+def pack_hops(idx_j, hops):
+    """Second-endpoint index and hop count of every pair in ONE int32 word: (hops << 24) | idx_j.  Needs fewer than
+    2^24 rows and hop counts < 255 (uint8).  Works on host or device tensors; this is the 4-byte-per-pair upload format
+    of `PairTrainer.step*(..., hops=None)` (GM_TGT_HOPS_PACKED)."""
+    if idx_j.dtype != torch.int32 or hops.dtype != torch.uint8:
+        raise ValueError('pack_hops: int32 indices and uint8 hop counts')
+    if idx_j.numel() and int(idx_j.max()) >= (1 << 24):
+        raise ValueError('pack_hops: row ids must be below 2^24')
+    return (idx_j | (hops.to(torch.int32) << 24)).contiguous()
+
+
 class PairTrainer:
     """Drives (I, J, hops) pair batches through a single-manifold embedding.
 
@@ -70,7 +81,12 @@ class PairTrainer:
     def step(self, idx_i, idx_j, hops, epoch=1):
         """One training step on device tensors; returns the (device, float64) loss of the batch."""
         pairs = _ops.PairSet.from_lists(idx_i, idx_j, self.x.device)
-        targets = _ops.TargetSpec.hops(hops, self.max_hops_sq)
+        if hops is None:  # hop counts packed into the top byte of idx_j (pack_hops)
+            if self.x.shape[0] > (1 << 24) or pairs.idx64:
+                raise ValueError('packed hop counts need int32 indices and fewer than 2^24 points')
+            targets = _ops.TargetSpec.hops_packed(self.max_hops_sq)
+        else:
+            targets = _ops.TargetSpec.hops(hops, self.max_hops_sq)
         loss_spec = self.obj.loss_spec(epoch=epoch, alpha=self.alpha)
         self.grad.zero_()
         self.acc.zero_()
@@ -134,10 +150,12 @@ class PairTrainer:
         """One step from PINNED host tensors in source-grouped (CSR-like) form, the natural output of a sampler that
         draws targets per BFS source: pairs offsets[g] <= k < offsets[g+1] are (sources[g], idx_j[k]) with hop count
         hops[k].  sources int32 (G,), offsets int64 (G+1,), idx_j int32 (P,), hops uint8/int16 (P,).  Uploads 5 bytes
-        per pair instead of 9; the first-endpoint index vector is expanded on the device (gm_expand_groups).
+        per pair instead of 9 -- or 4 with hops=None and idx_j = pack_hops(j, hops) -- and the first-endpoint index
+        vector is expanded on the device (gm_expand_groups).
         `next_batch` = the next step's (sources, offsets, idx_j, hops), uploaded on a second stream meanwhile."""
         P, G = idx_j.numel(), sources.numel()
-        self._ensure_staging(P, hops.dtype, G)
+        packed = hops is None  # idx_j carries the hop counts (pack_hops): 4 bytes per pair over PCIe
+        self._ensure_staging(P, torch.uint8 if packed else hops.dtype, G)
         cur = torch.cuda.current_stream(self.x.device)
 
         def upload(slot, batch):
@@ -146,7 +164,8 @@ class PairTrainer:
             ds[:s_.numel()].copy_(s_, non_blocking=True)
             do[:o_.numel()].copy_(o_, non_blocking=True)
             dj[:j_.numel()].copy_(j_, non_blocking=True)
-            dh[:h_.numel()].copy_(h_, non_blocking=True)
+            if h_ is not None:
+                dh[:h_.numel()].copy_(h_, non_blocking=True)
 
         if self._pending is not None and self._pending[0] is idx_j:
             slot, ev = self._pending[1], self._pending[2]
@@ -166,5 +185,5 @@ class PairTrainer:
             self._pending = (next_batch[2], nslot, ev)
         self._slot = 1 - slot
         _ops.expand_groups(ds[:G], do[:G + 1], di[:P])
-        loss = self.step(di[:P], dj[:P], dh[:P], epoch=epoch)
+        loss = self.step(di[:P], dj[:P], None if packed else dh[:P], epoch=epoch)
         return loss.item()

@@ -137,11 +137,14 @@ class _FusedObjective(torch.autograd.Function):
 
 class BatchedObjective(torch.nn.Module):
 
-    def __init__(self, objective_fn, dataset, embedding):
+    def __init__(self, objective_fn, dataset, embedding, shard=None):
+        """shard = (rank, world): evaluate only this rank's contiguous slice of every batch's pair triangle; the
+        caller sums losses and gradients over the ranks (TrainingEngine._combine_ranks)."""
         super().__init__()
         self.objective_fn = objective_fn
         self.dataset = dataset
         self.embedding = embedding
+        self.shard = shard
 
     def forward(self, indices, *args, **kwargs):
         emb = self.embedding
@@ -151,13 +154,21 @@ class BatchedObjective(torch.nn.Module):
                    and getattr(self.dataset, 'pdists', None) is not None
                    and self.dataset.pdists.device == emb.device and self.dataset.pdists.dtype == emb.xs[0].dtype)
         if not fusable:
+            if self.shard is not None:
+                raise RuntimeError('pair-sharded training needs an objective with a fused loss_spec (QuotientLoss, '
+                                   'StressLoss) and GPU-resident targets')
             return self.objective_fn(self.dataset[indices].to(emb.device), emb.compute_dists(indices), *args, **kwargs)
         if indices is None:
             pairs = _ops.PairSet.triu(emb.n)
         else:
             pairs = _ops.PairSet.triu(len(indices), indices, emb.device)
+        lo = 0
+        if self.shard is not None:
+            full_k0 = pairs.k0
+            pairs = pairs.slice(*self.shard)
+            lo = pairs.k0 - full_k0
         if emb.n_components == 1:
             targets = _ops.TargetSpec.dense(self.dataset.pdists)  # target gather fused into the pair kernel
         else:
-            targets = _ops.TargetSpec.vector(self.dataset[indices])
+            targets = _ops.TargetSpec.vector(self.dataset[indices][lo:lo + pairs.P])
         return _FusedObjective.apply(pairs, targets, loss_spec, emb.manifolds, emb.n_components, *emb.xs, *emb.scales)

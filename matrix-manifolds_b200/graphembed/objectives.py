@@ -5,6 +5,10 @@ the reference's graphembed/objectives.py:9-45 and run as one CUDA kernel (value,
 sum-reduction and derivative): csrc/gm_api.cu::product_loss_kernel.  When they
 are used through `BatchedObjective` the loss is fused into the pair kernel
 instead (graphembed/modules.py).
+
+`KLDiveregenceLoss` (spelling as in the reference, objectives.py:48-76) with the
+stochastic-neighbour inference model runs as two kernels (row statistics, pair
+terms: csrc/gm_objectives.cu) that also produce dKL/d mdists.
 """
 import abc
 
@@ -68,6 +72,39 @@ class StressLoss(ObjectiveFunction):
 
     def __str__(self):
         return 'stress_loss'
+
+
+class _SneKL(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, mdists, gdists, alpha, inclusive):
+        acc, g = _ops.sne_kl([mdists], [1.0], gdists, alpha, inclusive)
+        ctx.save_for_backward(g)
+        return acc[0].to(mdists.dtype)
+
+    @staticmethod
+    def backward(ctx, upstream):
+        g, = ctx.saved_tensors
+        return g * upstream, None, None, None
+
+
+class KLDiveregenceLoss(ObjectiveFunction):
+    r"""KL(p_x || p_z) (inclusive) or KL(p_z || p_x) between the stochastic-neighbour distributions induced by
+    theta_x = -alpha * gdists and theta_z = -mdists over all pairs of the batch."""
+
+    def __init__(self, inference_model, inclusive=True):
+        if inference_model == 'sste':
+            raise NotImplementedError('the stochastic-spanning-tree model (SSTE) is outside the B200 hot path')
+        if inference_model != 'sne':
+            raise ValueError(f'Inference model {inference_model} not supported.')
+        self.inference_model = inference_model
+        self.inclusive = inclusive
+
+    def __call__(self, gdists, mdists, *, epoch=None, alpha):
+        return _SneKL.apply(mdists, gdists, float(alpha), bool(self.inclusive))
+
+    def __str__(self):
+        return 'kl_loss'
 
 
 class Sum(ObjectiveFunction):

@@ -1,0 +1,326 @@
+"""TrainingEngine -- the epoch loop around the hot path, with the constructor keywords, defaults, batching rule,
+file names and call order of the reference's graphembed/train.py:22-352.
+
+Per epoch (`_train`, train.py:198-228): `perm = torch.randperm(N)`; node batches of `batch_size` (whole graph if
+None), tail batches shorter than `drop_last_n` dropped; per batch ONE fused kernel evaluates all B(B-1)/2 pair
+distances, the loss and the gradient (BatchedObjective), then the fused optimizer kernels run.  Validation
+(`_validate`, train.py:230-265) streams all N(N-1)/2 pairs through the distance + moments kernels
+(metrics.validation_moments) instead of materialising them.
+
+Multi-GPU: one process per GPU (torchrun).  With `process_group` set, every rank evaluates a contiguous slice of
+each batch's pair triangle, the dense gradients and the loss are summed with one all-reduce per step, and all ranks
+apply the same update.  The reference's nn.DataParallel path (train.py:107-109,203-204) drops pairs across device
+chunks; this keeps every pair.  Plots (`add_figure`) are not produced."""
+import logging
+import math
+import os
+import tempfile
+
+import torch
+
+from . import metrics as metrics_mod
+from .modules import BatchedObjective
+from .utils import Timer, check_mkdir, latest_path_by_basename_numeric_order
+
+logger = logging.getLogger(__name__)
+
+# every attribute of the engine with its default (train.py:22-44); the first three are mandatory
+default_attrs_ = dict(
+    embedding=None, optimizer=None, objective_fn=None, alpha=None, n_epochs=2000, batch_size=None, drop_last_n=50,
+    burnin_epochs=None, burnin_lower_lr=False, burnin_higher_lr=False, perturb_every_epochs=None,
+    stabilize_every_epochs=None, lr_scheduler=None, min_lr=None, metrics=None, main_metric_idx=None,
+    lazy_metrics=None, val_every_epochs=None, save_metrics_every_epochs=None, save_every_epochs=None, save_dir=None,
+    snapshot_path=None)
+
+
+class ScalarLog:
+    """SummaryWriter stand-in that also keeps every scalar in memory: `history[tag] = [(step, value), ...]`.
+    Forwards to a real tensorboard writer when one can be created."""
+
+    def __init__(self, log_dir=None, tensorboard=True):
+        self.history = {}
+        self._tb = None
+        if tensorboard and log_dir is not None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self._tb = SummaryWriter(log_dir=log_dir)
+            except Exception:  # tensorboard is optional
+                self._tb = None
+
+    def add_scalar(self, tag, value, step):
+        v = float(value)
+        self.history.setdefault(tag, []).append((int(step), v))
+        if self._tb is not None:
+            self._tb.add_scalar(tag, v, step)
+
+    def add_figure(self, *args, **kwargs):
+        pass
+
+    def close(self):
+        if self._tb is not None:
+            self._tb.close()
+
+
+class _Snapshot:
+    """What `best_struct['embedding']` needs to be: something with a state_dict() (train.py:324-341)."""
+
+    def __init__(self, module):
+        self._state = {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+    def state_dict(self):
+        return self._state
+
+
+class TrainingEngine:
+
+    def __init__(self, **kwargs):
+        self.__dict__.update(default_attrs_)
+        self.process_group = None
+        self.tensorboard = True
+        self.__dict__.update(kwargs)
+        if not self.embedding or not self.optimizer or not self.objective_fn:
+            raise ValueError('`embedding`, `optimizer`, and `objective_fn` must be specified to construct a '
+                             'TrainingEngine.')
+        if self.burnin_lower_lr and self.burnin_higher_lr:
+            raise ValueError('`burnin_lower_lr` and `burnin_higher_lr` are mutually exclusive.')
+        if not isinstance(self.optimizer, (tuple, list)):
+            self.optimizer = [self.optimizer]
+        if self.lr_scheduler is not None and not isinstance(self.lr_scheduler, (tuple, list)):
+            self.lr_scheduler = [self.lr_scheduler]
+        if self.burnin_epochs is None:
+            self.burnin_epochs = 0
+        if self.perturb_every_epochs is None:
+            self.perturb_every_epochs = self.n_epochs + 1
+        if self.stabilize_every_epochs is None:
+            self.stabilize_every_epochs = self.n_epochs + 1
+        if self.metrics is None:
+            self.metrics = ['pearsonr', 'average_distortion']
+        if self.main_metric_idx is None:
+            self.main_metric_idx = 0
+        if self.val_every_epochs is None:
+            self.val_every_epochs = self.n_epochs + 1
+        if self.save_metrics_every_epochs is None:
+            self.save_metrics_every_epochs = self.n_epochs // self.val_every_epochs * self.val_every_epochs
+        if self.save_every_epochs is None:
+            self.save_every_epochs = self.n_epochs
+        if self.save_dir is None:
+            self.save_dir = tempfile.gettempdir()
+            check_mkdir(self.save_dir)
+            logger.info('The save dir is (%s)', self.save_dir)
+        if self.snapshot_path:
+            self._load()
+
+    # ---- multi-GPU helpers ---------------------------------------------------------------------------------------
+    @property
+    def _world(self):
+        return 1 if self.process_group is None else torch.distributed.get_world_size(self.process_group)
+
+    @property
+    def _rank(self):
+        return 0 if self.process_group is None else torch.distributed.get_rank(self.process_group)
+
+    def __call__(self, graph_dataset, last_step=0):
+        shard = None if self._world == 1 else (self._rank, self._world)
+        self.batched_obj = BatchedObjective(self.objective_fn, graph_dataset, self.embedding, shard=shard)
+        if self.burnin_epochs > 0 and self.alpha is not None:
+            self._burnin_pre()
+            self._burnin(graph_dataset)
+            self._burnin_post()
+        self.pending_metric_results = []
+        self.pending_metric_idx = 0
+        self.best_struct = dict(epoch=0, loss=1e8, embedding=_Snapshot(self.embedding))
+        self.global_step = last_step
+        self.writer = ScalarLog(self.save_dir if self._rank == 0 else None, self.tensorboard)
+        try:
+            for epoch in range(1, self.n_epochs + 1):
+                self._run_epoch(graph_dataset, self.alpha, epoch)
+                if self._check_early_break():
+                    logger.warning('Early breaking (epoch=%d)', epoch)
+                    break
+        finally:
+            if self._rank == 0:
+                self._save_best()
+            self.writer.close()
+        self._consume_pending_metric_results(wait=True)
+
+    # ---- burn-in (train.py:135-166) --------------------------------------------------------------------------------
+    def _scale_lrs(self, factor):
+        for optim in self.optimizer:
+            for group in optim.param_groups:
+                group['lr'] *= factor
+
+    def _burnin_pre(self):
+        self.embedding.burnin(True)
+        self.global_step = 0
+        self.writer = ScalarLog(os.path.join(self.save_dir, 'burnin') if self._rank == 0 else None, self.tensorboard)
+        if self.burnin_lower_lr:
+            self._scale_lrs(0.1)
+        elif self.burnin_higher_lr:
+            self._scale_lrs(10)
+
+    def _burnin(self, graph_dataset):
+        for i, alpha in enumerate([self.alpha / d for d in range(4, 0, -1)]):
+            logger.info(f'Running burn-in epochs with alpha={alpha:.5f}')
+            for epoch in range(i * self.burnin_epochs + 1, (i + 1) * self.burnin_epochs + 1):
+                self._train(graph_dataset, alpha, epoch)
+                if epoch % self.stabilize_every_epochs:  # (sic) stabilises when NOT a multiple, train.py:157
+                    with Timer('stabilizing'), torch.no_grad():
+                        self.embedding.stabilize()
+
+    def _burnin_post(self):
+        if self.burnin_lower_lr:
+            self._scale_lrs(10)
+        elif self.burnin_higher_lr:
+            self._scale_lrs(0.1)
+        self.embedding.burnin(False)
+        self.writer.close()
+
+    # ---- one epoch ------------------------------------------------------------------------------------------------
+    def _run_epoch(self, graph_dataset, alpha, epoch):
+        with Timer('training'):
+            loss = self._train(graph_dataset, alpha, epoch)
+        self._lr_scheduler_step(loss, epoch)
+        with Timer('checking if better model'):
+            self._check_best(loss, epoch)
+        if epoch % self.perturb_every_epochs == 0:
+            with Timer('perturbing'), torch.no_grad():
+                self.embedding.perturb(1 / epoch)
+        if epoch % self.stabilize_every_epochs == 0:
+            with Timer('stabilizing'), torch.no_grad():
+                self.embedding.stabilize()
+        if epoch % self.val_every_epochs == 0:
+            with Timer('validating'), torch.no_grad():
+                self._validate(graph_dataset, epoch)
+            self._consume_pending_metric_results()
+        if epoch % self.save_every_epochs == 0 and self._rank == 0:
+            self._save(epoch)
+
+    def _train(self, graph_dataset, alpha, epoch):
+        n_points = len(graph_dataset)
+        bs = n_points if self.batch_size is None else min(n_points, self.batch_size)
+        perm = torch.randperm(n_points)  # default device / default generator, as train.py:206
+        total_loss = 0
+        for i in range(0, n_points, bs):
+            indices = perm[i:(i + bs)]
+            if len(indices) < self.drop_last_n:
+                break
+            loss = self.batched_obj(indices, alpha=alpha, epoch=epoch).sum()
+            for optim in self.optimizer:
+                optim.zero_grad()
+            loss.backward()
+            if self._world > 1:
+                loss = self._combine_ranks(loss)
+            for optim in self.optimizer:
+                optim.step()
+            self.global_step += 1
+            self.writer.add_scalar(str(self.objective_fn), loss / len(indices), self.global_step)
+            total_loss += loss.item()
+        logger.debug('epoch %d, train loss %.5f', epoch, total_loss / n_points)
+        return total_loss
+
+    def _combine_ranks(self, loss):
+        """Sum the per-rank partial gradients and loss (each rank covered a slice of the batch's pairs)."""
+        dist = torch.distributed
+        for optim in self.optimizer:
+            for group in optim.param_groups:
+                for p in group['params']:
+                    if p.grad is not None:
+                        dist.all_reduce(p.grad, group=self.process_group)
+        loss = loss.detach().clone()
+        dist.all_reduce(loss, group=self.process_group)
+        return loss
+
+    def _validate(self, graph_dataset, epoch):
+        n = len(graph_dataset)
+        total = n * (n - 1) // 2
+        streamed = all(m in metrics_mod.STREAMED_METRICS for m in self.metrics) and not self.lazy_metrics \
+            and hasattr(self.embedding, 'manifolds')
+        values = {}
+        if streamed:
+            base, extra = divmod(total, self._world)
+            lo = self._rank * base + min(self._rank, extra)
+            hi = lo + base + (1 if self._rank < extra else 0)
+            acc = metrics_mod.validation_moments(self.embedding, graph_dataset, pair_range=(lo, hi))
+            if self._world > 1:
+                torch.distributed.all_reduce(acc, group=self.process_group)
+            mom = metrics_mod.PairMoments(acc.cpu())
+            values = {m: mom.metric(m) for m in self.metrics}
+        else:
+            gpdists = graph_dataset[None].sqrt()
+            mpdists = self.embedding.compute_dists(None).sqrt_()
+            if self.lazy_metrics:
+                mp_np = mpdists.cpu().numpy()
+                for name, f in self.lazy_metrics.items():
+                    self.pending_metric_results.append((epoch, name, f(mp_np)))
+            gpdists = gpdists.to(mpdists.device)
+            values = {m: float(getattr(metrics_mod, m)(mpdists, gpdists)) for m in self.metrics}
+        self.embedding.add_stats(self.writer, epoch)
+        val_obj = None
+        for i, m in enumerate(self.metrics):
+            self.writer.add_scalar(m, values[m], epoch)
+            if i == self.main_metric_idx:
+                val_obj = values[m]
+        logger.info('epoch %d, val obj %.5f', epoch, val_obj)
+        return val_obj
+
+    def _consume_pending_metric_results(self, wait=False):
+        import numpy as np
+        while self.pending_metric_idx < len(self.pending_metric_results):
+            epoch, name, future = self.pending_metric_results[self.pending_metric_idx]
+            if not wait and not future.done():
+                break
+            value = future.result(None if wait else 0)
+            if isinstance(value, float):
+                self.writer.add_scalar(name, value, epoch)
+            else:  # (means, stds) of a per-layer metric
+                means, stds = value
+                self.writer.add_scalar('AUC_{}'.format(name), metrics_mod.area_under_curve(means)[0], epoch)
+                if epoch % self.save_metrics_every_epochs == 0:
+                    np.save(os.path.join(self.save_dir, f'mean_{name}_{epoch}'), means)
+                    np.save(os.path.join(self.save_dir, f'std_{name}_{epoch}'), stds)
+            self.pending_metric_idx += 1
+
+    def _lr_scheduler_step(self, loss, epoch):
+        if self.lr_scheduler:
+            for lrs in self.lr_scheduler:
+                if isinstance(lrs, torch.optim.lr_scheduler.ReduceLROnPlateau):
+                    lrs.step(loss)
+                else:
+                    lrs.step(epoch)
+
+    def _check_early_break(self):
+        if self.min_lr is None:
+            return False
+        return all(group['lr'] <= self.min_lr + 1e-10 for optim in self.optimizer for group in optim.param_groups)
+
+    def _check_best(self, loss, epoch):
+        if loss < self.best_struct['loss']:
+            self.best_struct = dict(epoch=epoch, loss=loss, embedding=_Snapshot(self.embedding))
+
+    # ---- on-disk formats (train.py:331-352) ---------------------------------------------------------------------
+    def _save(self, epoch):
+        torch.save(self.embedding.state_dict(), os.path.join(self.save_dir, f'embedding_{epoch}.pth'))
+
+    def _save_best(self):
+        epoch, loss, embedding = (self.best_struct[k] for k in ('epoch', 'loss', 'embedding'))
+        torch.save(embedding.state_dict(), os.path.join(self.save_dir, 'best_embedding.pth'))
+        with open(os.path.join(self.save_dir, 'best_loss_{}'.format(epoch)), 'w') as f:
+            f.write(f'{loss:.6f}')
+
+    def _load(self):
+        path = latest_path_by_basename_numeric_order(os.path.join(self.snapshot_path, 'embedding_*.pth'))
+        self.embedding.load_state_dict(torch.load(path, map_location=self.embedding.device))
+
+
+class SineLRScheduler(torch.optim.lr_scheduler._LRScheduler):
+    """lr_i(t) = base_i + (eta_max_i - base_i) (1 - cos(pi t / T_max_i)) / 2  (train.py:355-374)."""
+
+    def __init__(self, optimizer, T_max, eta_max=1, last_epoch=-1):
+        groups = len(optimizer.param_groups)
+        self.T_max = list(T_max) if isinstance(T_max, (list, tuple)) else [T_max] * groups
+        self.eta_max = list(eta_max) if isinstance(eta_max, (list, tuple)) else [eta_max] * groups
+        super().__init__(optimizer, last_epoch)
+
+    def get_lr(self):
+        return [base + (self.eta_max[i] - base) * (1 - math.cos(math.pi * self.last_epoch / self.T_max[i])) / 2
+                for i, base in enumerate(self.base_lrs)]

@@ -501,6 +501,50 @@ def stress_loss(g, m):  # objectives.py:41-42
     return (m - g).pow(2).sum()
 
 
+def _condensed_to_rows(theta):  # inference/stochastic_neighbors.py:13-18: n x (n-1) matrix of theta_ij, j != i
+    n = math.ceil(math.sqrt(2 * theta.shape[0]))
+    assert n * (n - 1) // 2 == theta.shape[0]
+    tm = torch.ones(n, n - 1, dtype=torch.bool).triu()
+    mat = theta.new_empty(n, n - 1)
+    mat = mat.masked_scatter(tm, theta)              # row i, columns >= i  <- pairs (i, j > i)
+    mat_t = mat.T.masked_scatter(~tm.T, theta)       # transposed fill     <- pairs (j < i, i)
+    return mat_t.T, tm
+
+
+def sne_log_partition(theta, ret_margs=False):  # inference/stochastic_neighbors.py:11-24
+    mat, tm = _condensed_to_rows(theta)
+    logz = torch.logsumexp(mat, dim=1).sum()
+    if not ret_margs:
+        return logz, None
+    margs = torch.softmax(mat, dim=1)
+    margs = margs.masked_select(tm) + margs.T.masked_select(~tm.T)
+    return logz, margs
+
+
+def kl_sne_loss(g, m, alpha, inclusive=True):  # objectives.py:61-74
+    theta_x, theta_z = -alpha * g, -m
+    if not inclusive:
+        theta_x, theta_z = theta_z, theta_x
+    a_x, margs_x = sne_log_partition(theta_x, ret_margs=True)
+    a_z, _ = sne_log_partition(theta_z, ret_margs=False)
+    return a_z - a_x - margs_x @ (theta_z - theta_x)
+
+
+def pearsonr(x, y):  # metrics.py:13-17
+    xm, ym = x - x.mean(), y - y.mean()
+    return xm @ ym / (xm.norm() * ym.norm())
+
+
+def average_distortion(mpdists, gpdists):  # metrics.py:46-56
+    return torch.mean(torch.abs(mpdists - gpdists) / gpdists)
+
+
+def validation_metrics(oracles, xs, scales, targets_sq_condensed):  # train.py:230-265 (the two default metrics)
+    g = targets_sq_condensed.sqrt()
+    m = product_dist2(oracles, xs, scales, lambda o, x: o.pdist2(x)).sqrt()
+    return dict(pearsonr=pearsonr(m, g).item(), average_distortion=average_distortion(m, g).item())
+
+
 def product_dist2(oracles, xs, scales, pair_fn):  # modules.py:84-88
     return sum(torch.nn.functional.softplus(s) * pair_fn(o, x) for o, x, s in zip(oracles, xs, scales))
 

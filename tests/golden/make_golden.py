@@ -151,11 +151,117 @@ def make_training_run():
     return out
 
 
+class _Recorder:
+    """Stands in for tensorboard's SummaryWriter inside the reference TrainingEngine."""
+    last = None
+
+    def __init__(self, log_dir=None):
+        self.scalars = {}
+        _Recorder.last = self
+
+    def add_scalar(self, tag, value, step):
+        self.scalars.setdefault(tag, []).append((int(step), float(value)))
+
+    def add_figure(self, *a, **k):
+        pass
+
+    add_histogram = add_figure
+
+
+def make_objectives(dtype):
+    """KL divergence with the stochastic-neighbour model (objectives.py:48-76), both directions: value and gradient."""
+    from graphembed.objectives import KLDiveregenceLoss
+    torch.set_default_dtype(dtype)
+    torch.manual_seed(11)
+    n = 13
+    P = n * (n - 1) // 2
+    g = torch.rand(P, dtype=dtype) * 0.9 + 0.1
+    m0 = torch.rand(P, dtype=dtype) * 2.0 + 0.05
+    out = dict(g=g.numpy(), m=m0.numpy(), alpha=np.array(3.5))
+    for inc in (True, False):
+        m = m0.clone().requires_grad_()
+        loss = KLDiveregenceLoss('sne', inclusive=inc)(g, m, alpha=3.5)
+        loss.backward()
+        out[f'kl_{int(inc)}_loss'] = np.array(loss.item())
+        out[f'kl_{int(inc)}_grad'] = m.grad.numpy()
+    # validation metrics on plain vectors (metrics.py:13-17,46-56)
+    import graphembed.metrics as M
+    out['pearsonr'] = np.array(M.pearsonr(m0, g).item())
+    out['average_distortion'] = np.array(M.average_distortion(m0, g).item())
+    return out
+
+
+def make_engine_runs():
+    """The reference's own TrainingEngine (train.py) for 3 epochs with validation every epoch on a 63-node tree:
+    (a) BASELINE config 1 in miniature: SPD 3x3, QuotientLoss, RSGD(exact, clip 20), full batch;
+    (b) the same with node mini-batches of 52 (tail batch of 11 < drop_last_n is dropped);
+    (c) example_config.yaml in miniature: SPD 2x2, KL/SNE loss, alpha 10, RAdam(clip 100), stabilize every 2 epochs;
+    (d) product SPD3 x Lorentz5, QuotientLoss, RAdam exact."""
+    import tempfile
+    import types
+    import networkx as nx
+    from scipy.sparse.csgraph import shortest_path
+    import graphembed.train as T
+    from graphembed.objectives import KLDiveregenceLoss
+    plt = sys.modules['matplotlib.pyplot']
+    plt.scatter = plt.gcf = plt.close = lambda *a, **k: None
+    T.SummaryWriter = _Recorder
+    torch.set_default_dtype(torch.float64)
+    g = nx.balanced_tree(2, 5)  # 63 nodes
+    n = g.number_of_nodes()
+    hops = shortest_path(nx.to_scipy_sparse_array(g), unweighted=True)
+    cond = torch.tensor(hops[np.triu_indices(n, 1)])
+    out = dict(edges=np.array(g.edges()), hops_condensed=cond.numpy())
+    runs = {
+        'spd3_full': (lambda: [SymmetricPositiveDefinite(3)], QuotientLoss,
+                      lambda ps: RiemannianSGD(ps, lr=0.01, max_grad_norm=20, exact=True), dict(alpha=1.0)),
+        'spd3_batched': (lambda: [SymmetricPositiveDefinite(3)], QuotientLoss,
+                         lambda ps: RiemannianSGD(ps, lr=0.01, max_grad_norm=20, exact=True),
+                         dict(alpha=1.0, batch_size=52)),
+        'spd2_kl': (lambda: [SymmetricPositiveDefinite(2)], lambda: KLDiveregenceLoss('sne', inclusive=True),
+                    lambda ps: RiemannianAdam(ps, lr=0.01, max_grad_norm=100, exact=False),
+                    dict(alpha=10.0, stabilize_every_epochs=2)),
+        'prod_radam': (lambda: [SymmetricPositiveDefinite(3), Lorentz(5)], QuotientLoss,
+                       lambda ps: RiemannianAdam(ps, lr=0.01, max_grad_norm=100, exact=True), dict(alpha=1.0)),
+    }
+    for tag, (mans, mkobj, mkopt, extra) in runs.items():
+        torch.manual_seed(42)
+        emb = ManifoldEmbedding(n, mans())
+        for i, x in enumerate(emb.xs):
+            out[f'{tag}_x0_{i}'] = x.data.clone().numpy()
+        obj = mkobj()
+        with tempfile.TemporaryDirectory() as tmp:
+            eng = T.TrainingEngine(embedding=emb, optimizer=mkopt(emb.xs), objective_fn=obj, n_epochs=3,
+                                   val_every_epochs=1, save_dir=tmp, **extra)
+            torch.manual_seed(1234)  # the engine draws one randperm per epoch from the global CPU generator
+            eng(GraphDataset(cond.clone()))
+            out[f'{tag}_files'] = np.array(sorted(os.listdir(tmp)))
+            best = [f for f in os.listdir(tmp) if f.startswith('best_loss_')][0]
+            out[f'{tag}_best'] = np.array([float(best.split('_')[-1]), float(open(os.path.join(tmp, best)).read())])
+            sd = torch.load(os.path.join(tmp, 'best_embedding.pth'))
+            out[f'{tag}_state_keys'] = np.array(sorted(sd.keys()))
+        rec = _Recorder.last.scalars
+        out[f'{tag}_step_loss'] = np.array([v for _, v in rec[str(obj)]])
+        out[f'{tag}_pearsonr'] = np.array([v for _, v in rec['pearsonr']])
+        out[f'{tag}_average_distortion'] = np.array([v for _, v in rec['average_distortion']])
+        for i, x in enumerate(emb.xs):
+            out[f'{tag}_xT_{i}'] = x.data.clone().numpy()
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'new':  # only the fixtures added after the first batch
+        for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
+            np.savez_compressed(os.path.join(HERE, f'objectives_{tag}.npz'), **make_objectives(dtype))
+        np.savez_compressed(os.path.join(HERE, 'engine_runs_f64.npz'), **make_engine_runs())
+        return
     for name in CASES:
         for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
             np.savez_compressed(os.path.join(HERE, f'{name}_{tag}.npz'), **make_case(name, dtype, seed=7))
     np.savez_compressed(os.path.join(HERE, 'training_run_f64.npz'), **make_training_run())
+    for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
+        np.savez_compressed(os.path.join(HERE, f'objectives_{tag}.npz'), **make_objectives(dtype))
+    np.savez_compressed(os.path.join(HERE, 'engine_runs_f64.npz'), **make_engine_runs())
     print('wrote', len(os.listdir(HERE)) - 1, 'fixtures to', HERE)
 
 

@@ -36,8 +36,12 @@ def test_argument_validation_without_gpu():
     assert lib.gm_supported(ctypes.byref(bad)) == 0
     bad = L.Manifold(kind=L.GM_SPD_AI, dtype=L.GM_F32, n=4, p=0, flags=L.GM_FAST_CHOL, reserved=0, wmin=0, wmax=1)
     assert lib.gm_supported(ctypes.byref(bad)) == 0
-    pairs = L.Pairs(mode=L.GM_PAIRS_TRIU, idx64=0, P=7, idx_i=None, idx_j=None, B=5, nodes=None)  # 5*4/2 != 7
+    pairs = L.Pairs(mode=L.GM_PAIRS_TRIU, idx64=0, P=11, idx_i=None, idx_j=None, B=5, nodes=None)  # > 5*4/2
     assert lib.gm_pairs_dist2(ctypes.byref(man), None, None, ctypes.byref(pairs), None, None) == -1
+    pairs = L.Pairs(mode=L.GM_PAIRS_TRIU, idx64=0, P=7, idx_i=None, idx_j=None, B=5, nodes=None, k0=4)  # 4+7 > 10
+    assert lib.gm_pairs_dist2(ctypes.byref(man), None, None, ctypes.byref(pairs), None, None) == -1
+    pairs = L.Pairs(mode=L.GM_PAIRS_TRIU, idx64=0, P=6, idx_i=None, idx_j=None, B=5, nodes=None, k0=4)  # slice ok
+    assert lib.gm_pairs_dist2(ctypes.byref(man), None, None, ctypes.byref(pairs), None, None) == -3
     pairs = L.Pairs(mode=L.GM_PAIRS_TRIU, idx64=0, P=10, idx_i=None, idx_j=None, B=5, nodes=None)
     assert lib.gm_pairs_dist2(ctypes.byref(man), None, None, ctypes.byref(pairs), None, None) == -3  # NULL data
     empty = L.Pairs(mode=L.GM_PAIRS_LIST, idx64=0, P=0, idx_i=None, idx_j=None, B=0, nodes=None)
@@ -98,3 +102,97 @@ def test_reference_api_surface():
         manifolds.Grassmann(5, 2, retr='nope')
     assert manifolds.SymmetricPositiveDefinite(4).dim == 10 and manifolds.Lorentz(11).dim == 10
     assert manifolds.Grassmann(6, 2).dim == 8 and str(manifolds.Lorentz(5)) == 'Lorentzian space of dimension 5'
+
+
+def test_new_entry_points_validate_arguments():
+    """gm_pairs_metrics / gm_sne_* / packed hop targets: bad arguments are rejected before any launch."""
+    from graphembed import _lib as L
+    lib = L.lib()
+    one = (ctypes.c_void_p * 1)(ctypes.c_void_p(16))
+    sp = (ctypes.c_double * 1)(1.0)
+    pairs = L.Pairs(mode=L.GM_PAIRS_ELEMENTWISE, idx64=0, P=0, idx_i=None, idx_j=None, B=0, nodes=None, k0=0)
+    tg = L.Targets(mode=L.GM_TGT_VECTOR, reserved=0, data=None, ld=0, max_sq=1.0)
+    acc = ctypes.c_void_p(32)
+    assert lib.gm_pairs_metrics(L.GM_F32, 1, one, sp, ctypes.byref(pairs), ctypes.byref(tg), 1, acc, None) == 0  # empty
+    assert lib.gm_pairs_metrics(L.GM_F32, 9, one, sp, ctypes.byref(pairs), ctypes.byref(tg), 1, acc, None) == -1
+    assert lib.gm_pairs_metrics(5, 1, one, sp, ctypes.byref(pairs), ctypes.byref(tg), 1, acc, None) == -1
+    pairs.P = 4
+    assert lib.gm_pairs_metrics(L.GM_F32, 1, one, sp, ctypes.byref(pairs), ctypes.byref(tg), 1, acc, None) == -3
+    assert lib.gm_sne_row_stats(L.GM_F64, 1, one, sp, None, 1, 1.0, 1, None, None) == 0  # B < 2: nothing to do
+    assert lib.gm_sne_row_stats(L.GM_F64, 1, one, sp, None, 5, 1.0, 1, None, None) == -3
+    assert lib.gm_sne_pair_terms(L.GM_F64, 0, one, sp, None, 5, 1.0, 1, None, None, None, None) == -1
+    # packed hop counts need int32 LIST pairs
+    man = L.Manifold(kind=L.GM_SPD_AI, dtype=L.GM_F32, n=4, p=0, flags=0, reserved=0, wmin=1e-8, wmax=1e8)
+    loss = L.Loss(kind=L.GM_LOSS_QUOTIENT, inc_l1=1, inc_l2=1, reserved=0, alpha=1.0, eps=0.5)
+    tgp = L.Targets(mode=L.GM_TGT_HOPS_PACKED, reserved=0, data=None, ld=0, max_sq=9.0)
+    p64 = L.Pairs(mode=L.GM_PAIRS_LIST, idx64=1, P=3, idx_i=16, idx_j=16, B=0, nodes=None, k0=0)
+    assert lib.gm_pairs_loss_fused(ctypes.byref(man), None, ctypes.byref(p64), ctypes.byref(tgp), ctypes.byref(loss),
+                                   1.0, None, None, None, None) == -1
+    ptri = L.Pairs(mode=L.GM_PAIRS_TRIU, idx64=0, P=3, idx_i=None, idx_j=None, B=3, nodes=None, k0=0)
+    assert lib.gm_pairs_loss_fused(ctypes.byref(man), None, ctypes.byref(ptri), ctypes.byref(tgp), ctypes.byref(loss),
+                                   1.0, None, None, None, None) == -1
+
+
+def test_pair_set_slices_cover_the_triangle():
+    from graphembed import _ops
+    ps = _ops.PairSet.triu(9)
+    parts = [ps.slice(r, 4) for r in range(4)]
+    assert [p.P for p in parts] == [9, 9, 9, 9] and [p.k0 for p in parts] == [0, 9, 18, 27]
+    parts = [_ops.PairSet.triu(5).slice(r, 3) for r in range(3)]
+    assert [(p.k0, p.P) for p in parts] == [(0, 4), (4, 3), (7, 3)]
+    with pytest.raises(ValueError):
+        _ops.PairSet.triu(5, k0=8, P=3)
+
+
+def test_yaml_config_grammar(tmp_path):
+    """object / closure nodes of the run.py YAML schema (example_config.yaml) build the drop-in classes."""
+    from graphembed.config import parse_config
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    from graphembed.objectives import KLDiveregenceLoss
+    cfg = tmp_path / 'c.yaml'
+    cfg.write_text("""
+save_dir_root: './runs/run'
+input_graph: 'g.edges.gz'
+embedding:
+  closure:
+    name: graphembed.modules.ManifoldEmbedding
+    params:
+      manifolds:
+        - object:
+            name: graphembed.manifolds.SymmetricPositiveDefinite
+            params:
+              n: 2
+              use_stein_div: False
+objective_fn:
+  closure:
+    name: graphembed.objectives.KLDiveregenceLoss
+    params:
+      inference_model: 'sne'
+      inclusive: True
+training_params:
+  alpha: 10.0
+  n_epochs: 1500
+  batch_size: null
+embedding_optimizer:
+  closure:
+    name: graphembed.optim.RiemannianAdam
+    params:
+      lr: 0.01
+      max_grad_norm: 100
+      exact: False
+lr:
+  object:
+    name: math.sqrt
+    params: [16.0]
+""")
+    c = parse_config(str(cfg))
+    assert callable(c['embedding']) and callable(c['embedding_optimizer'])
+    assert isinstance(c['objective_fn'], KLDiveregenceLoss) and c['objective_fn'].inclusive is True
+    assert c['training_params'] == dict(alpha=10.0, n_epochs=1500, batch_size=None)
+    assert c['lr'] == 4.0
+    p = torch.nn.Parameter(torch.zeros(2, 2, 2))
+    p.manifold = SymmetricPositiveDefinite(2)
+    opt = c['embedding_optimizer']([p])
+    assert type(opt).__name__ == 'RiemannianAdam' and opt.defaults['lr'] == 0.01 and opt.defaults['max_grad_norm'] == 100
+    with pytest.raises(RuntimeError, match='CUDA'):  # the closure reaches the (GPU-only) initialiser
+        c['embedding'](5)

@@ -99,3 +99,45 @@ def test_live_reference_if_present():
     ref = Lorentz(6)
     x = ref.rand(9, ir=0.5).double()
     assert rel_err(O.LorentzOracle(6).pdist2(x), ref.pdist(x, squared=True)) < 1e-12
+
+
+# ---- objectives / metrics / epoch loop added with the TrainingEngine row ------------------------
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+def test_kl_sne_and_metrics_vs_reference(tag):
+    g = load_golden('objectives', tag)
+    t = 1e-12 if tag == 'f64' else 1e-5
+    for inc in (1, 0):
+        m = g['m'].clone().requires_grad_()
+        loss = O.kl_sne_loss(g['g'], m, float(g['alpha']), inclusive=bool(inc))
+        loss.backward()
+        assert abs(loss.item() - g[f'kl_{inc}_loss'].item()) <= t * abs(g[f'kl_{inc}_loss'].item())
+        assert rel_err(m.grad, g[f'kl_{inc}_grad']) < t
+    assert abs(O.pearsonr(g['m'], g['g']).item() - g['pearsonr'].item()) < t
+    assert abs(O.average_distortion(g['m'], g['g']).item() - g['average_distortion'].item()) < t
+
+
+@pytest.mark.parametrize('tag', ['spd3_full', 'spd3_batched', 'spd2_kl', 'prod_radam'])
+def test_epoch_loop_vs_reference_training_engine(tag):
+    """oracle/engine_oracle.py against the real TrainingEngine's step losses, per-epoch metrics and final points."""
+    import engine_oracle as E
+    from helpers_engine import RUNS, ENGINE_SEED, N_EPOCHS, load_engine_golden
+    g = load_engine_golden()
+    factors, objective, (oname, okw), ekw = RUNS[tag]
+    oracles = [O.SpdOracle(n) if fam == 'spd' else O.LorentzOracle(n) for fam, n in factors]
+    xs = [g[f'{tag}_x0_{i}'].clone() for i in range(len(factors))]
+    scales = [torch.tensor(0.5, dtype=torch.float64) for _ in factors]
+    if objective == 'quotient':
+        loss_fn = lambda t, m, alpha, epoch: O.quotient_loss(t, m, alpha, epoch)
+    else:
+        loss_fn = lambda t, m, alpha, epoch: O.kl_sne_loss(t, m, alpha, inclusive=True)
+    step = O.rsgd_step if oname == 'rsgd' else O.radam_step
+    step_fn = lambda f, o, x, grad, st: step(o, x, grad, st, **okw)
+    ekw = dict(ekw)
+    out = E.run_engine(oracles, xs, scales, g['hops_condensed'], loss_fn, step_fn, N_EPOCHS, ekw.pop('alpha'),
+                       seed=ENGINE_SEED, **ekw)
+    assert np.allclose(out['step_loss'], g[f'{tag}_step_loss'].numpy(), rtol=1e-10)
+    assert np.allclose(out['pearsonr'], g[f'{tag}_pearsonr'].numpy(), rtol=1e-9)
+    assert np.allclose(out['average_distortion'], g[f'{tag}_average_distortion'].numpy(), rtol=1e-10)
+    for i, x in enumerate(out['xs']):
+        assert rel_err(x, g[f'{tag}_xT_{i}']) < 1e-10
+    assert out['best'][0] == int(g[f'{tag}_best'][0]) and abs(out['best'][1] - g[f'{tag}_best'][1].item()) < 1e-5
