@@ -302,10 +302,14 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_losses = []
     for k in range(args.steps):
-        trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1, next_batch=grouped(batches[(k + 1) % nb]))
+        host_losses.append(trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1,
+                                                     next_batch=grouped(batches[(k + 1) % nb]), defer_loss=True))
+    host_losses.append(trainer.flush_loss())  # every step's loss reaches the host, one step late
     e1.record()
     barrier()
+    assert all(v is not None and np.isfinite(v) for v in host_losses[1:]), host_losses
     ms_e2e = e0.elapsed_time(e1)
     h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
 
@@ -345,9 +349,10 @@ def main():
             'final_loss': final_loss,
         },
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
-                'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps,
+                'd2h_bytes_per_step': 16, 'ms_per_step': ms_e2e / args.steps,
                 'api': 'graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
-                       + ('int32 j, uint8 hops' if args.unpacked else 'int32 j | hops << 24') + '; per rank)'},
+                       + ('int32 j, uint8 hops' if args.unpacked else 'int32 j | hops << 24') + '; per rank); next batch '
+                       'uploaded on a second stream, loss read back through pinned memory one step late'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': 'spd_pair_stream_kernel<SpdAI<float,4>,K_FUSED>',

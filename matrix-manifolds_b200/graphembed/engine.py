@@ -146,13 +146,41 @@ class PairTrainer:
         loss = self.step(di[:P], dj[:P], dh[:P], epoch=epoch)
         return loss.item()
 
-    def step_host_grouped(self, sources, offsets, idx_j, hops, epoch=1, next_batch=None):
+    # ---- pipelined loss read-back --------------------------------------------------------------------------------
+    def _queue_loss_read(self):
+        """Async device->host copy of this step's [loss, d loss/d scale] accumulator into pinned memory; returns the
+        loss of the PREVIOUS queued step (None for the first).  The host then runs one step ahead of the GPU."""
+        if getattr(self, '_loss_host', None) is None:
+            self._loss_host = torch.empty(2, 2, dtype=torch.float64).pin_memory()
+            self._loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+            self._loss_slot, self._loss_pending = 0, False
+        prev = self.flush_loss()
+        s = self._loss_slot
+        self._loss_host[s].copy_(self.acc, non_blocking=True)
+        self._loss_events[s].record(torch.cuda.current_stream(self.x.device))
+        self._loss_pending = True
+        return prev
+
+    def flush_loss(self):
+        """Loss of the last step issued with defer_loss=True (waits for it), or None if nothing is pending."""
+        if not getattr(self, '_loss_pending', False):
+            return None
+        s = self._loss_slot
+        self._loss_events[s].synchronize()
+        self._loss_pending = False
+        self._loss_slot = 1 - s
+        return float(self._loss_host[s][0])
+
+    def step_host_grouped(self, sources, offsets, idx_j, hops, epoch=1, next_batch=None, defer_loss=False):
         """One step from PINNED host tensors in source-grouped (CSR-like) form, the natural output of a sampler that
         draws targets per BFS source: pairs offsets[g] <= k < offsets[g+1] are (sources[g], idx_j[k]) with hop count
         hops[k].  sources int32 (G,), offsets int64 (G+1,), idx_j int32 (P,), hops uint8/int16 (P,).  Uploads 5 bytes
         per pair instead of 9 -- or 4 with hops=None and idx_j = pack_hops(j, hops) -- and the first-endpoint index
         vector is expanded on the device (gm_expand_groups).
-        `next_batch` = the next step's (sources, offsets, idx_j, hops), uploaded on a second stream meanwhile."""
+        `next_batch` = the next step's (sources, offsets, idx_j, hops), uploaded on a second stream meanwhile.
+        defer_loss=True returns the loss of the previous deferred step instead of blocking on this one (its own loss
+        is copied to pinned host memory asynchronously; `flush_loss()` returns the last one), so that the host can
+        enqueue step k+1 while the GPU runs step k."""
         P, G = idx_j.numel(), sources.numel()
         packed = hops is None  # idx_j carries the hop counts (pack_hops): 4 bytes per pair over PCIe
         self._ensure_staging(P, torch.uint8 if packed else hops.dtype, G)
@@ -186,4 +214,6 @@ class PairTrainer:
         self._slot = 1 - slot
         _ops.expand_groups(ds[:G], do[:G + 1], di[:P])
         loss = self.step(di[:P], dj[:P], None if packed else dh[:P], epoch=epoch)
+        if defer_loss:  # read this step's loss back asynchronously, hand out the previous step's
+            return self._queue_loss_read()
         return loss.item()

@@ -276,3 +276,39 @@ def test_two_gpu_sharded_engine_matches_reference_engine():
     assert np.allclose(losses, g['spd3_batched_step_loss'].numpy(), rtol=1e-9)
     assert np.allclose(dist_metric, g['spd3_batched_average_distortion'].numpy(), rtol=1e-8)
     assert rel_err(torch.from_numpy(xT), g['spd3_batched_xT_0']) < 1e-9
+
+
+def test_deferred_loss_readback_matches_blocking_steps():
+    """defer_loss=True (loss copied to pinned memory asynchronously, returned one step late) gives the same loss
+    sequence and the same trajectory as the blocking step_host_grouped."""
+    from graphembed.engine import PairTrainer, pack_hops
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+    gen = torch.Generator().manual_seed(21)
+    n, G, per = 3000, 16, 128
+    batches = []
+    for _ in range(3):
+        src = torch.randperm(n, generator=gen)[:G].int().pin_memory()
+        J = torch.randint(n, (G * per,), generator=gen, dtype=torch.int32)
+        hops = torch.randint(1, 9, (G * per,), generator=gen, dtype=torch.uint8)
+        offs = (torch.arange(G + 1, dtype=torch.int64) * per).pin_memory()
+        batches.append((src, offs, pack_hops(J, hops).pin_memory(), None))
+    runs = []
+    for defer in (False, True):
+        torch.manual_seed(8)
+        emb = ManifoldEmbedding(n, [SymmetricPositiveDefinite(4)], device=DEV, dtype=torch.float32)
+        tr = PairTrainer(emb, RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True), QuotientLoss(),
+                         max_hops_sq=64.0)
+        losses = []
+        for k in range(5):
+            losses.append(tr.step_host_grouped(*batches[k % 3], epoch=1, next_batch=batches[(k + 1) % 3],
+                                               defer_loss=defer))
+        if defer:
+            assert losses[0] is None
+            losses = losses[1:] + [tr.flush_loss()]
+            assert tr.flush_loss() is None
+        runs.append((losses, emb.xs[0].detach().clone()))
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
+    assert rel_err(runs[1][1], runs[0][1]) < 1e-4
