@@ -7,7 +7,9 @@ workload : BASELINE config 5 -- synthetic 2M-node scale-free graph, SPD 4x4 affi
            multi-source BFS kernel, distortion loss (QuotientLoss, both terms), RiemannianAdam(lr .01, clip 100,
            exact) -- graphembed/experiments/run_grid.py:24-36,108-138 hyper-parameters.
 step     : zero grad -> ONE fused pair kernel (gather + distance + loss + gradient + scatter-add) over the batch
-           -> [N>1: NCCL all-reduce of the dense gradient] -> ONE fused optimizer kernel over all 2M points.
+           -> ONE fused optimizer kernel over all 2M points.  N>1: pairs sharded over ranks, and the optimizer
+           kernel is the peer-memory owner update (pull+sum the owned gradient rows of every rank over NVLink, update,
+           push the new rows to every rank) -- NCCL reduce-scatter / all-gather only if CUDA IPC is unavailable.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs-log2 24] [--nodes 2000000]
 
@@ -50,6 +52,8 @@ def parse():
     ap.add_argument('--batches', type=int, default=3, help='distinct pre-generated pair batches cycled through')
     ap.add_argument('--cpu-pairs-log2', type=int, default=17)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-peer', action='store_true', help='N>1: NCCL reduce-scatter / all-gather owner update instead '
+                    'of the fused peer-memory kernel (A/B)')
     ap.add_argument('--unpacked', action='store_true', help='separate uint8 hop-count vector instead of the packed '
                     '(j | hops << 24) pair format')
     return ap.parse_args()
@@ -130,7 +134,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE,
+                                          '-i', str(self.index), '-lms', '20'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -220,6 +224,8 @@ def main():
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     pg = None
+    if args.no_peer:
+        os.environ['GM_PEER_UPDATE'] = '0'
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
@@ -271,6 +277,21 @@ def main():
         return r
 
     _ops.pairs_loss_fused = timed_pairs
+    # N>1: also bracket the optimizer call (the fused peer-memory owner update, or the owner update between the NCCL
+    # reduce-scatter and all-gather); it includes the wait for the slowest rank's pair kernel
+    upd_events = []
+    opt_step = trainer.opt.step
+
+    def timed_update(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = opt_step(*a, **kw)
+        e1.record()
+        upd_events.append((e0, e1))
+        return r
+
+    if world > 1:
+        trainer.opt.step = timed_update
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -284,8 +305,9 @@ def main():
     t1.record()
     barrier()
     launches = _lib.launch_count() - launches0
-    clock_info = clocks.stop() if rank == 0 else None
     _ops.pairs_loss_fused = orig
+    trainer.opt.step = opt_step
+    upd_ms = float(np.mean([a.elapsed_time(b) for a, b in upd_events])) if upd_events else None
     ms = t0.elapsed_time(t1)
     pair_ms = float(np.mean([a.elapsed_time(b) for a, b in pair_events]))
     final_loss = float(loss.item())
@@ -311,6 +333,7 @@ def main():
     barrier()
     assert all(v is not None and np.isfinite(v) for v in host_losses[1:]), host_losses
     ms_e2e = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None  # sampled over both timed regions
     h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
 
     if pg is not None:
@@ -341,12 +364,16 @@ def main():
             'workload': 'BASELINE config 5: synthetic scale-free graph, SPD 4x4 affine-invariant, sampled pairs '
                         '(1024 BFS sources x targets) per step, QuotientLoss, RiemannianAdam(lr .01, clip 100, exact)',
             'nodes': N, 'pairs_per_step_per_gpu': P, 'parallelism': f'pair-sharded x{world}'
-            + (' + NCCL reduce-scatter of the (N,4,4) gradient, owner-rank optimizer update, all-gather of the points'
+            + (' + ONE fused kernel over NVLink peer memory: pull+sum the owned (N/G,4,4) gradient rows from every '
+               'rank, optimizer update, push the new rows to every rank (gm_optim_step_peer, no NCCL on the step path)'
+               if trainer.peer is not None else
+               ' + NCCL reduce-scatter of the (N,4,4) gradient, owner-rank optimizer update, all-gather of the points'
                if trainer.shards is not None else (' + NCCL all-reduce of the (N,4,4) gradient' if world > 1 else '')),
             'l2_policy': f'inputs larger than L2: {len(batches)} distinct batches of '
                          f'{P * (9 if args.unpacked else 8) / 1e6:.0f} MB cycled, '
                          f'{N * 64 / 1e6:.0f} MB embedding + {N * 64 / 1e6:.0f} MB gradient touched at random',
             'final_loss': final_loss,
+            **({'optimizer_call_ms_rank0': upd_ms} if upd_ms is not None else {}),
         },
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 16, 'ms_per_step': ms_e2e / args.steps,

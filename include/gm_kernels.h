@@ -198,6 +198,41 @@ typedef struct gm_optim {
 int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, const void* grad, void* buf1,
                   void* buf2, int64_t N, gm_stream_t stream);
 
+/* ---- multi-GPU: fused reduce-scatter + optimizer update + all-gather over NVLink peer memory ---------------------
+ * New capability (the reference's only multi-GPU mechanism is nn.DataParallel, train.py:107-109,203-204).  Pairs are
+ * sharded over ranks; every rank accumulates a full (N, ...) table of partial gradients.  Rank r owns rows
+ * [row_lo, row_lo + N_owned): gm_optim_step_peer sums those rows over ALL ranks' gradient tables through peer loads,
+ * applies the optimizer update of gm_optim_step to them (buf1/buf2 hold the owned rows only) and stores the new rows
+ * into EVERY rank's point table through peer stores -- one kernel instead of ncclReduceScatter + update +
+ * ncclAllGather.  The kernel carries its own cross-GPU barriers (flag words in the arenas): on entry it waits until
+ * every rank has launched it (=> all partial gradients are final), and it only completes once every rank has finished
+ * reading this rank's gradients and writing this rank's points.  All ranks must call it in lock step with the same
+ * `epoch`, which must increase by one from call to call starting at 1.
+ * The tables must live in memory obtained from gm_peer_alloc and mapped into the peers with gm_peer_export /
+ * gm_peer_open (CUDA IPC, one process per GPU on one NVLink domain).  Each rank's flag block is
+ * GM_PEER_FLAG_BYTES of zero-initialised arena memory. */
+#define GM_MAX_PEERS 8
+#define GM_PEER_FLAG_BYTES ((2 * GM_MAX_PEERS + 1) * 8)
+#define GM_PEER_HANDLE_BYTES 64
+typedef struct gm_peers {
+  int32_t world, rank;
+  int64_t row_lo;
+  uint64_t epoch;
+  void* x[GM_MAX_PEERS];          /* rank r's full point table (as mapped in THIS process)                  */
+  const void* grad[GM_MAX_PEERS]; /* rank r's full partial-gradient table                                   */
+  void* flags[GM_MAX_PEERS];      /* rank r's flag block                                                    */
+  const void* acc[GM_MAX_PEERS];  /* rank r's double[n_acc] step accumulator (loss, scale grads) or NULL    */
+  void* acc_out;                  /* local double[n_acc]: sum over ranks of acc                             */
+  int32_t n_acc, reserved;
+} gm_peers_t;
+int gm_peer_alloc(size_t bytes, void** ptr);            /* zero-filled device memory on the current device  */
+int gm_peer_free(void* ptr);
+int gm_peer_export(const void* ptr, void* handle);      /* writes GM_PEER_HANDLE_BYTES                      */
+int gm_peer_open(const void* handle, void** ptr);       /* maps a peer's arena; enables peer access         */
+int gm_peer_close(void* ptr);
+int gm_optim_step_peer(const gm_manifold_t* man, const gm_optim_t* opt, const gm_peers_t* peers, void* buf1,
+                       void* buf2, int64_t N_owned, gm_stream_t stream);
+
 /* ---- per-point manifold operations (Manifold API, manifolds/base.py:7-81) ----------------------------------- */
 enum gm_point_op {
   GM_OP_EXP = 0,         /* out = exp_x(u)                      */

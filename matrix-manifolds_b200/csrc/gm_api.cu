@@ -1,6 +1,7 @@
 // C-ABI entry points of libgm_b200.so (declared in include/gm_kernels.h):
 // argument validation and dispatch to the templated kernel launchers.
 #include <atomic>
+#include <cstring>
 #include <cuda_runtime.h>
 #include "gm_point_kernels.cuh"
 
@@ -275,6 +276,67 @@ int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, cons
   if (opt->kind == GM_OPT_RSGD && !opt->has_momentum) a.buf1 = nullptr;
   a.N = N;
   a.stream = (cudaStream_t)stream;
+  return point_dispatch(a);
+}
+
+int gm_peer_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return GM_ENULL;
+  if (bytes == 0) return GM_EINVAL;
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemset(*ptr, 0, bytes);
+}
+int gm_peer_free(void* ptr) { return ptr ? (int)cudaFree(ptr) : GM_OK; }
+int gm_peer_export(const void* ptr, void* handle) {
+  if (!ptr || !handle) return GM_ENULL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == GM_PEER_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr));
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle, &h, sizeof(h));
+  return GM_OK;
+}
+int gm_peer_open(const void* handle, void** ptr) {
+  if (!handle || !ptr) return GM_ENULL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int gm_peer_close(void* ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : GM_OK; }
+
+int gm_optim_step_peer(const gm_manifold_t* man, const gm_optim_t* opt, const gm_peers_t* peers, void* buf1,
+                       void* buf2, int64_t N_owned, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  if (!opt || !peers) return GM_ENULL;
+  if (N_owned <= 0 || peers->row_lo < 0 || peers->epoch == 0) return GM_EINVAL;  // every rank must launch: no empty shards
+  if (peers->world < 1 || peers->world > GM_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return GM_EINVAL;
+  if (peers->n_acc < 0 || peers->n_acc > 64) return GM_EINVAL;
+  if (opt->kind != GM_OPT_RSGD && opt->kind != GM_OPT_RADAM) return GM_EINVAL;
+  if (opt->kind == GM_OPT_RADAM && (!buf1 || !buf2 || opt->step < 1)) return GM_EINVAL;
+  if (opt->kind == GM_OPT_RSGD && opt->has_momentum && !buf1) return GM_ENULL;
+  PeerTable pt{};
+  pt.world = peers->world; pt.rank = peers->rank; pt.row_lo = peers->row_lo; pt.epoch = peers->epoch;
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->x[r] || !peers->grad[r] || !peers->flags[r]) return GM_ENULL;
+    if (peers->n_acc > 0 && !peers->acc[r]) return GM_ENULL;
+    pt.x[r] = peers->x[r]; pt.g[r] = peers->grad[r];
+    pt.flags[r] = (unsigned long long*)peers->flags[r];
+    pt.acc[r] = (const double*)peers->acc[r];
+  }
+  if (peers->n_acc > 0 && !peers->acc_out) return GM_ENULL;
+  pt.acc_out = (double*)peers->acc_out; pt.n_acc = peers->n_acc;
+  PointArgs a{};
+  a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
+  a.wmin = man->wmin; a.wmax = man->wmax;
+  a.op = -1;
+  a.oc = make_optim_cfg(opt);
+  a.grassmann_retr_qr = opt->grassmann_retr_qr;
+  a.buf1 = buf1; a.buf2 = (opt->kind == GM_OPT_RADAM) ? buf2 : nullptr;
+  if (opt->kind == GM_OPT_RSGD && !opt->has_momentum) a.buf1 = nullptr;
+  a.N = N_owned;
+  a.stream = (cudaStream_t)stream;
+  a.peer = &pt;
   return point_dispatch(a);
 }
 

@@ -6,6 +6,25 @@
 
 namespace gm {
 
+// Peer-memory owner update (multi-GPU): every rank holds a full point table and a full table of its own partial
+// gradients in memory that every other rank of the NVLink domain has mapped (cudaIpc).  Rank `rank` owns rows
+// [row_lo, row_lo + N): it sums those rows over all ranks' gradient tables (the reduce-scatter), applies the optimizer
+// update, and stores the new rows into every rank's point table (the all-gather) -- one kernel, no staging copies.
+// flags[r] is rank r's flag block: [0, MAXP) "ready" words, [MAXP, 2 MAXP) "done" words, each written by the rank
+// of that index, and [2 MAXP] a block counter private to rank r.
+constexpr int kMaxPeers = GM_MAX_PEERS;
+struct PeerTable {
+  int world, rank;
+  long long row_lo;
+  unsigned long long epoch;  // strictly increasing over calls, identical on every rank
+  void* x[kMaxPeers];
+  const void* g[kMaxPeers];
+  unsigned long long* flags[kMaxPeers];
+  const double* acc[kMaxPeers];  // every rank's [loss, scale-grad, ...] accumulator (may be null)
+  double* acc_out;               // local: sum over ranks of acc[r][0..n_acc)
+  int n_acc;
+};
+
 struct PointArgs {
   int kind, dtype, n, p;
   unsigned flags;
@@ -21,6 +40,7 @@ struct PointArgs {
   void* buf2;
   long long N;
   cudaStream_t stream;
+  const PeerTable* peer;  // non-null: peer-memory owner update (x / u ignored, taken from the table)
 };
 
 template <class Man, typename T>
@@ -58,6 +78,198 @@ optim_kernel(Man man, OptimCfg oc, T* __restrict__ x, const T* __restrict__ grad
       x[base + e] = xs[e];
       if (buf1) buf1[base + e] = b1[e];
       if (buf2) buf2[base + e] = b2[e];
+    }
+  }
+}
+
+// ---- cross-GPU flag words (system scope) ------------------------------------------------------------------------------
+__device__ __forceinline__ void flag_store_release(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long flag_load_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Spin until *p >= epoch.  A peer that never arrives (crashed rank) must not hang the GPU: trap after ~10 s.
+__device__ __forceinline__ void flag_wait(const unsigned long long* p, unsigned long long epoch) {
+  unsigned long long t0 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+  unsigned spins = 0;
+  while (flag_load_acquire(p) < epoch) {
+    if ((++spins & 0x3ff) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) __trap();
+    }
+    __nanosleep(64);
+  }
+}
+
+// Fused reduce-scatter + optimizer update + all-gather over peer memory (see PeerTable).
+//   entry : block 0 tells every peer "my partial gradients are final" (ready[rank] = epoch); every block waits for
+//           the ready word of every rank before it touches a gradient table
+//   body  : a block owns a tile of 128 consecutive rows.  (1) all threads pull the tile from every rank's gradient
+//           table with warp-contiguous 16-byte loads (512 B per warp instruction -- NVLink packets stay full; a
+//           thread-per-row gather would issue 32-byte requests), sum it in rank order and park it in shared memory;
+//           (2) thread k updates row k (x, buf1, buf2) and writes the new row back into the tile; (3) all threads
+//           push the tile into every rank's point table with the same warp-contiguous stores.
+//   exit  : the last block to finish tells every peer "I have read your gradients and written your points"
+//           (done[rank] = epoch) and waits for the same from everyone, so that when this kernel completes the local
+//           point table is fully updated and the local gradient table may be zeroed again.
+// Tiles that do not fit the shared-memory budget (row > kPeerTileRowBytes) take the per-thread path.
+constexpr int kPeerTileRowBytes = 256;
+constexpr int kPeerTileBytes = 128 * kPeerTileRowBytes;
+
+template <typename T, typename V>
+__device__ __forceinline__ V vec_add(V a, V b) {
+  constexpr int n = sizeof(V) / sizeof(T);
+  T* pa = reinterpret_cast<T*>(&a);
+  const T* pb = reinterpret_cast<const T*>(&b);
+  GM_UNROLL for (int j = 0; j < n; ++j) pa[j] += pb[j];
+  return a;
+}
+
+// tile <- sum over ranks of g[r][off .. off + nvec) in units of V; U vectors in flight per thread and rank
+template <typename T, typename V>
+__device__ __forceinline__ void peer_pull_sum(const PeerTable& pt, size_t byte_off, int nvec, V* tile, int tid) {
+  constexpr int U = 4;
+  for (int c0 = tid; c0 < nvec; c0 += 128 * U) {
+    V acc[U];
+    GM_UNROLL for (int u = 0; u < U; ++u) {
+      int c = c0 + u * 128;
+      acc[u] = (c < nvec) ? reinterpret_cast<const V*>((const char*)pt.g[0] + byte_off)[c] : V{};
+    }
+    for (int r = 1; r < pt.world; ++r) {
+      const V* src = reinterpret_cast<const V*>((const char*)pt.g[r] + byte_off);
+      V v[U];
+      GM_UNROLL for (int u = 0; u < U; ++u) {
+        int c = c0 + u * 128;
+        v[u] = (c < nvec) ? src[c] : V{};
+      }
+      GM_UNROLL for (int u = 0; u < U; ++u) acc[u] = vec_add<T, V>(acc[u], v[u]);
+    }
+    GM_UNROLL for (int u = 0; u < U; ++u) {
+      int c = c0 + u * 128;
+      if (c < nvec) tile[c] = acc[u];
+    }
+  }
+}
+
+template <typename V>
+__device__ __forceinline__ void peer_push(const PeerTable& pt, size_t byte_off, int nvec, const V* tile, int tid) {
+  for (int c = tid; c < nvec; c += 128) {
+    V v = tile[c];
+    for (int r = 0; r < pt.world; ++r) reinterpret_cast<V*>((char*)pt.x[r] + byte_off)[c] = v;
+  }
+}
+
+template <class Man, typename T>
+__global__ void __launch_bounds__(128)
+peer_optim_kernel(Man man, OptimCfg oc, PeerTable pt, T* __restrict__ buf1, T* __restrict__ buf2, long long N,
+                  int use_tile) {
+  constexpr int CAP = Man::CAP;
+  extern __shared__ __align__(16) char tile_mem[];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  unsigned long long* my_flags = pt.flags[pt.rank];
+  if (blockIdx.x == 0 && tid < pt.world) flag_store_release(pt.flags[tid] + pt.rank, pt.epoch);
+  if (tid < pt.world) flag_wait(my_flags + tid, pt.epoch);
+  __syncthreads();
+
+  const int cnt = man.count();
+  const long long row0 = (long long)blockIdx.x * 128;
+  const long long k = row0 + tid;
+  const int rows_here = (int)((N - row0 < 128) ? (N - row0) : 128);
+  const size_t tile_off = (size_t)(pt.row_lo + row0) * cnt * sizeof(T);  // byte offset of the tile in every table
+  const int tile_bytes = rows_here * cnt * (int)sizeof(T);
+  const bool vec16 = use_tile && (tile_off % 16 == 0) && (tile_bytes % 16 == 0);
+  T* tile = reinterpret_cast<T*>(tile_mem);
+  if (use_tile) {
+    if (vec16) peer_pull_sum<T, float4>(pt, tile_off, tile_bytes / 16, reinterpret_cast<float4*>(tile_mem), tid);
+    else peer_pull_sum<T, T>(pt, tile_off, tile_bytes / (int)sizeof(T), tile, tid);
+    __syncthreads();
+  }
+  if (k < N) {
+    const long long row = pt.row_lo + k;
+    const long long base = row * cnt, lbase = k * cnt;
+    T xs[CAP], gs[CAP], b1[CAP], b2[CAP];
+    if constexpr (Man::kStatic) {
+      if (use_tile) {
+        GM_UNROLL for (int e = 0; e < CAP; ++e) gs[e] = tile[tid * CAP + e];
+      } else {
+        load_row<T, CAP>((const T*)pt.g[0], row, gs);
+        for (int r = 1; r < pt.world; ++r) {
+          T gr[CAP];
+          load_row<T, CAP>((const T*)pt.g[r], row, gr);
+          GM_UNROLL for (int e = 0; e < CAP; ++e) gs[e] += gr[e];
+        }
+      }
+      load_row<T, CAP>((const T*)pt.x[pt.rank], row, xs);
+      if (buf1) load_row<T, CAP>(buf1, k, b1);
+      if (buf2) load_row<T, CAP>(buf2, k, b2);
+      if (!buf1) { GM_UNROLL for (int e = 0; e < CAP; ++e) b1[e] = (T)0; }
+      if (!buf2) { GM_UNROLL for (int e = 0; e < CAP; ++e) b2[e] = (T)0; }
+    } else {
+      const T* xl = (const T*)pt.x[pt.rank];
+      for (int e = 0; e < cnt; ++e) {
+        T sum;
+        if (use_tile) {
+          sum = tile[tid * cnt + e];
+        } else {
+          sum = ((const T*)pt.g[0])[base + e];
+          for (int r = 1; r < pt.world; ++r) sum += ((const T*)pt.g[r])[base + e];
+        }
+        gs[e] = sum;
+        xs[e] = xl[base + e];
+        b1[e] = buf1 ? buf1[lbase + e] : (T)0;
+        b2[e] = buf2 ? buf2[lbase + e] : (T)0;
+      }
+    }
+    optim_update<Man, T>(man, oc, xs, gs, b1, b2);
+    if constexpr (Man::kStatic) {
+      if (use_tile) {
+        GM_UNROLL for (int e = 0; e < CAP; ++e) tile[tid * CAP + e] = xs[e];
+      } else {
+        for (int r = 0; r < pt.world; ++r) store_row<T, CAP>((T*)pt.x[r], row, xs);
+      }
+      if (buf1) store_row<T, CAP>(buf1, k, b1);
+      if (buf2) store_row<T, CAP>(buf2, k, b2);
+    } else {
+      for (int e = 0; e < cnt; ++e) {
+        if (use_tile) {
+          tile[tid * cnt + e] = xs[e];
+        } else {
+          for (int r = 0; r < pt.world; ++r) ((T*)pt.x[r])[base + e] = xs[e];
+        }
+        if (buf1) buf1[lbase + e] = b1[e];
+        if (buf2) buf2[lbase + e] = b2[e];
+      }
+    }
+  }
+  if (use_tile) {
+    __syncthreads();
+    if (vec16) peer_push<float4>(pt, tile_off, tile_bytes / 16, reinterpret_cast<const float4*>(tile_mem), tid);
+    else peer_push<T>(pt, tile_off, tile_bytes / (int)sizeof(T), tile, tid);
+  }
+  // per-step scalars (loss, scale gradients): every rank's accumulator is final once its ready word is seen
+  if (blockIdx.x == 0 && tid >= 32 && tid < 32 + pt.n_acc) {
+    double s = 0.0;
+    for (int r = 0; r < pt.world; ++r) s += pt.acc[r][tid - 32];
+    pt.acc_out[tid - 32] = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long prev = atomicAdd(my_flags + 2 * kMaxPeers, 1ull);
+    is_last = (prev == (unsigned long long)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (tid == 0) my_flags[2 * kMaxPeers] = 0;
+    if (tid < pt.world) {
+      flag_store_release(pt.flags[tid] + kMaxPeers + pt.rank, pt.epoch);
+      flag_wait(my_flags + kMaxPeers + tid, pt.epoch);
     }
   }
 }
@@ -116,7 +328,12 @@ static int launch_point(const Man& man, const PointArgs& a) {
   const int threads = 128;
   long long blocks = (a.N + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return GM_EINVAL;
-  if (a.op < 0)
+  if (a.op < 0 && a.peer) {
+    const size_t tile_bytes = (size_t)threads * man.count() * sizeof(T);
+    const int use_tile = tile_bytes <= (size_t)kPeerTileBytes;
+    peer_optim_kernel<Man, T><<<(unsigned)blocks, threads, use_tile ? tile_bytes : 0, a.stream>>>(
+        man, a.oc, *a.peer, (T*)a.buf1, (T*)a.buf2, a.N, use_tile);
+  } else if (a.op < 0)
     optim_kernel<Man, T><<<(unsigned)blocks, threads, 0, a.stream>>>(man, a.oc, (T*)a.x, (const T*)a.u, (T*)a.buf1,
                                                                      (T*)a.buf2, a.N);
   else

@@ -58,6 +58,18 @@ class Optim(ctypes.Structure):
                 ('dampening', ctypes.c_double), ('max_grad_norm', ctypes.c_double), ('eps', ctypes.c_double)]
 
 
+GM_MAX_PEERS, GM_PEER_HANDLE_BYTES = 8, 64
+GM_PEER_FLAG_BYTES = (2 * GM_MAX_PEERS + 1) * 8
+
+
+class Peers(ctypes.Structure):
+    _fields_ = [('world', ctypes.c_int32), ('rank', ctypes.c_int32), ('row_lo', ctypes.c_int64),
+                ('epoch', ctypes.c_uint64), ('x', ctypes.c_void_p * GM_MAX_PEERS),
+                ('grad', ctypes.c_void_p * GM_MAX_PEERS), ('flags', ctypes.c_void_p * GM_MAX_PEERS),
+                ('acc', ctypes.c_void_p * GM_MAX_PEERS), ('acc_out', ctypes.c_void_p), ('n_acc', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
+
+
 _vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 _PROTOTYPES = {
     'gm_version': (ctypes.c_char_p, []),
@@ -77,6 +89,13 @@ _PROTOTYPES = {
     'gm_sne_pair_terms': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl), _vp, _i64, _dbl, _i32,
                                          _vp, _vp, _vp, _vp]),
     'gm_optim_step': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(Optim), _vp, _vp, _vp, _vp, _i64, _vp]),
+    'gm_optim_step_peer': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(Optim), ctypes.POINTER(Peers), _vp,
+                                          _vp, _i64, _vp]),
+    'gm_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    'gm_peer_free': (ctypes.c_int, [_vp]),
+    'gm_peer_export': (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    'gm_peer_open': (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    'gm_peer_close': (ctypes.c_int, [_vp]),
     'gm_point_op': (ctypes.c_int, [ctypes.POINTER(Manifold), _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     'gm_bfs_workspace_bytes': (ctypes.c_size_t, [_i32, _i32]),
     'gm_bfs_multi_source': (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, ctypes.c_size_t, _vp]),

@@ -289,6 +289,18 @@ def optim_step(spec, cfg, x, grad, buf1=None, buf2=None):
     L.check(rc, 'gm_optim_step')
 
 
+def optim_step_peer(spec, cfg, arena, own_rows, buf1=None, buf2=None):
+    """Fused reduce-scatter + optimizer update + all-gather over NVLink peer memory (gm_optim_step_peer): updates the
+    rows of arena.x this rank owns from the sum of every rank's arena.grad and publishes them to every rank."""
+    L.require_cuda(arena.x, buf1, buf2)
+    m = spec.c_struct(arena.x.dtype)
+    table = arena.next_table()
+    with torch.cuda.device(arena.x.device):
+        rc = L.lib().gm_optim_step_peer(ctypes.byref(m), ctypes.byref(cfg), ctypes.byref(table), L.ptr(buf1),
+                                        L.ptr(buf2), own_rows, L.stream_ptr(arena.x.device))
+    L.check(rc, 'gm_optim_step_peer')
+
+
 # ----------------------------------------------------------------------------
 # autograd Functions
 # ----------------------------------------------------------------------------

@@ -16,7 +16,7 @@ from torch.nn.functional import softplus
 
 from . import _ops
 from .modules import ManifoldParameter
-from .parallel import RowShards, allreduce_step_buffers
+from .parallel import RowShards, allreduce_step_buffers, try_peer_arena
 
 
 def pack_hops(idx_j, hops):
@@ -42,6 +42,10 @@ class PairTrainer:
     owner_update : with a process group, reduce-scatter the gradient and let every rank update (and keep optimizer
         state for) only the rows it owns, then all-gather the new points; otherwise all-reduce and update replicas.
         Both give the same trajectory up to summation order.  Default: owner update whenever the rows split evenly.
+        On GPUs of one NVLink domain the owner update is a single kernel over peer memory (gm_optim_step_peer: pull
+        and sum the owned gradient rows from every rank, update, push the new rows to every rank) instead of
+        ncclReduceScatter + update + ncclAllGather; it is chosen automatically when CUDA IPC between the ranks works
+        (`self.peer` is then the PeerArena; GM_PEER_UPDATE=0 forces the NCCL collectives).
     """
 
     def __init__(self, embedding, optimizer, objective, max_hops_sq, alpha=1.0, process_group=None, owner_update=None):
@@ -58,15 +62,29 @@ class PairTrainer:
         self._staging = None
         self._copy_stream = None
         self.shards = None
+        self.peer = None
         if process_group is not None and torch.distributed.get_world_size(process_group) > 1:
             even = self.x.shape[0] % torch.distributed.get_world_size(process_group) == 0
             if owner_update is None:
                 owner_update = even
             if owner_update:
-                self.shards = RowShards(self.x.shape[0], process_group)
+                self.peer = try_peer_arena(self.x.data, 2, process_group)
+                if self.peer is not None:
+                    # points, gradient and step accumulator move into the IPC-mapped arena
+                    self.x.data = self.peer.x
+                    self.grad = self.peer.grad
+                    self.x.grad = self.grad
+                    self.acc = self.peer.acc
+                    self.shards = self.peer  # same own()/lo/hi/rows interface as RowShards
+                else:
+                    self.shards = RowShards(self.x.shape[0], process_group)
                 # the optimizer now drives a parameter that aliases the owned rows of x
                 own = ManifoldParameter(self.shards.own(self.x.data), manifold=self.man)
-                own.grad = torch.zeros_like(own.data)
+                if self.peer is not None:
+                    own.grad = self.peer.own(self.grad)  # placeholder: the kernel sums every rank's rows itself
+                    own._gm_peer_arena = self.peer
+                else:
+                    own.grad = torch.zeros_like(own.data)
                 self._own = own
                 replaced = False
                 for g in optimizer.param_groups:
@@ -91,6 +109,9 @@ class PairTrainer:
         self.grad.zero_()
         self.acc.zero_()
         _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, self._sp, self.grad, self.acc)
+        if self.peer is not None:
+            self.opt.step()  # ONE kernel: cross-GPU barrier, pull+sum gradients, update, push points, sum the loss
+            return self.peer.acc_out[0]
         if self.shards is None:
             allreduce_step_buffers(self.grad, self.acc, self.pg)
             self.opt.step()
@@ -156,7 +177,7 @@ class PairTrainer:
             self._loss_slot, self._loss_pending = 0, False
         prev = self.flush_loss()
         s = self._loss_slot
-        self._loss_host[s].copy_(self.acc, non_blocking=True)
+        self._loss_host[s].copy_(self.acc if self.peer is None else self.peer.acc_out, non_blocking=True)
         self._loss_events[s].record(torch.cuda.current_stream(self.x.device))
         self._loss_pending = True
         return prev

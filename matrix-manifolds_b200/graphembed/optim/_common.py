@@ -21,4 +21,9 @@ def fused_step(param, grad, cfg, buf1=None, buf2=None):
     spec, manifold = spec_of(param)
     cfg.grassmann_retr_qr = int(getattr(manifold, 'retr_kind', 'svd') == 'qr')
     with torch.no_grad():
-        _ops.optim_step(spec, cfg, param.data, grad, buf1, buf2)
+        arena = getattr(param, '_gm_peer_arena', None)
+        if arena is not None:  # multi-GPU owner update over NVLink peer memory (graphembed.parallel.PeerArena):
+            # `param` aliases the owned rows of arena.x; the gradient is the sum of every rank's arena.grad rows
+            _ops.optim_step_peer(spec, cfg, arena, param.shape[0], buf1, buf2)
+        else:
+            _ops.optim_step(spec, cfg, param.data, grad, buf1, buf2)

@@ -9,8 +9,13 @@ gloo in the CPU tests).  Two ways to combine the per-rank dense node gradients:
 
 The reference's only multi-GPU mechanism is nn.DataParallel over node chunks (train.py:107-109,203-204), which
 silently drops pairs that straddle two chunks; sharding the *pair list* keeps every pair."""
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
 
 
 def shard_range(n_items, rank, world):
@@ -60,3 +65,132 @@ class RowShards:
         """Publish this rank's rows of `full` to every rank (in place: the send buffer is the owned slice)."""
         dist.all_gather_into_tensor(full, self.own(full), group=self.group)
         return full
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# NVLink peer memory: the owner update as ONE kernel (gm_optim_step_peer) instead of three collectives
+# ---------------------------------------------------------------------------------------------------------------------
+class _RawCuda:
+    """A device allocation that is not torch's, exposed through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, address, nbytes):
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (address, False), 'version': 2}
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class PeerArena:
+    """Per-rank device arena [points | partial gradients | step accumulator | accumulator sum | flag block] that every
+    other rank of the process group maps through CUDA IPC, plus the table of mapped peer arenas that
+    gm_optim_step_peer (include/gm_kernels.h) walks: the owner of a row block pulls the partial gradient rows from all
+    ranks over NVLink, applies the optimizer update and pushes the new rows into every rank's point table.
+
+    x : the (N, ...) CUDA tensor holding the points (its values are copied into the arena); N must divide evenly.
+    """
+
+    def __init__(self, x, n_acc, group):
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > L.GM_MAX_PEERS:
+            raise RuntimeError(f'peer update supports up to {L.GM_MAX_PEERS} ranks (one NVLink domain)')
+        if x.shape[0] % self.world != 0:
+            raise RuntimeError(f'{x.shape[0]} rows do not split evenly over {self.world} ranks')
+        self.rows = x.shape[0] // self.world
+        self.lo, self.hi = self.rank * self.rows, (self.rank + 1) * self.rows
+        self.n_acc = n_acc
+        dev = x.device
+        xb = _align(x.numel() * x.element_size())
+        ab = _align(8 * n_acc)
+        self.off_x, self.off_g, self.off_acc, self.off_out, self.off_flags = 0, xb, 2 * xb, 2 * xb + ab, 2 * xb + 2 * ab
+        self.nbytes = self.off_flags + _align(L.GM_PEER_FLAG_BYTES)
+        lib = L.lib()
+        base = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            L.check(lib.gm_peer_alloc(self.nbytes, ctypes.byref(base)), 'gm_peer_alloc')
+            self.base = base.value
+            handle = ctypes.create_string_buffer(L.GM_PEER_HANDLE_BYTES)
+            L.check(lib.gm_peer_export(ctypes.c_void_p(self.base), handle), 'gm_peer_export')
+        raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=dev)
+        self._raw = raw
+        nb = x.numel() * x.element_size()
+        self.x = raw[self.off_x:self.off_x + nb].view(x.dtype).view(x.shape)
+        self.grad = raw[self.off_g:self.off_g + nb].view(x.dtype).view(x.shape)
+        self.acc = raw[self.off_acc:self.off_acc + 8 * n_acc].view(torch.float64)
+        self.acc_out = raw[self.off_out:self.off_out + 8 * n_acc].view(torch.float64)
+        self.x.copy_(x)
+        # exchange the IPC handles and map every peer's arena
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (os.getpid(), handle.raw), group=group)
+        self.peer_base = []
+        self._opened = []
+        with torch.cuda.device(dev):
+            for r, (pid, h) in enumerate(handles):
+                if r == self.rank:
+                    self.peer_base.append(self.base)
+                    continue
+                p = ctypes.c_void_p()
+                hbuf = ctypes.create_string_buffer(L.GM_PEER_HANDLE_BYTES)
+                hbuf.raw = h
+                L.check(lib.gm_peer_open(hbuf, ctypes.byref(p)), f'gm_peer_open(rank {r})')
+                self.peer_base.append(p.value)
+                self._opened.append(p.value)
+        self.table = L.Peers()
+        self.table.world, self.table.rank, self.table.row_lo = self.world, self.rank, self.lo
+        self.table.n_acc = n_acc
+        self.table.acc_out = self.base + self.off_out
+        for r, b in enumerate(self.peer_base):
+            self.table.x[r] = b + self.off_x
+            self.table.grad[r] = b + self.off_g
+            self.table.flags[r] = b + self.off_flags
+            self.table.acc[r] = b + self.off_acc
+        self.epoch = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # every arena is zero-filled and mapped before anyone raises a flag
+
+    def own(self, t):
+        return t[self.lo:self.hi]
+
+    def next_table(self):
+        """The peer table for the next lock-step call (epoch advanced by one)."""
+        self.epoch += 1
+        self.table.epoch = self.epoch
+        return self.table
+
+    def close(self):
+        lib = L.lib()
+        for p in self._opened:
+            lib.gm_peer_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self.base:
+            lib.gm_peer_free(ctypes.c_void_p(self.base))
+            self.base = None
+
+
+def try_peer_arena(x, n_acc, group):
+    """PeerArena if EVERY rank of `group` could allocate, export and map the arenas (NCCL backend, CUDA IPC between
+    the processes, at most GM_MAX_PEERS ranks); otherwise None on every rank, and the caller keeps the NCCL
+    reduce-scatter / all-gather owner update.  GM_PEER_UPDATE=0 disables the attempt."""
+    if group is None or not x.is_cuda or dist.get_backend(group) != 'nccl':
+        return None
+    world = dist.get_world_size(group)
+    if world < 2 or os.environ.get('GM_PEER_UPDATE', '1') == '0':
+        return None
+    arena, err = None, None
+    ok = world <= L.GM_MAX_PEERS and x.shape[0] % world == 0
+    if ok:
+        try:
+            arena = PeerArena(x, n_acc, group)
+        except Exception as e:  # noqa: BLE001 -- any failure on any rank => all ranks fall back together
+            err, ok = e, False
+    flag = torch.tensor([1 if ok else 0], device=x.device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
+        return arena
+    if arena is not None:
+        arena.close()
+    if err is not None and dist.get_rank(group) == 0:
+        import logging
+        logging.getLogger(__name__).warning('peer-memory owner update unavailable (%s); using NCCL collectives', err)
+    return None

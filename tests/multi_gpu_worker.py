@@ -1,0 +1,98 @@
+"""Worker of tests/test_gpu_multi.py -- run as `torchrun --nproc-per-node G tests/multi_gpu_worker.py`.
+
+Every rank trains the same embedding on its own shard of a pair batch for a few steps, three ways:
+  peer   : owner update as ONE kernel over NVLink peer memory (gm_optim_step_peer)
+  nccl   : ncclReduceScatter + owner update + ncclAllGather (GM_PEER_UPDATE=0)
+  single : all shards concatenated on one GPU, no process group (rank 0 only)
+and checks that the three trajectories agree (summation order differs: 1e-5 fp32 / 1e-10 fp64 relative).
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'matrix-manifolds_b200'))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def make(kind, dtype, n_nodes, dev):
+    from graphembed.manifolds import Lorentz, SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    torch.manual_seed(7)
+    man = SymmetricPositiveDefinite(4) if kind == 'spd4' else Lorentz(6)
+    return ManifoldEmbedding(n_nodes, [man], device=dev, dtype=dtype)
+
+
+def shard_pairs(n_nodes, P, r):
+    g = torch.Generator().manual_seed(100 + r)
+    I = torch.randint(n_nodes, (P,), generator=g, dtype=torch.int32)
+    J = (I + 1 + torch.randint(n_nodes - 1, (P,), generator=g, dtype=torch.int32)) % n_nodes
+    hops = torch.randint(1, 9, (P,), generator=g, dtype=torch.uint8)
+    return I, J, hops
+
+
+def run(kind, dtype, opt_name, n_nodes, P, steps, dev, pg, ranks):
+    from graphembed.engine import PairTrainer
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam, RiemannianSGD
+    emb = make(kind, dtype, n_nodes, dev)
+    if opt_name == 'radam':
+        opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
+    else:
+        opt = RiemannianSGD(emb.xs, lr=0.001, momentum=0.9, max_grad_norm=100)
+    tr = PairTrainer(emb, opt, QuotientLoss(), max_hops_sq=64.0, process_group=pg)
+    parts = [shard_pairs(n_nodes, P, r) for r in ranks]
+    I, J, H = (torch.cat([p[k] for p in parts]).to(dev) for k in range(3))
+    losses = []
+    for s in range(steps):
+        losses.append(float(tr.step(I, J, H, epoch=s + 1).item()))
+    return emb.xs[0].detach().clone(), losses, tr
+
+
+def main():
+    world, rank, local = int(os.environ['WORLD_SIZE']), int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group('nccl', device_id=dev)
+    pg = dist.group.WORLD
+    n_nodes, P, steps = 4096 * world, 20000, 3
+    bad = 0
+    for kind, dtype, opt_name in (('spd4', torch.float32, 'radam'), ('spd4', torch.float64, 'radam'),
+                                  ('lorentz', torch.float64, 'rsgd')):
+        tol = 2e-5 if dtype == torch.float32 else 1e-10
+        os.environ['GM_PEER_UPDATE'] = '1'
+        x_peer, l_peer, tr = run(kind, dtype, opt_name, n_nodes, P, steps, dev, pg, [rank])
+        used_peer = tr.peer is not None
+        os.environ['GM_PEER_UPDATE'] = '0'
+        x_nccl, l_nccl, tr2 = run(kind, dtype, opt_name, n_nodes, P, steps, dev, pg, [rank])
+        assert tr2.peer is None and tr2.shards is not None
+        # every rank must hold the same replica after the all-gather / peer push
+        ref = x_peer.clone()
+        dist.broadcast(ref, src=0)
+        same = bool(torch.equal(ref, x_peer))
+        scale = x_nccl.abs().max()
+        d_pn = float(((x_peer - x_nccl).abs().max() / scale).item())
+        d_l = max(abs(a - b) / abs(b) for a, b in zip(l_peer, l_nccl))
+        msg = f'[rank {rank}] {kind} {dtype} {opt_name}: peer={used_peer} replicas_identical={same} ' \
+              f'peer-vs-nccl x {d_pn:.2e} loss {d_l:.2e}'
+        ok = used_peer and same and d_pn < tol and d_l < tol
+        if rank == 0:
+            x_one, l_one, _ = run(kind, dtype, opt_name, n_nodes, P, steps, dev, None, list(range(world)))
+            d_p1 = float(((x_peer - x_one).abs().max() / scale).item())
+            d_l1 = max(abs(a - b) / abs(b) for a, b in zip(l_peer, l_one))
+            msg += f' | peer-vs-single x {d_p1:.2e} loss {d_l1:.2e}'
+            ok = ok and d_p1 < tol and d_l1 < tol
+        print(msg + (' OK' if ok else ' FAIL'), flush=True)
+        bad += 0 if ok else 1
+        dist.barrier()
+    t = torch.tensor([bad], device=dev)
+    dist.all_reduce(t)
+    if rank == 0:
+        print('MULTI_GPU_PARITY ' + ('PASS' if int(t.item()) == 0 else 'FAIL'), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 0 else 1)
+
+
+if __name__ == '__main__':
+    main()

@@ -50,6 +50,30 @@ def test_argument_validation_without_gpu():
     assert lib.gm_launch_count() == 0 or torch.cuda.is_available()
 
 
+def test_peer_update_argument_validation_without_gpu():
+    """gm_optim_step_peer rejects malformed peer tables before any launch (struct layout check included)."""
+    from graphembed import _lib as L
+    lib = L.lib()
+    man = L.Manifold(kind=L.GM_SPD_AI, dtype=L.GM_F32, n=4, p=0, flags=0, reserved=0, wmin=1e-8, wmax=1e8)
+    opt = L.Optim(kind=L.GM_OPT_RSGD, exact=0, has_clip=0, step=0, has_momentum=0, first_step=0, grassmann_retr_qr=0,
+                  reserved=0, lr=0.1, beta1=0, beta2=0, momentum=0, dampening=0, max_grad_norm=0, eps=1e-8)
+    t = L.Peers()
+    t.world, t.rank, t.row_lo, t.epoch, t.n_acc = 2, 0, 0, 1, 0
+    call = lambda n=8: lib.gm_optim_step_peer(ctypes.byref(man), ctypes.byref(opt), ctypes.byref(t), None, None, n, None)  # noqa: E731
+    assert call() == -3  # NULL tables
+    t.world = 9
+    assert call() == -1  # more ranks than GM_MAX_PEERS
+    t.world, t.rank = 2, 2
+    assert call() == -1  # rank out of range
+    t.rank, t.epoch = 0, 0
+    assert call() == -1  # epochs start at 1
+    t.epoch = 1
+    assert call(0) == -1  # every rank must own rows
+    assert ctypes.sizeof(L.Peers) == 8 + 8 + 8 + 4 * 8 * L.GM_MAX_PEERS + 8 + 8
+    assert lib.gm_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) == -1
+    assert lib.gm_peer_export(None, None) == -3
+
+
 def test_no_cpu_fallback():
     from graphembed.manifolds import SymmetricPositiveDefinite, Lorentz
     from graphembed.modules import ManifoldParameter
