@@ -46,7 +46,9 @@ enum gm_manifold_kind {
   GM_LORENTZ = 2,   /* manifolds/lorentz.py:72-77                                          */
   GM_SPHERE = 3,    /* manifolds/sphere.py:68-74                                           */
   GM_GRASSMANN = 4, /* manifolds/grassmann.py:91-96                                        */
-  GM_EUCLIDEAN = 5  /* manifolds/euclidean.py:46-50 via base.py:56-57                      */
+  GM_EUCLIDEAN = 5, /* manifolds/euclidean.py:46-50 via base.py:56-57                      */
+  GM_UNIVERSAL = 6  /* manifolds/universal.py:76-81 + manifolds/impl/math.py:567-572: kappa-stereographic model
+                       (c > 0: Poincare ball of curvature -c, c < 0: stereographic sphere), learnable c       */
 };
 
 /* gm_manifold_t.flags */
@@ -63,6 +65,11 @@ typedef struct gm_manifold {
   int32_t reserved;
   double wmin; /* SPD eigenvalue / distance clamp (spd.py:28-29), default 1e-8 */
   double wmax; /* default 1e8 */
+  /* GM_UNIVERSAL only (ignored otherwise; zero-initialise).  The curvature parameter is read ON THE DEVICE so that a
+   * curvature optimizer can update it between steps without a host round trip (universal.py:28-32 get_c()). */
+  const void* c_dev; /* DEVICE pointer to one scalar of `dtype`: c = Universal.get_c(), must be non-zero          */
+  double* c_grad;    /* optional DEVICE double: gm_pairs_grad / gm_pairs_loss_fused add sum_k w_k d(d2_k)/dc to it
+                        (w_k = the per-pair weight the point gradients are scaled with); NULL: not wanted        */
 } gm_manifold_t;
 
 /* How the P pairs of one launch are enumerated. */

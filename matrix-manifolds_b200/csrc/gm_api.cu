@@ -41,12 +41,14 @@ int vec_point_0(const PointArgs& a);
 int vec_point_1(const PointArgs& a);
 int vec_point_2(const PointArgs& a);
 int vec_point_3(const PointArgs& a);
+int vec_point_4(const PointArgs& a);
 static int vec_point(const PointArgs& a) {
   switch (a.kind) {
     case GM_LORENTZ: return vec_point_0(a);
     case GM_SPHERE: return vec_point_1(a);
     case GM_EUCLIDEAN: return vec_point_2(a);
     case GM_GRASSMANN: return vec_point_3(a);
+    case GM_UNIVERSAL: return vec_point_4(a);
     default: return GM_EINVAL;
   }
 }
@@ -96,6 +98,9 @@ static int manifold_ok(const gm_manifold_t* m) {
     case GM_SPHERE:
     case GM_EUCLIDEAN:
       return m->n >= 1 ? GM_OK : GM_EINVAL;
+    case GM_UNIVERSAL:
+      if (m->n < 1) return GM_EINVAL;
+      return m->c_dev ? GM_OK : GM_ENULL;
     case GM_GRASSMANN:
       if (m->n < 1 || m->p < 1 || m->p > m->n) return GM_EINVAL;
       if (m->p > 5) return GM_EUNSUPPORTED;
@@ -109,6 +114,7 @@ static int manifold_ok(const gm_manifold_t* m) {
 static void fill_manifold(PairArgs& a, const gm_manifold_t* m) {
   a.kind = m->kind; a.dtype = m->dtype; a.n = m->n; a.p = m->p; a.flags = m->flags;
   a.wmin = m->wmin; a.wmax = m->wmax;
+  a.c_dev = m->c_dev; a.c_grad = m->c_grad;
 }
 
 static int pair_dispatch(const PairArgs& a) {
@@ -268,7 +274,7 @@ int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, cons
   if (opt->kind == GM_OPT_RSGD && opt->has_momentum && !buf1) return GM_ENULL;
   PointArgs a{};
   a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
-  a.wmin = man->wmin; a.wmax = man->wmax;
+  a.wmin = man->wmin; a.wmax = man->wmax; a.c_dev = man->c_dev;
   a.op = -1;
   a.oc = make_optim_cfg(opt);
   a.grassmann_retr_qr = opt->grassmann_retr_qr;
@@ -328,7 +334,7 @@ int gm_optim_step_peer(const gm_manifold_t* man, const gm_optim_t* opt, const gm
   pt.acc_out = (double*)peers->acc_out; pt.n_acc = peers->n_acc;
   PointArgs a{};
   a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
-  a.wmin = man->wmin; a.wmax = man->wmax;
+  a.wmin = man->wmin; a.wmax = man->wmax; a.c_dev = man->c_dev;
   a.op = -1;
   a.oc = make_optim_cfg(opt);
   a.grassmann_retr_qr = opt->grassmann_retr_qr;
@@ -353,7 +359,7 @@ int gm_point_op(const gm_manifold_t* man, int32_t op, const void* x, const void*
   if ((needs_u && !u) || (needs_v && !v)) return GM_ENULL;
   PointArgs a{};
   a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
-  a.wmin = man->wmin; a.wmax = man->wmax;
+  a.wmin = man->wmin; a.wmax = man->wmax; a.c_dev = man->c_dev;
   a.op = op;
   a.grassmann_retr_qr = 0;
   if (op == GM_OP_RETR_QR) { a.op = GM_OP_RETR; a.grassmann_retr_qr = 1; }

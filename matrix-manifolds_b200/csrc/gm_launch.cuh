@@ -60,6 +60,8 @@ struct PairArgs {
   int kind, dtype, n, p;
   unsigned flags;
   double wmin, wmax;
+  const void* c_dev;  // GM_UNIVERSAL: device scalar c
+  double* c_grad;     // GM_UNIVERSAL: optional device accumulator of d(loss)/dc
   int kmode;
   PairSpec ps;
   const void* xa;

@@ -441,18 +441,80 @@ struct GrassmannCore {
 //   value(x, y, n, c): returns d^2 and the scalar c = d(d^2)/d(dot-like quantity)
 //   gx[k] = c * sx(k) * y[k]  (Lorentz/Sphere),  Euclidean: gx = -2 (y - x).
 // ===========================================================================
-enum VecKind { VEC_LORENTZ = 0, VEC_SPHERE = 1, VEC_EUCLIDEAN = 2 };
+enum VecKind { VEC_LORENTZ = 0, VEC_SPHERE = 1, VEC_EUCLIDEAN = 2, VEC_UNIVERSAL = 3 };
+
+// Per-pair gradient coefficients.  Lorentz / Sphere / Euclidean use `c` only; Universal:
+//   z_k = zA x_k + zB y_k,  gx_k = p1 z_k + p2 x_k + p3 y_k,  gy_k = q1 z_k + q2 y_k + p3 x_k,  dc = d(d^2)/d(c)
+template <typename T>
+struct VecCoef {
+  T c;
+  T zA, zB, p1, p2, p3, q1, q2, dc;
+};
+
+// ---------------------------------------------------------------------------
+// kappa-stereographic ("Universal") model: manifolds/universal.py + manifolds/impl/math.py.
+// c > 0: Poincare ball (tanh / artanh), c < 0: stereographic sphere (tan / atan).
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Kappa {
+  static constexpr double kMinNorm = 1e-15;  // math.py:15 MIN_NORM
+  // math.py:21-22
+  GM_HD static T tanh_clamped(T x) { return Num<T>::tanh(clampv(x, (T)-15, (T)15)); }
+  // Artanh.forward (math.py:25-35): clamp in T, evaluate in double, cast back.  `xc` returns the clamped input the
+  // backward divides by (math.py:37-40).
+  GM_HD static T artanh(T x, T& xc) {
+    xc = clampv(x, (T)(-1.0 + 1e-15), (T)(1.0 - 1e-15));
+    double xd = (double)xc;
+    return (T)((::log(1.0 + xd) - ::log(1.0 - xd)) * 0.5);
+  }
+  GM_HD static T tan_func(T x, T c) { return c > (T)0 ? tanh_clamped(x) : Num<T>::tan(x); }  // math.py:73-85
+  // arctan_func (math.py:88-99) and its derivative at x
+  GM_HD static T arctan_func(T x, T c, T& dphi) {
+    if (c > (T)0) {
+      T xc;
+      T r = artanh(x, xc);
+      dphi = (T)1 / ((T)1 - xc * xc);
+      return r;
+    }
+    dphi = (T)1 / ((T)1 + x * x);
+    return Num<T>::atan(x);
+  }
+  GM_HD static T lambda_x(T x2, T c) { return (T)2 / clamp_min((T)1 - c * x2, (T)kMinNorm); }  // math.py:187-190
+  // out = x (+)_c y  (math.py:326-345)
+  GM_HD static void mobius_add(const T* x, const T* y, int n, T c, T* out) {
+    T x2 = (T)0, y2 = (T)0, xy = (T)0;
+    for (int k = 0; k < n; ++k) { x2 += x[k] * x[k]; y2 += y[k] * y[k]; xy += x[k] * y[k]; }
+    T a = (T)1 + (T)2 * c * xy + c * y2;
+    T b = (T)1 - c * x2;
+    T den = clamp_min((T)1 + (T)2 * c * xy + c * c * x2 * y2, (T)kMinNorm);
+    for (int k = 0; k < n; ++k) out[k] = (a * x[k] + b * y[k]) / den;
+  }
+  // project (math.py:142-156): only the ball (c > 0) has a boundary
+  GM_HD static void project(const T* x, int n, T c, T ball_eps, T* out) {
+    T s = (T)0;
+    for (int k = 0; k < n; ++k) s += x[k] * x[k];
+    T nrm = clamp_min(Num<T>::sqrt(s), (T)kMinNorm);
+    T maxnorm = ((T)1 - ball_eps) / Num<T>::sqrt(Num<T>::abs(c));
+    bool cond = (c > (T)0) && (nrm > maxnorm);
+    for (int k = 0; k < n; ++k) out[k] = cond ? (x[k] / nrm) * maxnorm : x[k];
+  }
+};
 
 template <typename T, int KIND>
 struct VecMan {
   T eps;    // EPS[dtype] = 1e-8 (utils.py:13)
   T one_m;  // 1 - EPS^2 in T
+  const T* c_dev;  // Universal: device scalar c = get_c() (universal.py:28-32)
 
   // Lorentz (lorentz.py:72-77,101-141): z = x0 y0 - sum_{k>=1} xk yk, clamp z >= 1,
   //   d = log(z + sqrt(z^2-1)) clamped >= EPS; Acosh backward divides by max(sqrt(z^2-1), EPS).
   // Sphere (sphere.py:68-74): s = <x,y> clamped to +-(1-EPS^2), d = acos(s) clamped >= EPS.
   // Euclidean (euclidean.py:46-50 + base.py:29-32): d^2 = max(|y-x|^2, EPS).
-  GM_HD T value(const T* __restrict__ x, const T* __restrict__ y, int n, T& c) const {
+  // Universal (universal.py:76-81, math.py:567-572): z = (-x) (+)_c y, d = 2 arctan_c(sqrt|c| |z|) / sqrt|c|,
+  //   d^2 clamped >= EPS (value only).  The gradient is taken through the vector z exactly as autograd does
+  //   (z_k has no cancellation when x ~ y; a closed form in <x,x>, <y,y>, <x,y> would).
+  GM_HD T value(const T* __restrict__ x, const T* __restrict__ y, int n, VecCoef<T>& co) const {
+    T& c = co.c;
     if constexpr (KIND == VEC_LORENTZ) {
       T s = -(x[0] * y[0]);
       for (int k = 1; k < n; ++k) s += x[k] * y[k];
@@ -468,23 +530,67 @@ struct VecMan {
       T d = clamp_min(Num<T>::acos(s), eps);
       c = -(T)2 * d / Num<T>::sqrt((T)1 - s * s);
       return d * d;
-    } else {
+    } else if constexpr (KIND == VEC_EUCLIDEAN) {
       T s = (T)0;
       for (int k = 0; k < n; ++k) { T d = y[k] - x[k]; s += d * d; }
       c = (T)2;
       return clamp_min(s, eps);
+    } else {
+      const T cc = *c_dev;
+      c = cc;
+      T x2 = (T)0, y2 = (T)0, xy = (T)0;
+      for (int k = 0; k < n; ++k) { x2 += x[k] * x[k]; y2 += y[k] * y[k]; xy += x[k] * y[k]; }
+      // mobius_add(-x, y): num = A (-x) + B y, denom = D  (math.py:326-345 with <-x, y> = -xy)
+      const T A = (T)1 - (T)2 * cc * xy + cc * y2;
+      const T B = (T)1 - cc * x2;
+      const T D = (T)1 - (T)2 * cc * xy + cc * cc * x2 * y2;
+      const bool d_free = D >= (T)Kappa<T>::kMinNorm;  // clamp_min passes the gradient only where it is inactive
+      const T invD = (T)1 / clamp_min(D, (T)Kappa<T>::kMinNorm);
+      co.zA = -A * invD;
+      co.zB = B * invD;
+      T r2 = (T)0, zx = (T)0, zy = (T)0;
+      for (int k = 0; k < n; ++k) {
+        T z = co.zA * x[k] + co.zB * y[k];
+        r2 += z * z; zx += z * x[k]; zy += z * y[k];
+      }
+      const T r = Num<T>::sqrt(r2);
+      const T sc = Num<T>::sqrt(Num<T>::abs(cc));
+      T dphi;
+      const T phi = Kappa<T>::arctan_func(sc * r, cc, dphi);
+      const T d = phi * (T)2 / sc;
+      const T d2 = d * d;
+      // d(d^2)/dz_k = gz z_k, gz = 4 d phi' / r (torch.norm's subgradient at r == 0 is 0)
+      const T gz = (r > (T)0) ? (T)4 * d * dphi / r : (T)0;
+      const T dA = -(gz * zx) * invD;
+      const T dB = (gz * zy) * invD;
+      const T dD = d_free ? -(gz * r2) * invD : (T)0;
+      const T g_xy = -(T)2 * cc * (dA + dD);
+      const T g_x2 = -cc * dB + cc * cc * y2 * dD;
+      const T g_y2 = cc * dA + cc * cc * x2 * dD;
+      co.p1 = co.zA * gz; co.p2 = (T)2 * g_x2; co.p3 = g_xy;
+      co.q1 = co.zB * gz; co.q2 = (T)2 * g_y2;
+      // d(d^2)/dc: through A, B, D and through sqrt|c| (u = sc r and the 2/sc factor)
+      const T sgn = cc > (T)0 ? (T)1 : (T)-1;
+      co.dc = dA * (y2 - (T)2 * xy) - dB * x2 + dD * ((T)2 * cc * x2 * y2 - (T)2 * xy) +
+              ((T)4 * d * dphi * r - (T)2 * d2) / sc * (sgn * (T)0.5 / sc);
+      return clamp_min(d2, eps);
     }
   }
   // gradient element k of d^2 w.r.t. x and y
-  GM_HD void grad_elem(int k, T xk, T yk, T c, T& gxk, T& gyk) const {
+  GM_HD void grad_elem(int k, T xk, T yk, const VecCoef<T>& co, T& gxk, T& gyk) const {
+    const T c = co.c;
     if constexpr (KIND == VEC_LORENTZ) {
       T sg = (k == 0) ? c : -c;
       gxk = sg * yk; gyk = sg * xk;
     } else if constexpr (KIND == VEC_SPHERE) {
       gxk = c * yk; gyk = c * xk;
-    } else {
+    } else if constexpr (KIND == VEC_EUCLIDEAN) {
       T d = yk - xk;
       gxk = -c * d; gyk = c * d;
+    } else {
+      T z = co.zA * xk + co.zB * yk;
+      gxk = co.p1 * z + co.p2 * xk + co.p3 * yk;
+      gyk = co.q1 * z + co.q2 * yk + co.p3 * xk;
     }
   }
 };

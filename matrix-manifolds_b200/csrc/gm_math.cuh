@@ -128,6 +128,8 @@ template <> struct Num<float> {
   GM_HD static float exp(float x) { return expf(x); }
   GM_HD static float acos(float x) { return acosf(x); }
   GM_HD static float atan(float x) { return atanf(x); }
+  GM_HD static float tan(float x) { return tanf(x); }
+  GM_HD static float tanh(float x) { return tanhf(x); }
   GM_HD static float cos(float x) { return cosf(x); }
   GM_HD static float sin(float x) { return sinf(x); }
   GM_HD static float cosh(float x) { return coshf(x); }
@@ -159,6 +161,8 @@ template <> struct Num<double> {
   GM_HD static double exp(double x) { return ::exp(x); }
   GM_HD static double acos(double x) { return ::acos(x); }
   GM_HD static double atan(double x) { return ::atan(x); }
+  GM_HD static double tan(double x) { return ::tan(x); }
+  GM_HD static double tanh(double x) { return ::tanh(x); }
   GM_HD static double cos(double x) { return ::cos(x); }
   GM_HD static double sin(double x) { return ::sin(x); }
   GM_HD static double cosh(double x) { return ::cosh(x); }

@@ -1,11 +1,12 @@
-// Pair kernels for the vector manifolds (Lorentz, Sphere, Euclidean) and the
-// Grassmannian.  One pair per thread; points have a run-time length and are
+// Pair kernels for the vector manifolds (Lorentz, Sphere, Euclidean, Universal)
+// and the Grassmannian.  One pair per thread; points have a run-time length and are
 // streamed from global memory (rows are short, the second pass hits L1).
 //
 // Replaces Lorentz.dist (manifolds/lorentz.py:72-77 + LorentzDot/Acosh :101-141),
 // Sphere.dist (manifolds/sphere.py:68-74), the Euclidean distance obtained from
-// base.py:56-57, Grassmann.dist (manifolds/grassmann.py:91-96), each fused with
-// the pair gather (base.py:59-63), the loss and the gradient scatter-add.
+// base.py:56-57, Universal.dist (manifolds/universal.py:76-81 + impl/math.py:567-572),
+// Grassmann.dist (manifolds/grassmann.py:91-96), each fused with the pair gather
+// (base.py:59-63), the loss and the gradient scatter-add.
 #include "gm_launch.cuh"
 
 namespace gm {
@@ -25,13 +26,15 @@ template <typename T, int KIND, int KMODE>
 __global__ void __launch_bounds__(128)
 vec_pair_kernel(VecMan<T, KIND> op, int n, PairSpec ps, const T* __restrict__ xa, const T* __restrict__ xb,
                 const T* __restrict__ gout, T coef, T* __restrict__ ga, T* __restrict__ gb,
-                T* __restrict__ out_d2, TargetSpec tg, LossCfg lc, T scale_sp, double* __restrict__ acc) {
-  __shared__ double red[2][4];
+                T* __restrict__ out_d2, TargetSpec tg, LossCfg lc, T scale_sp, double* __restrict__ acc,
+                double* __restrict__ c_grad) {
+  __shared__ double red[3][4];
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = k < ps.P;
   long long ra = -1, rb = -1;
   double loss_v = 0.0, gd2_v = 0.0;
-  T c = (T)0, w = (T)0;
+  VecCoef<T> c{};
+  T w = (T)0;
   const T* px = xa;
   const T* py = xb;
   if (active) {
@@ -83,6 +86,9 @@ vec_pair_kernel(VecMan<T, KIND> op, int n, PairSpec ps, const T* __restrict__ xa
     block_accumulate(loss_v, acc, red[0]);
     block_accumulate(gd2_v, acc + 1, red[1]);
   }
+  if constexpr (KIND == VEC_UNIVERSAL && KMODE != K_FWD) {  // d(loss)/dc (block-uniform branch)
+    if (c_grad) block_accumulate(active ? (double)w * (double)c.dc : 0.0, c_grad, red[2]);
+  }
 }
 
 template <typename T, int P, bool FAST, int KMODE>
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(128)
 grassmann_pair_kernel(GrassmannCore<T, P, FAST> op, int n, PairSpec ps, const T* __restrict__ xa,
                       const T* __restrict__ xb, const T* __restrict__ gout, T coef, T* __restrict__ ga,
                       T* __restrict__ gb, T* __restrict__ out_d2, TargetSpec tg, LossCfg lc, T scale_sp,
-                      double* __restrict__ acc) {
+                      double* __restrict__ acc, double* __restrict__ /*c_grad: Universal only*/) {
   __shared__ double red[2][4];
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = k < ps.P;
@@ -170,17 +176,18 @@ grassmann_pair_kernel(GrassmannCore<T, P, FAST> op, int n, PairSpec ps, const T*
   switch (a.kmode) {                                                                                             \
     case K_FWD:                                                                                                  \
       KERNEL<__VA_ARGS__, K_FWD><<<grid, block, 0, a.stream>>>(OP, a.n, a.ps, xa, xb, nullptr, (T)0, nullptr,     \
-                                                               nullptr, (T*)a.out_d2, a.tg, a.lc, (T)0, nullptr); \
+                                                               nullptr, (T*)a.out_d2, a.tg, a.lc, (T)0, nullptr, \
+                                                               nullptr);                                          \
       break;                                                                                                     \
     case K_BWD:                                                                                                  \
       KERNEL<__VA_ARGS__, K_BWD><<<grid, block, 0, a.stream>>>(OP, a.n, a.ps, xa, xb, (const T*)a.gout,           \
                                                                (T)a.coef, (T*)a.ga, (T*)a.gb, nullptr, a.tg,      \
-                                                               a.lc, (T)0, nullptr);                              \
+                                                               a.lc, (T)0, nullptr, a.c_grad);                    \
       break;                                                                                                     \
     default:                                                                                                     \
       KERNEL<__VA_ARGS__, K_FUSED><<<grid, block, 0, a.stream>>>(OP, a.n, a.ps, xa, xb, nullptr, (T)0,            \
                                                                  (T*)a.ga, (T*)a.gb, (T*)a.out_d2, a.tg, a.lc,    \
-                                                                 (T)a.scale_sp, a.acc);                           \
+                                                                 (T)a.scale_sp, a.acc, a.c_grad);                 \
   }
 
 template <typename T>
@@ -201,14 +208,17 @@ static int vec_launch_typed(const PairArgs& a) {
   const T* xb = (const T*)a.xb;
   const T eps = (T)1e-8;
   if (a.kind == GM_LORENTZ) {
-    VecMan<T, VEC_LORENTZ> op{eps, one_minus_eps2<T>()};
+    VecMan<T, VEC_LORENTZ> op{eps, one_minus_eps2<T>(), nullptr};
     GM_LAUNCH3(vec_pair_kernel, op, T, VEC_LORENTZ)
   } else if (a.kind == GM_SPHERE) {
-    VecMan<T, VEC_SPHERE> op{eps, one_minus_eps2<T>()};
+    VecMan<T, VEC_SPHERE> op{eps, one_minus_eps2<T>(), nullptr};
     GM_LAUNCH3(vec_pair_kernel, op, T, VEC_SPHERE)
   } else if (a.kind == GM_EUCLIDEAN) {
-    VecMan<T, VEC_EUCLIDEAN> op{eps, one_minus_eps2<T>()};
+    VecMan<T, VEC_EUCLIDEAN> op{eps, one_minus_eps2<T>(), nullptr};
     GM_LAUNCH3(vec_pair_kernel, op, T, VEC_EUCLIDEAN)
+  } else if (a.kind == GM_UNIVERSAL) {
+    VecMan<T, VEC_UNIVERSAL> op{(T)a.wmin, one_minus_eps2<T>(), (const T*)a.c_dev};  // value floor: wmin
+    GM_LAUNCH3(vec_pair_kernel, op, T, VEC_UNIVERSAL)
   } else if (a.kind == GM_GRASSMANN) {
     const bool fast = (a.flags & GM_FAST_SVD) != 0;
     if (a.p == 2 && fast) {

@@ -29,6 +29,7 @@ struct PointArgs {
   int kind, dtype, n, p;
   unsigned flags;
   double wmin, wmax;
+  const void* c_dev;  // GM_UNIVERSAL: device scalar c
   int op;  // gm_point_op, or -1 for the optimizer step
   OptimCfg oc;
   int grassmann_retr_qr;

@@ -268,6 +268,86 @@ struct EuclideanPt {  // manifolds/euclidean.py
   }
 };
 
+// kappa-stereographic "Universal" manifold (manifolds/universal.py over manifolds/impl/math.py); the curvature
+// parameter c = get_c() is read from device memory (it is itself being optimised).
+template <typename T, int CAP_>
+struct UniversalPt {
+  static constexpr int CAP = CAP_;
+  static constexpr bool kStatic = false;
+  int n;
+  T eps;
+  const T* c_dev;
+  T ball_eps;  // BALL_EPS[dtype]: 4e-3 (fp32) / 1e-5 (fp64), math.py:16
+  GM_HD int count() const { return n; }
+  GM_HD T c() const { return *c_dev; }
+  GM_HD T sq(const T* u) const {
+    T s = (T)0;
+    for (int k = 0; k < n; ++k) s += u[k] * u[k];
+    return s;
+  }
+  GM_HD void proju(const T* x, const T* u, T* out) const { for (int k = 0; k < n; ++k) out[k] = u[k]; }  // :50-51
+  GM_HD void projx(const T* x, T* out) const { Kappa<T>::project(x, n, c(), ball_eps, out); }            // :53-57
+  GM_HD void egrad2rgrad(const T* x, const T* g, T* out) const {  // :59-60, math.py:1452-1453
+    T lam = Kappa<T>::lambda_x(sq(x), c());
+    T l2 = lam * lam;
+    for (int k = 0; k < n; ++k) out[k] = g[k] / l2;
+  }
+  // Universal.norm calls math.norm WITHOUT c (universal.py:44-48) => lambda_x is evaluated with the default c = 1.0
+  GM_HD T norm2(const T* x, const T* u) const {
+    T nn = Kappa<T>::lambda_x(sq(x), (T)1) * Num<T>::sqrt(sq(u));
+    return nn * nn;
+  }
+  GM_HD T inner(const T* x, const T* u, const T* v) const {  // :41-42, math.py:225-228
+    T lam = Kappa<T>::lambda_x(sq(x), c());
+    T s = (T)0;
+    for (int k = 0; k < n; ++k) s += u[k] * v[k];
+    return lam * lam * s;
+  }
+  GM_HD void exp(const T* x, const T* u, T* out) const {  // :62-67, math.py:720-727 then project
+    const T cc = c();
+    T sc = Num<T>::sqrt(Num<T>::abs(cc));
+    T un = clamp_min(Num<T>::sqrt(sq(u)), (T)Kappa<T>::kMinNorm);
+    T f = Kappa<T>::tan_func(sc / (T)2 * Kappa<T>::lambda_x(sq(x), cc) * un, cc);
+    T second[CAP], g1[CAP];
+    for (int k = 0; k < n; ++k) second[k] = f * u[k] / (sc * un);
+    Kappa<T>::mobius_add(x, second, n, cc, g1);
+    Kappa<T>::project(g1, n, cc, ball_eps, out);
+  }
+  GM_HD void retr(const T* x, const T* u, T* out) const {  // :69-70
+    T t[CAP];
+    for (int k = 0; k < n; ++k) t[k] = x[k] + u[k];
+    Kappa<T>::project(t, n, c(), ball_eps, out);
+  }
+  GM_HD void log(const T* x, const T* y, T* out) const {  // :72-73, math.py:835-841
+    const T cc = c();
+    T nx[CAP], sub[CAP];
+    for (int k = 0; k < n; ++k) nx[k] = -x[k];
+    Kappa<T>::mobius_add(nx, y, n, cc, sub);
+    T sn = clamp_min(Num<T>::sqrt(sq(sub)), (T)Kappa<T>::kMinNorm);
+    T lam = Kappa<T>::lambda_x(sq(x), cc);
+    T sc = Num<T>::sqrt(Num<T>::abs(cc));
+    T dphi;
+    T f = (T)2 / sc / lam * Kappa<T>::arctan_func(sc * sn, cc, dphi);
+    for (int k = 0; k < n; ++k) out[k] = f * sub[k] / sn;
+  }
+  // parallel_transport (math.py:1359-1362): gyr[y, -x] u * lambda_x / lambda_y, gyration simplified as math.py:1282-1298
+  GM_HD void transp(const T* x, const T* y, const T* w, T* out) const {  // :83-84
+    const T cc = c();
+    // u := y, v := -x
+    T u2 = sq(y), v2 = sq(x), uv = (T)0, uw = (T)0, vw = (T)0;
+    for (int k = 0; k < n; ++k) { uv -= y[k] * x[k]; uw += y[k] * w[k]; vw -= x[k] * w[k]; }
+    T c2 = cc * cc;
+    T a = -c2 * uw * v2 + cc * vw + (T)2 * c2 * uv * vw;
+    T b = -c2 * vw * u2 - cc * uw;
+    T d = clamp_min((T)1 + (T)2 * cc * uv + c2 * u2 * v2, (T)Kappa<T>::kMinNorm);
+    T ratio_x = Kappa<T>::lambda_x(v2, cc), ratio_y = Kappa<T>::lambda_x(u2, cc);
+    for (int k = 0; k < n; ++k) {
+      T gyr = w[k] + (T)2 * (a * y[k] + b * (-x[k])) / d;
+      out[k] = gyr * ratio_x / ratio_y;
+    }
+  }
+};
+
 // ===========================================================================
 // Grassmann Gr(n, P), points are n x P row-major, n <= NMAX (manifolds/grassmann.py).
 // Thin SVDs are taken through the P x P Gram matrix (Jacobi, registers): every

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get('GM_B200_LIB') or os.path.join(os.path.dirname(_HERE),
 
 # ---- enums (include/gm_kernels.h) -------------------------------------------
 GM_F32, GM_F64 = 0, 1
-GM_SPD_AI, GM_SPD_STEIN, GM_LORENTZ, GM_SPHERE, GM_GRASSMANN, GM_EUCLIDEAN = range(6)
+GM_SPD_AI, GM_SPD_STEIN, GM_LORENTZ, GM_SPHERE, GM_GRASSMANN, GM_EUCLIDEAN, GM_UNIVERSAL = range(7)
 GM_FAST_EIG, GM_FAST_CHOL, GM_FAST_SVD = 1, 2, 4
 GM_PAIRS_ELEMENTWISE, GM_PAIRS_LIST, GM_PAIRS_TRIU = 0, 1, 2
 GM_LOSS_QUOTIENT, GM_LOSS_STRESS = 0, 1
@@ -31,7 +31,7 @@ _ERRORS = {-1: 'GM_EINVAL (bad argument combination)', -2: 'GM_EUNSUPPORTED (no 
 class Manifold(ctypes.Structure):
     _fields_ = [('kind', ctypes.c_int32), ('dtype', ctypes.c_int32), ('n', ctypes.c_int32), ('p', ctypes.c_int32),
                 ('flags', ctypes.c_uint32), ('reserved', ctypes.c_int32), ('wmin', ctypes.c_double),
-                ('wmax', ctypes.c_double)]
+                ('wmax', ctypes.c_double), ('c_dev', ctypes.c_void_p), ('c_grad', ctypes.c_void_p)]
 
 
 class Pairs(ctypes.Structure):

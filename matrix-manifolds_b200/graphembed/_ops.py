@@ -14,15 +14,31 @@ from . import _lib as L
 class ManifoldSpec:
     """(kind, n, p, flags, wmin, wmax) of one manifold; dtype is taken from the tensors."""
 
-    __slots__ = ('kind', 'n', 'p', 'flags', 'wmin', 'wmax', 'point_shape')
+    __slots__ = ('kind', 'n', 'p', 'flags', 'wmin', 'wmax', 'point_shape', 'c_source', '_keep')
 
-    def __init__(self, kind, n, p=0, flags=0, wmin=1e-8, wmax=1e8, point_shape=None):
+    def __init__(self, kind, n, p=0, flags=0, wmin=1e-8, wmax=1e8, point_shape=None, c_source=None):
         self.kind, self.n, self.p, self.flags, self.wmin, self.wmax = kind, n, p, flags, wmin, wmax
         self.point_shape = tuple(point_shape)
+        self.c_source = c_source  # Universal: callable returning the current curvature tensor get_c()
+        self._keep = None
 
-    def c_struct(self, dtype):
+    def c_struct(self, dtype, device=None, c=None, c_grad=None, wmin=None):
+        """gm_manifold_t for tensors of `dtype`.  Universal: `c` (default: c_source()) is passed as a DEVICE scalar so
+        that no host sync is needed while a curvature optimizer updates it; `c_grad` is an optional float64 CUDA
+        scalar that the backward kernels add d(loss)/dc to."""
+        c_dev = None
+        if self.kind == L.GM_UNIVERSAL:
+            if c is None:
+                c = self.c_source()
+            c = c.detach().reshape(-1)[:1].to(dtype=dtype)
+            if device is not None and c.device != device:
+                c = c.to(device)
+            L.require_cuda(c)
+            self._keep = c = c.contiguous()  # alive until the next launch on this (stream-ordered) allocator
+            c_dev = c.data_ptr()
         return L.Manifold(kind=self.kind, dtype=L.dtype_code(dtype), n=self.n, p=self.p, flags=self.flags,
-                          reserved=0, wmin=self.wmin, wmax=self.wmax)
+                          reserved=0, wmin=self.wmin if wmin is None else wmin, wmax=self.wmax, c_dev=c_dev,
+                          c_grad=None if c_grad is None else c_grad.data_ptr())
 
     @property
     def numel(self):
@@ -101,12 +117,12 @@ class PairSet:
                        nodes=None if self.nodes is None else self.nodes.data_ptr(), k0=self.k0)
 
 
-def pairs_dist2(spec, xa, xb, pairs):
+def pairs_dist2(spec, xa, xb, pairs, c=None, wmin=None):
     xa, xb = _prep(xa), _prep(xb)
     if xa.dtype != xb.dtype:
         raise RuntimeError('dtype mismatch between the two endpoint tensors')
     out = torch.empty(pairs.P, dtype=xa.dtype, device=xa.device)
-    m, p = spec.c_struct(xa.dtype), pairs.c_struct()
+    m, p = spec.c_struct(xa.dtype, xa.device, c=c, wmin=wmin), pairs.c_struct()
     with torch.cuda.device(xa.device):
         rc = L.lib().gm_pairs_dist2(ctypes.byref(m), L.ptr(xa), L.ptr(xb), ctypes.byref(p), L.ptr(out),
                                     L.stream_ptr(xa.device))
@@ -114,12 +130,13 @@ def pairs_dist2(spec, xa, xb, pairs):
     return out
 
 
-def pairs_grad(spec, xa, xb, pairs, gout, ga, gb, coef=1.0):
-    """ga/gb += coef * gout[k] * d(d2_k)/d(rows) (ELEMENTWISE: plain stores)."""
+def pairs_grad(spec, xa, xb, pairs, gout, ga, gb, coef=1.0, c=None, c_grad=None):
+    """ga/gb += coef * gout[k] * d(d2_k)/d(rows) (ELEMENTWISE: plain stores).  Universal: c_grad (float64 CUDA
+    scalar) += coef * sum_k gout[k] * d(d2_k)/dc."""
     xa, xb, gout = _prep(xa), _prep(xb), _prep(gout)
     if gout.dtype != xa.dtype:
         gout = gout.to(xa.dtype)
-    m, p = spec.c_struct(xa.dtype), pairs.c_struct()
+    m, p = spec.c_struct(xa.dtype, xa.device, c=c, c_grad=c_grad), pairs.c_struct()
     with torch.cuda.device(xa.device):
         rc = L.lib().gm_pairs_grad(ctypes.byref(m), L.ptr(xa), L.ptr(xb), ctypes.byref(p), L.ptr(gout), float(coef),
                                    L.ptr(ga), L.ptr(gb), L.stream_ptr(xa.device))
@@ -167,16 +184,18 @@ class TargetSpec:
                          ld=self.ld, max_sq=float(self.max_sq))
 
 
-def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, want_d2=False):
+def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, want_d2=False, c=None, c_grad=None):
     """One kernel: distances, loss and gradient.  Returns (acc, d2 or None); acc is a 2-element float64 tensor
-    [sum loss, sum l'(m) * d2] that is accumulated into (pass a zeroed one or None)."""
+    [sum loss, sum l'(m) * d2] that is accumulated into (pass a zeroed one or None).  Universal: c_grad (float64
+    CUDA scalar) += d(loss)/dc."""
     x = _prep(x)
     if targets.mode in (L.GM_TGT_VECTOR, L.GM_TGT_DENSE) and targets.data.dtype != x.dtype:
         raise RuntimeError('targets must have the dtype of the embedding')
     if acc is None:
         acc = torch.zeros(2, dtype=torch.float64, device=x.device)
     d2 = torch.empty(pairs.P, dtype=x.dtype, device=x.device) if want_d2 else None
-    m, p, t, l = spec.c_struct(x.dtype), pairs.c_struct(), targets.c_struct(), loss.c_struct()
+    m, p, t, l = (spec.c_struct(x.dtype, x.device, c=c, c_grad=c_grad), pairs.c_struct(), targets.c_struct(),
+                  loss.c_struct())
     with torch.cuda.device(x.device):
         rc = L.lib().gm_pairs_loss_fused(ctypes.byref(m), L.ptr(x), ctypes.byref(p), ctypes.byref(t), ctypes.byref(l),
                                          float(scale_sp), L.ptr(d2), L.ptr(acc), L.ptr(grad),
@@ -267,7 +286,7 @@ def point_op(spec, op, x, u=None, v=None, scalar=False):
     for b in batch:
         N *= b
     out = torch.empty(batch if scalar else x.shape, dtype=x.dtype, device=x.device)
-    m = spec.c_struct(x.dtype)
+    m = spec.c_struct(x.dtype, x.device)
     with torch.cuda.device(x.device):
         rc = L.lib().gm_point_op(ctypes.byref(m), op, L.ptr(x), L.ptr(u), L.ptr(v), L.ptr(out), N,
                                  L.stream_ptr(x.device))
@@ -282,7 +301,7 @@ def optim_step(spec, cfg, x, grad, buf1=None, buf2=None):
         raise RuntimeError('parameters must be contiguous')
     grad = _prep(grad.to(x.dtype))
     N = x.numel() // spec.numel
-    m = spec.c_struct(x.dtype)
+    m = spec.c_struct(x.dtype, x.device)
     with torch.cuda.device(x.device):
         rc = L.lib().gm_optim_step(ctypes.byref(m), ctypes.byref(cfg), L.ptr(x), L.ptr(grad), L.ptr(buf1),
                                    L.ptr(buf2), N, L.stream_ptr(x.device))
@@ -293,7 +312,7 @@ def optim_step_peer(spec, cfg, arena, own_rows, buf1=None, buf2=None):
     """Fused reduce-scatter + optimizer update + all-gather over NVLink peer memory (gm_optim_step_peer): updates the
     rows of arena.x this rank owns from the sum of every rank's arena.grad and publishes them to every rank."""
     L.require_cuda(arena.x, buf1, buf2)
-    m = spec.c_struct(arena.x.dtype)
+    m = spec.c_struct(arena.x.dtype, arena.x.device)
     table = arena.next_table()
     with torch.cuda.device(arena.x.device):
         rc = L.lib().gm_optim_step_peer(ctypes.byref(m), ctypes.byref(cfg), ctypes.byref(table), L.ptr(buf1),
@@ -308,21 +327,35 @@ class _Dist2Elementwise(torch.autograd.Function):
     """d2[k] = dist^2(x[k], y[k]); backward writes per-row gradients."""
 
     @staticmethod
-    def forward(ctx, x, y, spec):
+    def forward(ctx, x, y, spec, c=None, wmin=None):
         ctx.spec = spec
         x, y = _prep(x), _prep(y)
+        ctx.c = None if c is None else c.detach()
         ctx.save_for_backward(x, y)
         nd = len(spec.point_shape)
         ctx.batch_shape = x.shape[:x.ndim - nd]
-        d2 = pairs_dist2(spec, x, y, PairSet.elementwise(x.numel() // spec.numel))
+        d2 = pairs_dist2(spec, x, y, PairSet.elementwise(x.numel() // spec.numel), c=c, wmin=wmin)
         return d2.view(ctx.batch_shape)
 
     @staticmethod
     def backward(ctx, g):
         x, y = ctx.saved_tensors
         gx, gy = torch.empty_like(x), torch.empty_like(y)
-        pairs_grad(ctx.spec, x, y, PairSet.elementwise(x.numel() // ctx.spec.numel), g.reshape(-1), gx, gy)
-        return gx, gy, None
+        gc = _curvature_grad_buffer(ctx.c, ctx.needs_input_grad[3])
+        pairs_grad(ctx.spec, x, y, PairSet.elementwise(x.numel() // ctx.spec.numel), g.reshape(-1), gx, gy,
+                   c=ctx.c, c_grad=gc)
+        return gx, gy, None, _curvature_grad(ctx.c, gc), None
+
+
+def _curvature_grad_buffer(c, wanted):
+    """float64 device accumulator for d(loss)/dc when the (Universal) curvature tensor wants a gradient."""
+    if c is None or not wanted:
+        return None
+    return torch.zeros(1, dtype=torch.float64, device=c.device)
+
+
+def _curvature_grad(c, gc):
+    return None if gc is None else gc.to(c.dtype).reshape(c.shape)
 
 
 class _Dist2Indexed(torch.autograd.Function):
@@ -330,26 +363,28 @@ class _Dist2Indexed(torch.autograd.Function):
     gradient of x's shape (the fused equivalent of x[I], x[J] gathers + index_put_ backward)."""
 
     @staticmethod
-    def forward(ctx, x, spec, pairs):
-        ctx.spec, ctx.pairs = spec, pairs
+    def forward(ctx, x, spec, pairs, c=None, wmin=None):
+        ctx.spec, ctx.pairs, ctx.c = spec, pairs, (None if c is None else c.detach())
         x = _prep(x)
         ctx.save_for_backward(x)
-        return pairs_dist2(spec, x, x, pairs)
+        return pairs_dist2(spec, x, x, pairs, c=c, wmin=wmin)
 
     @staticmethod
     def backward(ctx, g):
         x, = ctx.saved_tensors
         gx = torch.zeros_like(x)
-        pairs_grad(ctx.spec, x, x, ctx.pairs, g, gx, gx)
-        return gx, None, None
+        gc = _curvature_grad_buffer(ctx.c, ctx.needs_input_grad[3])
+        pairs_grad(ctx.spec, x, x, ctx.pairs, g, gx, gx, c=ctx.c, c_grad=gc)
+        return gx, None, None, _curvature_grad(ctx.c, gc), None
 
 
-def dist2_elementwise(spec, x, y):
-    return _Dist2Elementwise.apply(x, y, spec)
+def dist2_elementwise(spec, x, y, c=None, wmin=None):
+    """`c`: the Universal manifold's curvature tensor get_c() (receives a gradient); None otherwise."""
+    return _Dist2Elementwise.apply(x, y, spec, c, wmin)
 
 
-def dist2_indexed(spec, x, pairs):
-    return _Dist2Indexed.apply(x, spec, pairs)
+def dist2_indexed(spec, x, pairs, c=None, wmin=None):
+    return _Dist2Indexed.apply(x, spec, pairs, c, wmin)
 
 
 def expand_groups(group_rows, offsets, out):

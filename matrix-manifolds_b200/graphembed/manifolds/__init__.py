@@ -4,5 +4,6 @@ from .grassmann import Grassmann
 from .lorentz import Lorentz
 from .spd import SymmetricPositiveDefinite
 from .sphere import Sphere
+from .universal import Universal
 
-__all__ = ['Manifold', 'Euclidean', 'Grassmann', 'Lorentz', 'SymmetricPositiveDefinite', 'Sphere']
+__all__ = ['Manifold', 'Euclidean', 'Grassmann', 'Lorentz', 'SymmetricPositiveDefinite', 'Sphere', 'Universal']

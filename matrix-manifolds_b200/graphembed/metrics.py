@@ -97,7 +97,9 @@ def validation_moments(embedding, dataset, chunk_pairs=1 << 24, pair_range=None)
     if pd.device != dev or pd.dtype != embedding.xs[0].dtype:
         pd = pd.to(device=dev, dtype=embedding.xs[0].dtype)
     targets = _ops.TargetSpec.dense(pd)
-    sps = [float(softplus(s.detach())) for s in embedding.scales]
+    # products.Embedding has no scales: plain sum of the factors' squared distances (products/embedding.py:52-57)
+    sps = [float(softplus(s.detach())) for s in embedding.scales] if hasattr(embedding, 'scales') \
+        else [1.0] * len(embedding.xs)
     acc = torch.zeros(8, dtype=torch.float64, device=dev)
     for lo in range(k0, k1, chunk_pairs):
         pairs = _ops.PairSet.triu(n, k0=lo, P=min(chunk_pairs, k1 - lo))

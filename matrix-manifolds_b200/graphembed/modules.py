@@ -52,6 +52,8 @@ class ManifoldEmbedding(EmbeddingBase):
     """n points on each of the given manifolds; the product distance is
     sum_f softplus(scale_f) * dist_f^2 (modules.py:84-88)."""
 
+    fused_pair_kernels = True  # BatchedObjective may run distance + loss + gradient as fused kernels
+
     def __init__(self, n, manifolds, device=None, dtype=None):
         super().__init__()
         self.n = n
@@ -103,36 +105,53 @@ class ManifoldEmbedding(EmbeddingBase):
         return self.n
 
 
+def _curvature_of(manifold):
+    """The curvature tensor of a Universal factor (it receives a gradient), None for every other manifold."""
+    get_c = getattr(manifold, 'get_c', None)
+    return None if get_c is None else get_c()
+
+
 class _FusedObjective(torch.autograd.Function):
-    """loss(targets(pairs), sum_f softplus(s_f) dist_f^2(pairs)) with the gradients w.r.t. every x_f and s_f
-    produced in the forward pass; backward only rescales them."""
+    """loss(targets(pairs), sum_f sp_f * dist_f^2(pairs)), sp_f = softplus(s_f) (ManifoldEmbedding) or 1
+    (products.Embedding), with the gradients w.r.t. every x_f, s_f and Universal curvature c_f produced in the
+    forward pass; backward only rescales them.  params = (*xs, *scales [if has_scales], *curvatures-or-None)."""
 
     @staticmethod
-    def forward(ctx, pairs, targets, loss_spec, manifolds, n_factors, *params):
-        xs, scales = params[:n_factors], params[n_factors:]
-        sps = [float(softplus(s.detach())) for s in scales]
+    def forward(ctx, pairs, targets, loss_spec, manifolds, n_factors, has_scales, *params):
+        F = n_factors
+        xs = params[:F]
+        scales = params[F:2 * F] if has_scales else ()
+        cs = params[len(params) - F:]
+        sps = [float(softplus(s.detach())) for s in scales] if has_scales else [1.0] * F
         grads = [torch.zeros_like(x, memory_format=torch.contiguous_format) for x in xs]
-        if n_factors == 1:
+        c_needs = ctx.needs_input_grad[len(ctx.needs_input_grad) - F:]
+        cgrads = [torch.zeros(1, dtype=torch.float64, device=xs[0].device) if (c is not None and need) else None
+                  for c, need in zip(cs, c_needs)]
+        cvals = [None if c is None else c.detach() for c in cs]
+        if F == 1:
             acc, _ = _ops.pairs_loss_fused(manifolds[0].spec, xs[0].detach(), pairs, targets, loss_spec, sps[0],
-                                           grads[0])
+                                           grads[0], c=cvals[0], c_grad=cgrads[0])
         else:
-            d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs) for m, x in zip(manifolds, xs)]
+            d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs, c=c) for m, x, c in zip(manifolds, xs, cvals)]
             acc, g = _ops.product_loss(d2s, sps, targets, loss_spec)
-            for m, x, gx, sp in zip(manifolds, xs, grads, sps):
-                _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, gx, gx, coef=sp)
-        dscale = [acc[1 + f] * torch.sigmoid(scales[f].detach().double()) for f in range(n_factors)]
-        ctx.save_for_backward(*grads, *dscale)
-        ctx.n_factors = n_factors
+            for m, x, gx, sp, c, cg in zip(manifolds, xs, grads, sps, cvals, cgrads):
+                _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, gx, gx, coef=sp, c=c, c_grad=cg)
+        dscale = [acc[1 + f] * torch.sigmoid(scales[f].detach().double()) for f in range(len(scales))]
+        ctx.save_for_backward(*grads, *dscale, *[cg for cg in cgrads if cg is not None])
+        ctx.n_factors, ctx.n_scales = F, len(scales)
         ctx.scale_dtypes = [s.dtype for s in scales]
+        ctx.c_meta = [None if cg is None else (c.dtype, c.shape) for c, cg in zip(cs, cgrads)]
         return acc[0].to(xs[0].dtype)
 
     @staticmethod
     def backward(ctx, upstream):
         saved = ctx.saved_tensors
-        F = ctx.n_factors
+        F, S = ctx.n_factors, ctx.n_scales
         gx = [g * upstream for g in saved[:F]]
-        gs = [(d * upstream).to(dt) for d, dt in zip(saved[F:], ctx.scale_dtypes)]
-        return (None, None, None, None, None, *gx, *gs)
+        gs = [(d * upstream).to(dt) for d, dt in zip(saved[F:F + S], ctx.scale_dtypes)]
+        rest = list(saved[F + S:])
+        gc = [None if meta is None else (rest.pop(0) * upstream).to(meta[0]).reshape(meta[1]) for meta in ctx.c_meta]
+        return (None, None, None, None, None, None, *gx, *gs, *gc)
 
 
 class BatchedObjective(torch.nn.Module):
@@ -150,7 +169,7 @@ class BatchedObjective(torch.nn.Module):
         emb = self.embedding
         spec_fn = getattr(self.objective_fn, 'loss_spec', None)
         loss_spec = spec_fn(**kwargs) if (spec_fn is not None and not args) else None
-        fusable = (loss_spec is not None and isinstance(emb, ManifoldEmbedding)
+        fusable = (loss_spec is not None and getattr(emb, 'fused_pair_kernels', False)
                    and getattr(self.dataset, 'pdists', None) is not None
                    and self.dataset.pdists.device == emb.device and self.dataset.pdists.dtype == emb.xs[0].dtype)
         if not fusable:
@@ -167,8 +186,12 @@ class BatchedObjective(torch.nn.Module):
             full_k0 = pairs.k0
             pairs = pairs.slice(*self.shard)
             lo = pairs.k0 - full_k0
-        if emb.n_components == 1:
+        n_factors = len(emb.xs)
+        if n_factors == 1:
             targets = _ops.TargetSpec.dense(self.dataset.pdists)  # target gather fused into the pair kernel
         else:
             targets = _ops.TargetSpec.vector(self.dataset[indices][lo:lo + pairs.P])
-        return _FusedObjective.apply(pairs, targets, loss_spec, emb.manifolds, emb.n_components, *emb.xs, *emb.scales)
+        scales = tuple(getattr(emb, 'scales', ()))  # products.Embedding has none: plain sum of squared distances
+        curvatures = [_curvature_of(m) for m in emb.manifolds]
+        return _FusedObjective.apply(pairs, targets, loss_spec, list(emb.manifolds), n_factors, bool(scales), *emb.xs,
+                                     *scales, *curvatures)

@@ -415,6 +415,129 @@ class EuclideanOracle:
 
 
 # ----------------------------------------------------------------------------
+# Universal: kappa-stereographic model (manifolds/universal.py over manifolds/impl/math.py)
+# ----------------------------------------------------------------------------
+MIN_NORM = 1e-15  # impl/math.py:15
+BALL_EPS = {torch.float32: 4e-3, torch.float64: 1e-5}  # impl/math.py:16
+
+
+class _Artanh(torch.autograd.Function):  # impl/math.py:25-40
+    @staticmethod
+    def forward(ctx, x):
+        x = x.clamp(-1 + 1e-15, 1 - 1e-15)
+        ctx.save_for_backward(x)
+        xd = x.double()
+        return ((1 + xd).log() - (1 - xd).log()).mul(0.5).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return g / (1 - x**2)
+
+
+class UniversalOracle:
+    """`c` is the tensor Universal.get_c() returns (shape (1,), may require grad)."""
+
+    def __init__(self, n, c):
+        self.n, self.c = n, c
+
+    # impl/math.py:73-99 (scalar c: one branch)
+    def _tan(self, x):
+        return x.clamp(-15, 15).tanh() if self.c.item() > 0 else torch.tan(x)
+
+    def _arctan(self, x):
+        return _Artanh.apply(x) if self.c.item() > 0 else torch.atan(x)
+
+    def _lambda(self, x, c=None):  # impl/math.py:187-190 (keepdim=True)
+        c = self.c if c is None else c
+        return 2 / (1 - c * x.pow(2).sum(-1, keepdim=True)).clamp_min(MIN_NORM)
+
+    def _madd(self, x, y):  # impl/math.py:326-345
+        c = self.c
+        x2 = x.pow(2).sum(-1, keepdim=True)
+        y2 = y.pow(2).sum(-1, keepdim=True)
+        xy = (x * y).sum(-1, keepdim=True)
+        num = (1 + 2 * c * xy + c * y2) * x + (1 - c * x2) * y
+        den = 1 + 2 * c * xy + c**2 * x2 * y2
+        return num / den.clamp_min(MIN_NORM)
+
+    def projx(self, x):  # impl/math.py:142-156 (what Universal.projx(inplace=True) leaves in x)
+        if self.c.item() <= 0:
+            return x
+        norm = x.norm(dim=-1, keepdim=True, p=2).clamp_min(MIN_NORM)
+        maxnorm = (1 - BALL_EPS[x.dtype]) / self.c.abs().sqrt()
+        return torch.where(norm > maxnorm, x / norm * maxnorm, x)
+
+    def dist2(self, x, y):  # universal.py:76-81 (squared=True) + impl/math.py:567-572
+        sc = self.c.abs()**0.5
+        d = self._arctan(sc * self._madd(-x, y).norm(dim=-1, p=2)) * 2 / sc
+        d = d.pow(2)
+        return _st_clamp_(d, EPS)
+
+    def dist(self, x, y):  # squared=False: the value clamp acts on d itself
+        sc = self.c.abs()**0.5
+        d = self._arctan(sc * self._madd(-x, y).norm(dim=-1, p=2)) * 2 / sc
+        return _st_clamp_(d, EPS)
+
+    def pdist2(self, x):  # base.py:59-63
+        i, j = torch.triu_indices(x.shape[0], x.shape[0], 1)
+        return self.dist2(x[i], x[j])
+
+    def proju(self, x, u):  # universal.py:50-51
+        return u
+
+    def egrad2rgrad(self, x, g):  # impl/math.py:1452-1453
+        return g / self._lambda(x)**2
+
+    def norm(self, x, u):  # universal.py:44-48: math.norm is called WITHOUT c => c = 1.0; keepdim=True
+        return self._lambda(x, c=1.0) * u.norm(dim=-1, keepdim=True, p=2)
+
+    def inner(self, x, u, v):  # impl/math.py:225-228 with keepdim=False: the (N, 1) conformal factor (keepdim=True
+        # is hard-coded there) broadcasts against the (N,) dot products into an (N, N) matrix -- kept as is
+        return self._lambda(x)**2 * (u * v).sum(-1)
+
+    def exp(self, x, u):  # universal.py:62-67, impl/math.py:720-727
+        sc = self.c.abs()**0.5
+        un = u.norm(dim=-1, p=2, keepdim=True).clamp_min(MIN_NORM)
+        second = self._tan(sc / 2 * self._lambda(x) * un) * u / (sc * un)
+        return self.projx(self._madd(x, second))
+
+    def retr(self, x, u):  # universal.py:69-70
+        return self.projx(x + u)
+
+    def log(self, x, y):  # impl/math.py:835-841
+        sub = self._madd(-x, y)
+        sn = sub.norm(dim=-1, p=2, keepdim=True).clamp_min(MIN_NORM)
+        sc = self.c.abs()**0.5
+        return 2 / sc / self._lambda(x) * self._arctan(sc * sn) * sub / sn
+
+    def transp(self, x, y, w):  # impl/math.py:1359-1362 with the gyration of :1282-1298 (u = y, v = -x)
+        c = self.c
+        u, v = y, -x
+        u2 = u.pow(2).sum(-1, keepdim=True)
+        v2 = v.pow(2).sum(-1, keepdim=True)
+        uv = (u * v).sum(-1, keepdim=True)
+        uw = (u * w).sum(-1, keepdim=True)
+        vw = (v * w).sum(-1, keepdim=True)
+        c2 = c**2
+        a = -c2 * uw * v2 + c * vw + 2 * c2 * uv * vw
+        b = -c2 * vw * u2 - c * uw
+        d = 1 + 2 * c * uv + c2 * u2 * v2
+        gyr = w + 2 * (a * u + b * v) / d.clamp_min(MIN_NORM)
+        return gyr * self._lambda(x) / self._lambda(y)
+
+    def rand(self, n_points, ir=1e-2, dtype=torch.float64, generator=None):  # universal.py:86-88
+        x = torch.empty(n_points, self.n, dtype=dtype).uniform_(-ir, ir, generator=generator)
+        return self.projx(x)
+
+
+def universal_get_c(c_param, c_min=0.001, sign=None):  # universal.py:28-32
+    if sign:
+        return sign * (c_min + torch.nn.functional.softplus(c_param))
+    return c_param.sign() * c_min + c_param
+
+
+# ----------------------------------------------------------------------------
 # Grassmann (manifolds/grassmann.py)
 # ----------------------------------------------------------------------------
 def singular_values_2x2_closed(a, eps=1e-8):  # fast.py:138-159

@@ -249,7 +249,145 @@ def make_engine_runs():
     return out
 
 
+UNIVERSAL_CASES = {
+    # name: (n, ctor kwargs, init radius): hyperbolic (c > 0), spherical (c < 0), sign-fixed softplus parametrisation
+    'universal5_pos': (5, dict(c_init=0.5), 0.5),
+    'universal5_neg': (5, dict(c_init=-0.7), 0.5),
+    'universal3_fixed_sign': (3, dict(c_init=-0.3, keep_sign_fixed=True), 0.4),
+    'universal4_default_init': (4, dict(), 1e-2),
+}
+
+
+def make_universal(name, dtype, seed):
+    """Universal (kappa-stereographic) manifold, graphembed/manifolds/universal.py: distances and gradients w.r.t.
+    the points AND the curvature parameter, point ops, optimizer trajectories, and a products.Embedding training
+    run with a curvature optimizer."""
+    from graphembed.manifolds import Universal
+    n, kw, ir = UNIVERSAL_CASES[name]
+    torch.set_default_dtype(dtype)
+    torch.manual_seed(seed)
+    man = Universal(n, **kw)
+    with torch.no_grad():  # rand() -> projx(inplace) set_()s a tensor that depends on c (not differentiable today)
+        x = man.rand(N, ir=ir).contiguous()
+        y = man.rand(N, ir=ir).contiguous()
+    out = dict(x=x.numpy(), y=y.numpy(), c_param=man.c.detach().numpy(), c=man.get_c().detach().numpy(),
+               c_min=np.array(man.c_min), sign=np.array(0 if man.sign is None else man.sign))
+    w = torch.linspace(0.5, 1.5, N, dtype=dtype)
+    xr, yr = x.clone().requires_grad_(), y.clone().requires_grad_()
+    d2 = man.dist(xr, yr, squared=True)
+    (d2 * w).sum().backward()
+    out.update(dist2=d2.detach().numpy(), w=w.numpy(), gx=xr.grad.numpy(), gy=yr.grad.numpy(),
+               gc=man.c.grad.clone().numpy())
+    man.c.grad = None
+    with torch.no_grad():
+        out['dist'] = man.dist(x, y).numpy()
+    P = N * (N - 1) // 2
+    g = torch.rand(P, dtype=dtype) * 0.9 + 0.1
+    out['targets'] = g.numpy()
+    for lname, fn, kwargs in (('quot', QuotientLoss(), dict(epoch=3, alpha=1.7)),
+                              ('quot_l1', QuotientLoss(inc_l2=False), dict(epoch=3, alpha=1.7)),
+                              ('stress', StressLoss(), dict())):
+        xr = x.clone().requires_grad_()
+        pd2 = man.pdist(xr, squared=True)
+        loss = fn(g, 0.9 * pd2, **kwargs)
+        loss.backward()
+        out['pdist2'] = pd2.detach().numpy()
+        out[f'loss_{lname}'] = np.array(loss.item())
+        out[f'grad_{lname}'] = xr.grad.numpy()
+        out[f'gradc_{lname}'] = man.c.grad.clone().numpy()
+        man.c.grad = None
+    with torch.no_grad():
+        u = (torch.randn_like(x) * 0.3).contiguous()
+        v = (torch.randn_like(x) * 0.2).contiguous()
+        eg = torch.randn_like(x)
+        far = (torch.randn(N, n) * 3.0).contiguous()  # outside the ball for c > 0
+        far_proj = far.clone()
+        man.projx(far_proj, inplace=True)
+        out.update(u=u.numpy(), v=v.numpy(), eg=eg.numpy(), far=far.numpy(), projx=far_proj.numpy(),
+                   exp=man.exp(x, u).numpy(), retr=man.retr(x, u).numpy(), log=man.log(x, y).numpy(),
+                   proju=man.proju(x, eg.clone()).numpy(), egrad2rgrad=man.egrad2rgrad(x, eg.clone()).numpy(),
+                   transp=man.transp(x, y, u).numpy(), inner=man.inner(x, u, v).numpy(),
+                   norm2=man.norm(x, u, squared=True).numpy())
+        grads = [torch.randn_like(x), torch.zeros_like(x), torch.randn_like(x)]
+        out['opt_grads'] = np.stack([t.numpy() for t in grads])
+        for oname, mk in (('radam_clip', lambda ps: RiemannianAdam(ps, lr=0.05, max_grad_norm=1.5)),
+                          ('radam_exact', lambda ps: RiemannianAdam(ps, lr=0.05, exact=True)),
+                          ('rsgd_exact_clip', lambda ps: RiemannianSGD(ps, lr=0.05, max_grad_norm=0.5, exact=True)),
+                          ('rsgd_momentum', lambda ps: RiemannianSGD(ps, lr=0.05, momentum=0.9, dampening=0.1))):
+            p = ManifoldParameter(x.clone(), manifold=man)
+            opt = mk([p])
+            traj = []
+            for gk in grads:
+                p.grad = gk.clone()
+                opt.step()
+                traj.append(p.data.clone().numpy())
+            out[f'{oname}_x'] = np.stack(traj)
+            st = opt.state[p]
+            for key in ('exp_avg', 'exp_avg_sq', 'momentum_buffer'):
+                if key in st:
+                    out[f'{oname}_{key}'] = st[key].detach().numpy()
+    return out
+
+
+def make_universal_training_run():
+    """products.Embedding (two Universal factors, one hyperbolic one spherical) on a 31-node tree, fp64:
+    QuotientLoss through the reference's BatchedObjective, RAdam on the points + SGD on the curvatures, stabilize()
+    after every step; 4 steps (full batch / node mini-batch alternating)."""
+    import networkx as nx
+    from scipy.sparse.csgraph import shortest_path
+    from graphembed.products import Embedding
+    torch.set_default_dtype(torch.float64)
+    g = nx.balanced_tree(2, 4)
+    n = g.number_of_nodes()
+    hops = shortest_path(nx.to_scipy_sparse_array(g), unweighted=True)
+    cond = torch.tensor(hops[np.triu_indices(n, 1)])
+    out = dict(edges=np.array(g.edges()), hops_condensed=cond.numpy())
+    torch.manual_seed(42)
+    ds = GraphDataset(cond.clone())
+    with torch.no_grad():
+        emb = Embedding(n, [3, 2], c_init=0.4)
+        emb.manifolds[1].c.fill_(-0.6)
+        for x in emb.xs:  # spread the points (the default ir=1e-2 start is degenerate for 4 steps)
+            x.mul_(30.0)
+            x.proj_()
+    out['c0'] = np.array([m.c.item() for m in emb.manifolds])
+    for i, x in enumerate(emb.xs):
+        out[f'x0_{i}'] = x.data.clone().numpy()
+    opt = RiemannianAdam(emb.xs, lr=0.02, max_grad_norm=100, exact=True)
+    copt = torch.optim.SGD(list(emb.curvature_params), lr=1e-4)
+    bobj = BatchedObjective(QuotientLoss(), ds, emb)
+    perm = torch.randperm(n)
+    out['perm'] = perm.numpy()
+    losses, cs, cgrads = [], [], []
+    for step in range(4):
+        idx = perm if step % 2 == 0 else perm[:20]
+        loss = bobj(idx, alpha=1.0, epoch=step + 1).sum()
+        opt.zero_grad()
+        copt.zero_grad()
+        loss.backward()
+        if step == 0:
+            for i, x in enumerate(emb.xs):
+                out[f'grad0_{i}'] = x.grad.clone().numpy()
+        cgrads.append([m.c.grad.item() for m in emb.manifolds])
+        with torch.no_grad():
+            opt.step()
+        copt.step()
+        emb.stabilize()
+        losses.append(loss.item())
+        cs.append([m.c.item() for m in emb.manifolds])
+    out.update(losses=np.array(losses), cs=np.array(cs), cgrads=np.array(cgrads))
+    for i, x in enumerate(emb.xs):
+        out[f'xT_{i}'] = x.data.clone().numpy()
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'universal':  # SURVEY 8f-3 fixtures only
+        for name in UNIVERSAL_CASES:
+            for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
+                np.savez_compressed(os.path.join(HERE, f'{name}_{tag}.npz'), **make_universal(name, dtype, seed=7))
+        np.savez_compressed(os.path.join(HERE, 'universal_training_run_f64.npz'), **make_universal_training_run())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'new':  # only the fixtures added after the first batch
         for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
             np.savez_compressed(os.path.join(HERE, f'objectives_{tag}.npz'), **make_objectives(dtype))
@@ -262,6 +400,10 @@ def main():
     for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
         np.savez_compressed(os.path.join(HERE, f'objectives_{tag}.npz'), **make_objectives(dtype))
     np.savez_compressed(os.path.join(HERE, 'engine_runs_f64.npz'), **make_engine_runs())
+    for name in UNIVERSAL_CASES:
+        for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
+            np.savez_compressed(os.path.join(HERE, f'{name}_{tag}.npz'), **make_universal(name, dtype, seed=7))
+    np.savez_compressed(os.path.join(HERE, 'universal_training_run_f64.npz'), **make_universal_training_run())
     print('wrote', len(os.listdir(HERE)) - 1, 'fixtures to', HERE)
 
 

@@ -59,9 +59,9 @@ static int spd_t(int kind, int n, unsigned flags, double wmin, double wmax, cons
 
 template <typename T, int KIND>
 static void vec_rows(int n, const T* x, const T* y, long P, T* d2, T* gx, T* gy) {
-  VecMan<T, KIND> op{(T)1e-8, (T)(1.0 - 1e-16)};
+  VecMan<T, KIND> op{(T)1e-8, (T)(1.0 - 1e-16), nullptr};
   for (long k = 0; k < P; ++k) {
-    T c;
+    VecCoef<T> c{};
     d2[k] = op.value(x + k * n, y + k * n, n, c);
     if (gx)
       for (int e = 0; e < n; ++e) op.grad_elem(e, x[k * n + e], y[k * n + e], c, gx[k * n + e], gy[k * n + e]);
@@ -111,6 +111,28 @@ static int any_t(int kind, int n, int p, unsigned flags, double wmin, double wma
   }
   return -1;
 }
+
+// Universal (kappa-stereographic): curvature passed by value; gc[k] = d(d2_k)/dc
+template <typename T>
+static void universal_rows(int n, double c, double wmin, const T* x, const T* y, long P, T* d2, T* gx, T* gy, T* gc) {
+  T cc = (T)c;
+  VecMan<T, VEC_UNIVERSAL> op{(T)wmin, (T)(1.0 - 1e-16), &cc};
+  for (long k = 0; k < P; ++k) {
+    VecCoef<T> co{};
+    d2[k] = op.value(x + k * n, y + k * n, n, co);
+    if (gx)
+      for (int e = 0; e < n; ++e) op.grad_elem(e, x[k * n + e], y[k * n + e], co, gx[k * n + e], gy[k * n + e]);
+    if (gc) gc[k] = co.dc;
+  }
+}
+extern "C" int hc_universal_pairs(int dtype, int n, double c, double wmin, const void* x, const void* y, long P,
+                                  void* d2, void* gx, void* gy, void* gc) {
+  if (dtype == GM_F32) universal_rows<float>(n, c, wmin, (const float*)x, (const float*)y, P, (float*)d2, (float*)gx, (float*)gy, (float*)gc);
+  else universal_rows<double>(n, c, wmin, (const double*)x, (const double*)y, P, (double*)d2, (double*)gx, (double*)gy, (double*)gc);
+  return 0;
+}
+static double g_universal_c = 1.0;  // hc_point(kind = GM_UNIVERSAL) reads the curvature from here
+extern "C" void hc_set_universal_c(double c) { g_universal_c = c; }
 
 extern "C" int hc_pairs(int kind, int dtype, int n, int p, unsigned flags, double wmin, double wmax, const void* x,
                         const void* y, long P, void* d2, void* gx, void* gy) {
@@ -207,6 +229,11 @@ static int pt_any(int kind, int n, int p, unsigned flags, double wmin, double wm
     case GM_LORENTZ: { LorentzPt<T, 64> m{n, eps}; return pt_rows<decltype(m), T>(m, a); }
     case GM_SPHERE: { SpherePt<T, 64> m{n, eps}; return pt_rows<decltype(m), T>(m, a); }
     case GM_EUCLIDEAN: { EuclideanPt<T, 64> m{n, eps}; return pt_rows<decltype(m), T>(m, a); }
+    case GM_UNIVERSAL: {
+      T cc = (T)g_universal_c;
+      UniversalPt<T, 64> m{n, eps, &cc, (T)(sizeof(T) == 4 ? 4e-3 : 1e-5)};
+      return pt_rows<decltype(m), T>(m, a);
+    }
     case GM_GRASSMANN:
       switch (p) {
         case 1: { GrassmannPt<T, 1, 16> m{n, eps, retr_qr}; return pt_rows<decltype(m), T>(m, a); }

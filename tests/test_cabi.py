@@ -220,3 +220,28 @@ lr:
     assert type(opt).__name__ == 'RiemannianAdam' and opt.defaults['lr'] == 0.01 and opt.defaults['max_grad_norm'] == 100
     with pytest.raises(RuntimeError, match='CUDA'):  # the closure reaches the (GPU-only) initialiser
         c['embedding'](5)
+
+
+def test_universal_has_no_cpu_path_and_mirrors_the_reference_surface():
+    """the Universal manifold / products.Embedding classes exist under the reference's module paths,
+    construct without a GPU, and refuse to compute on CPU tensors (no fallback)."""
+    from graphembed import _lib as L
+    from graphembed.manifolds import Universal
+    from graphembed.products import Embedding, TrainingEngine  # noqa: F401
+    man = Universal(4, c_init=-0.3, keep_sign_fixed=True)
+    assert man.ndim == 1 and man.dim == 4 and str(man) == 'Universal 4-dimensional manifold'
+    assert abs(man.get_c().item() + (0.001 + torch.nn.functional.softplus(torch.tensor(-0.3)).item())) < 1e-6
+    assert abs(man.get_K().item() + man.get_c().item()) < 1e-12 and man.get_R().item() > 0
+    assert [n for n, _ in man.named_parameters()] == ['c']
+    x = torch.zeros(3, 4)
+    assert man.proju(x, x) is x
+    with pytest.raises(RuntimeError):
+        man.dist(x, x)
+    with pytest.raises(RuntimeError):
+        man.exp(x, x)
+    with pytest.raises(ValueError):
+        TrainingEngine(stabilize_every_epochs=2)
+    m = L.Manifold(kind=L.GM_UNIVERSAL, dtype=L.GM_F32, n=4, p=0, flags=0, reserved=0, wmin=1e-8, wmax=1e8)
+    assert L.lib().gm_supported(ctypes.byref(m)) == 0  # c_dev missing
+    m.c_dev = 16
+    assert L.lib().gm_supported(ctypes.byref(m)) == 1

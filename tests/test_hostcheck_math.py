@@ -60,3 +60,92 @@ def test_pair_math_matches_oracle(hc, name, tag):
     assert rel_err(d2, g['dist2']) < t
     assert rel_err(fix(gx * w), fix(g['gx'])) < t * 10
     assert rel_err(fix(gy * w), fix(g['gy'])) < t * 10
+
+
+# ---- Universal (kappa-stereographic) manifold, SURVEY 8f-3: kernel arithmetic vs golden vectors of the reference --------
+from helpers_universal import OPTS as U_OPTS, UNIVERSAL_CASES, check_curvature_grad, tol_u  # noqa: E402
+
+_vp = ctypes.c_void_p
+
+
+def _p(t):
+    return None if t is None else _vp(t.data_ptr())
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('name', sorted(UNIVERSAL_CASES))
+def test_universal_pair_math(hc, name, tag):
+    g = load_golden(name, tag)
+    x, y = g['x'].contiguous(), g['y'].contiguous()
+    P, n = x.shape
+    d2, gc = torch.empty(P, dtype=x.dtype), torch.empty(P, dtype=x.dtype)
+    gx, gy = torch.empty_like(x), torch.empty_like(y)
+    c = float(g['c'].item())
+    hc.hc_universal_pairs(0 if x.dtype == torch.float32 else 1, n, ctypes.c_double(c), ctypes.c_double(1e-8), _p(x),
+                          _p(y), ctypes.c_long(P), _p(d2), _p(gx), _p(gy), _p(gc))
+    t = tol_u(tag, name)
+    w = g['w']
+    assert rel_err(d2, g['dist2']) < t
+    assert rel_err(gx * w[:, None], g['gx']) < t * 10
+    assert rel_err(gy * w[:, None], g['gy']) < t * 10
+    sign = int(g['sign'])
+    chain = 1.0 if not sign else sign * torch.sigmoid(g['c_param'].double()).item()  # d get_c / d c_param
+    check_curvature_grad((gc.double() * w.double()).sum().reshape(1) * chain, g, name, tag, 'gc', t * 10)
+    # non-squared distance: value floor EPS on d  <=>  EPS^2 on d^2
+    hc.hc_universal_pairs(0 if x.dtype == torch.float32 else 1, n, ctypes.c_double(c), ctypes.c_double(1e-16), _p(x),
+                          _p(y), ctypes.c_long(P), _p(d2), None, None, None)
+    assert rel_err(d2.sqrt(), g['dist']) < t
+
+
+def _hc_point(hc, g, op, x, u=None, v=None, scalar=False, opt=None, b1=None, b2=None):
+    from graphembed import _lib as L
+    n = x.shape[-1]
+    out = torch.empty(x.shape[0] if scalar else x.shape, dtype=x.dtype)
+    hc.hc_set_universal_c(ctypes.c_double(float(g['c'].item())))
+    rc = hc.hc_point(L.GM_UNIVERSAL, 0 if x.dtype == torch.float32 else 1, n, 0, 0, ctypes.c_double(1e-8),
+                     ctypes.c_double(1e8), 0, op, None if opt is None else ctypes.byref(opt), _p(x), _p(u), _p(v),
+                     _p(out), _p(b1), _p(b2), ctypes.c_long(x.shape[0]))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('name', sorted(UNIVERSAL_CASES))
+def test_universal_point_ops(hc, name, tag):
+    from graphembed import _lib as L
+    g = load_golden(name, tag)
+    x, y, u, v, eg, far = (g[k].contiguous() for k in ('x', 'y', 'u', 'v', 'eg', 'far'))
+    t = 2e-4 if tag == 'f32' else 1e-10
+    assert rel_err(_hc_point(hc, g, L.GM_OP_EXP, x, u), g['exp']) < t
+    assert rel_err(_hc_point(hc, g, L.GM_OP_RETR, x, u), g['retr']) < t
+    assert rel_err(_hc_point(hc, g, L.GM_OP_LOG, x, y), g['log']) < t * 50
+    assert rel_err(_hc_point(hc, g, L.GM_OP_EGRAD2RGRAD, x, eg), g['egrad2rgrad']) < t
+    assert rel_err(_hc_point(hc, g, L.GM_OP_TRANSP, x, y, u), g['transp']) < t
+    assert rel_err(_hc_point(hc, g, L.GM_OP_NORM2, x, u, scalar=True), g['norm2'].reshape(-1)) < t
+    assert rel_err(_hc_point(hc, g, L.GM_OP_INNER, x, u, v, scalar=True), g['inner'].diagonal()) < t
+    assert rel_err(_hc_point(hc, g, L.GM_OP_PROJX, far), g['projx']) < t
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+@pytest.mark.parametrize('oname', sorted(U_OPTS))
+@pytest.mark.parametrize('name', sorted(UNIVERSAL_CASES))
+def test_universal_optimizer_update(hc, name, oname, tag):
+    from graphembed import _lib as L
+    g = load_golden(name, tag)
+    kind, kw = U_OPTS[oname]
+    x = g['x'].clone().contiguous()
+    radam = kind == 'radam'
+    b1 = torch.zeros_like(x) if (radam or kw.get('momentum', 0) > 0) else None
+    b2 = torch.zeros_like(x) if radam else None
+    t = 1e-9 if tag == 'f64' else 2e-4
+    for k in range(3):
+        opt = L.Optim(kind=L.GM_OPT_RADAM if radam else L.GM_OPT_RSGD, exact=int(kw.get('exact', False)),
+                      has_clip=int('max_grad_norm' in kw), step=k + 1, has_momentum=int(kw.get('momentum', 0) > 0),
+                      first_step=int(k == 0), grassmann_retr_qr=0, reserved=0, lr=kw['lr'], beta1=0.9, beta2=0.999,
+                      momentum=kw.get('momentum', 0.0), dampening=kw.get('dampening', 0.0),
+                      max_grad_norm=kw.get('max_grad_norm', 0.0), eps=1e-8)
+        _hc_point(hc, g, -1, x, g['opt_grads'][k].contiguous(), opt=opt, b1=b1, b2=b2)
+        assert rel_err(x, g[f'{oname}_x'][k]) < t
+    for key, buf in (('exp_avg', b1 if radam else None), ('exp_avg_sq', b2), ('momentum_buffer', None if radam else b1)):
+        if f'{oname}_{key}' in g and buf is not None:
+            assert rel_err(buf, g[f'{oname}_{key}']) < t
