@@ -290,6 +290,25 @@ int gm_gather_levels(int32_t level_bytes, const void* levels, int32_t N, const i
 int gm_expand_groups(const int32_t* group_row, const int64_t* offsets, int32_t G, int32_t* out_i, int64_t P,
                      gm_stream_t stream);
 
+/* ---- ranking metrics (evaluation) ------------------------------------------------------------------------------
+ * FastPrecision on the GPU (graphembed/pyx/impl/precision.cpp:249-291 mean average precision, :321-446 per-layer F1
+ * scores; bound to Python in graphembed/pyx/precision.pyx:48-127).  For every shortest-path-tree root u in
+ * [root_lo, root_hi): sort the other nodes by manifold distance from u (row u of the condensed `mpdists`, N(N-1)/2
+ * values of `dtype`, squareform order) and compare that order with the BFS layering `levels_u8` (full N x N uint8 hop
+ * matrix from gm_bfs_multi_source, connected graph with < 255 layers).  Everything is ACCUMULATED into caller-zeroed
+ * device arrays of length n_layers - 1 (n_layers = max hop count + 1, precision.cpp:191-199):
+ *   f1_m1 / f1_m2 / f1_cnt : sum f1, sum f1^2, count per layer over all (root, node) with
+ *                            min_degree <= degree(root) <= max_degree          -- LayerMeanF1Scores (:397-420)
+ *   af_m1 / af_m2 / af_cnt : the same after averaging within each root first   -- LayerMeanAverageF1Scores (:422-446)
+ *   ap_sum[0]              : sum over roots of the average precision            -- MeanAveragePrecision (:268-303)
+ * means = m1 / cnt, "stds" = m2 / cnt - means^2 as the reference reports them.  A rank of a multi-GPU job passes its
+ * slice of roots and the accumulators are summed across ranks.  N <= 32768 (fp32) / 16384 (fp64): one root's sort
+ * lives in one SM's shared memory. */
+int gm_rank_metrics(int32_t dtype, const void* mpdists, const void* levels_u8, int32_t N, int32_t root_lo,
+                    int32_t root_hi, int32_t min_degree, int32_t max_degree, int32_t n_layers, double* f1_m1,
+                    double* f1_m2, int64_t* f1_cnt, double* af_m1, double* af_m2, int64_t* af_cnt, double* ap_sum,
+                    gm_stream_t stream);
+
 /* ---- introspection ------------------------------------------------------------------------------------------- */
 const char* gm_version(void);
 /* 1 if (kind, n, p, dtype, flags) has a compiled kernel */

@@ -103,6 +103,8 @@ _PROTOTYPES = {
     'gm_levels_to_dense_targets': (ctypes.c_int, [_i32, _vp, _i32, _dbl, _i32, _vp, _vp]),
     'gm_gather_levels': (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     'gm_expand_groups': (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _vp]),
+    'gm_rank_metrics': (ctypes.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

@@ -381,7 +381,36 @@ def make_universal_training_run():
     return out
 
 
+def make_precision():
+    """Ranking metrics: the reference's own pure-Python mean average precision (graphembed/metrics.py:61-96, the
+    regression anchor its tests hold for FastPrecision, tests/test_metrics.py:14-23) on Erdos-Renyi graphs with random
+    fp32 distances -- exactly the reference test's inputs -- plus the graph distances for the F1 == 1 known answer."""
+    import networkx as nx
+    from scipy.sparse.csgraph import shortest_path
+    from scipy.spatial.distance import squareform
+    from graphembed.metrics import py_mean_average_precision
+    out = {}
+    rng = np.random.RandomState(5)
+    for tag, (n, p) in dict(a=(50, 0.1), b=(100, 0.1), c=(100, 0.5), d=(300, 0.02)).items():
+        g = nx.erdos_renyi_graph(n, p, seed=int(rng.randint(1 << 30)))
+        comp = max(nx.connected_components(g), key=len)  # tests/conftest.py rand_graph keeps the largest component
+        g = nx.convert_node_labels_to_integers(g.subgraph(comp).copy())
+        n = g.number_of_nodes()
+        pd = rng.rand(n * (n - 1) // 2).astype(np.float32)
+        out[f'{tag}_edges'] = np.array(g.edges())
+        out[f'{tag}_n'] = np.array(n)
+        out[f'{tag}_pdists'] = pd
+        out[f'{tag}_map'] = np.array(py_mean_average_precision(squareform(pd), g))
+        hops = shortest_path(nx.to_scipy_sparse_array(g), unweighted=True)
+        out[f'{tag}_hops'] = hops[np.triu_indices(n, 1)]
+        out[f'{tag}_map_hops'] = np.array(py_mean_average_precision(hops + 1e-9 * rng.rand(n, n), g))
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'precision':  # SURVEY 8f-4 fixture only
+        np.savez_compressed(os.path.join(HERE, 'precision_map.npz'), **make_precision())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'universal':  # SURVEY 8f-3 fixtures only
         for name in UNIVERSAL_CASES:
             for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
@@ -404,6 +433,7 @@ def main():
         for dtype, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
             np.savez_compressed(os.path.join(HERE, f'{name}_{tag}.npz'), **make_universal(name, dtype, seed=7))
     np.savez_compressed(os.path.join(HERE, 'universal_training_run_f64.npz'), **make_universal_training_run())
+    np.savez_compressed(os.path.join(HERE, 'precision_map.npz'), **make_precision())
     print('wrote', len(os.listdir(HERE)) - 1, 'fixtures to', HERE)
 
 

@@ -38,13 +38,13 @@ def tol_u(tag, name=''):
 
 
 def check_curvature_grad(got, g, name, tag, key, t):
-    """d(loss)/dc_param against the reference.  For the default init in fp32 the quantity is pure cancellation noise
-    in the reference itself (d^2 ~ 4|x - y|^2 barely depends on c: the reference's fp32 value is 30 % off its own fp64
-    value), so there both are only required to sit within a factor 2 of the fp64 reference."""
+    """d(loss)/dc_param against the reference.  For the default init in fp32 the quantity is cancellation noise in the
+    reference itself (d^2 ~ 4|x - y|^2 barely depends on c: the reference's fp32 values are 1.5x-3x off its own fp64
+    values, see tests/golden/universal4_default_init_f{32,64}.npz), so there only sign and magnitude (within a factor
+    2 of the reference's fp32 number) are required; the same inputs in fp64 are checked to 1e-10."""
     from helpers import rel_err
     if tag == 'f32' and 'default_init' in name:
-        truth = load_golden(name, 'f64')[key].double()
-        for val in (got.double().cpu().reshape(-1), g[key].double().reshape(-1)):
-            assert (val / truth).item() > 0.5 and (val / truth).item() < 2.0
+        ratio = (got.double().cpu().reshape(-1) / g[key].double().reshape(-1)).item()
+        assert 0.5 < ratio < 2.0
         return
     assert rel_err(got, g[key]) < t
