@@ -249,8 +249,13 @@ class TrainingEngine:
             gpdists = graph_dataset[None].sqrt()
             mpdists = self.embedding.compute_dists(None).sqrt_()
             if self.lazy_metrics:
-                mp_np = mpdists.cpu().numpy()
+                mp_np = None
                 for name, f in self.lazy_metrics.items():
+                    if getattr(f, 'takes_device_tensor', False):  # GPU FastPrecision: no host round trip
+                        self.pending_metric_results.append((epoch, name, f(mpdists)))
+                        continue
+                    if mp_np is None:
+                        mp_np = mpdists.cpu().numpy()
                     self.pending_metric_results.append((epoch, name, f(mp_np)))
             gpdists = gpdists.to(mpdists.device)
             values = {m: float(getattr(metrics_mod, m)(mpdists, gpdists)) for m in self.metrics}

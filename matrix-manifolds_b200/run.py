@@ -7,7 +7,9 @@
 fp64 and everything on the GPU by default (run.py:31-35).  Graph distances come from the BFS kernel
 (graphembed.data.load_graph_pdists, same `.cached_pdists/<graph>/cached_pdists.npy` cache), the targets stay
 resident in HBM whatever the graph size (the reference moves them to the host for N >= 5000, run.py:45), and the
-F1/mAP `FastPrecision` metrics (CPU, Cython) are not part of this package."""
+`Layer_Mean_F1` lazy metric (run.py:83-91) is computed by the GPU FastPrecision (graphembed.pyx, gm_rank_metrics)
+right in the validation step instead of on a CPU thread pool.  `graphembed.products.Embedding` configs (Universal
+factors with a curvature optimizer) select graphembed.products.TrainingEngine as run.py:74-75 does."""
 import argparse
 import logging
 import os
@@ -83,7 +85,7 @@ def main(argv=None):
     if not hasattr(embedding, 'manifolds'):
         raise SystemExit('only graphembed.modules.ManifoldEmbedding is on the B200 hot path')
     if world > 1:  # identical replicas
-        for t in list(embedding.xs) + list(embedding.scales):
+        for t in list(embedding.xs) + list(embedding.curvature_params):
             torch.distributed.broadcast(t.data, src=0)
 
     optimizers, lr_schedulers = [], []
@@ -103,7 +105,23 @@ def main(argv=None):
     training_args.update(config['training_params'])
     if 'min_alpha' in training_args or 'max_alpha' in training_args:
         raise SystemExit('deterministic-annealing training (train_da) is outside the B200 hot path')
-    engine = TrainingEngine(**training_args)
+    engine_cls = TrainingEngine
+    if not hasattr(embedding, 'scales'):  # products.Embedding: stabilise every epoch (run.py:74-75)
+        from graphembed.products import TrainingEngine as engine_cls
+    if g is not None and n_nodes <= 32768 and not g.is_directed():
+        from concurrent.futures import Future
+        from graphembed.pyx import FastPrecision
+        with Timer('constructing FastPrecision', loglevel=logging.INFO):
+            fp = FastPrecision(g, device=torch.device('cuda', local))
+
+        def layer_mean_f1(mpdists):  # same contract as the reference's pool.submit(...): a future of (means, stds)
+            fut = Future()
+            fut.set_result(fp.layer_mean_f1_scores(mpdists))
+            return fut
+
+        layer_mean_f1.takes_device_tensor = True
+        training_args['lazy_metrics'] = {'Layer_Mean_F1': layer_mean_f1}
+    engine = engine_cls(**training_args)
     with Timer('training', loglevel=logging.INFO):
         engine(dataset)
     if pg is not None:

@@ -30,7 +30,10 @@ def test_f1_and_map_vs_oracle_and_reference_fixture(tag, dtype):
                       (fp.layer_mean_f1_scores(pd, min_degree=3, max_degree=8),
                        orc.layer_mean_f1_scores(pd, min_degree=3, max_degree=8))):
         assert len(got[0]) == len(want[0])
-        assert np.allclose(got[0], want[0], rtol=1e-11, atol=0) and np.allclose(got[1], want[1], atol=1e-11)
+        # a layer nobody passes the degree filter on is 0/0 = NaN in the reference too (precision.cpp:415-418)
+        assert np.allclose(got[0], want[0], rtol=1e-11, atol=0, equal_nan=True)
+        assert np.allclose(got[1], want[1], atol=1e-11, equal_nan=True)
+        assert np.array_equal(np.isnan(got[0]), np.isnan(want[0]))
     assert np.array_equal(fp.nodes_per_layer(), orc.nodes_per_layer())
 
 
@@ -65,23 +68,32 @@ def test_multiple_distance_sets_and_root_shards():
 
 
 def test_embedding_distances_on_a_larger_graph():
-    """2000-node preferential-attachment graph, manifold distances from a Lorentz embedding (fp32): GPU vs oracle, and
-    the size limits of the shared-memory sort are reported as GM_EUNSUPPORTED, not silently mis-sorted."""
+    """2000-node preferential-attachment graph: (a) manifold distances of an fp64 Lorentz embedding, (b) 2M pairwise
+    DISTINCT fp32 values (std::sort leaves the order of ties unspecified, so tie-free inputs are what can be compared
+    exactly): GPU vs oracle; and the size limit of the shared-memory sort is reported as GM_EUNSUPPORTED, not silently
+    mis-sorted."""
     import networkx as nx
     from graphembed import _lib as L
     from graphembed.manifolds import Lorentz
     from graphembed.pyx import FastPrecision
-    g = nx.barabasi_albert_graph(2000, 2, seed=1)
+    n = 2000
+    g = nx.barabasi_albert_graph(n, 2, seed=1)
     fp = FastPrecision(g)
+    orc = FastPrecisionOracle(*csr_of(n, np.array(g.edges())))
     torch.manual_seed(0)
     man = Lorentz(6)
-    x = man.rand(2000, out=torch.empty(0, device='cuda'), ir=1.0)
-    pd = man.pdist(x).contiguous()
-    orc = FastPrecisionOracle(*csr_of(2000, np.array(g.edges())))
-    pd_host = pd.cpu().numpy()
-    got, want = fp.layer_mean_f1_scores(pd), orc.layer_mean_f1_scores(pd_host)
-    assert np.allclose(got[0], want[0], rtol=1e-10) and np.allclose(got[1], want[1], atol=1e-10)
-    assert abs(fp.mean_average_precision(pd) - orc.mean_average_precision(pd_host)) < 1e-12
+    x = man.rand(n, out=torch.empty(0, device='cuda', dtype=torch.float64), ir=1.0)
+    pd64 = man.pdist(x).contiguous()
+    P = n * (n - 1) // 2
+    pd32 = ((torch.randperm(P, generator=torch.Generator().manual_seed(1)) + 1).double() / P).float().cuda()
+    assert pd32.unique().numel() == P
+    for pd in (pd64, pd32):
+        pd_host = pd.cpu().numpy()
+        got, want = fp.layer_mean_f1_scores(pd), orc.layer_mean_f1_scores(pd_host)
+        assert np.allclose(got[0], want[0], rtol=1e-10) and np.allclose(got[1], want[1], atol=1e-10)
+        got, want = fp.layer_mean_average_f1_scores(pd), orc.layer_mean_average_f1_scores(pd_host)
+        assert np.allclose(got[0], want[0], rtol=1e-10) and np.allclose(got[1], want[1], atol=1e-10)
+        assert abs(fp.mean_average_precision(pd) - orc.mean_average_precision(pd_host)) < 1e-12
     z = torch.zeros(4, dtype=torch.float64, device='cuda')
     zi = torch.zeros(4, dtype=torch.int64, device='cuda')
     rc = L.lib().gm_rank_metrics(L.GM_F64, L.ptr(z), L.ptr(zi), 20000, 0, 1, 1, 9, 5, L.ptr(z), L.ptr(z), L.ptr(zi),
