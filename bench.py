@@ -56,6 +56,9 @@ def parse():
                     'of the fused peer-memory kernel (A/B)')
     ap.add_argument('--unpacked', action='store_true', help='separate uint8 hop-count vector instead of the packed '
                     '(j | hops << 24) pair format')
+    ap.add_argument('--workload', default='5', help="--impl reference only: '5' (default, the bench line) or one of "
+                    "1, 2a, 2b, 3a, 3b, 4 -- the CPU epoch time of that BASELINE config (the GPU side of those is "
+                    'tools/bench_configs.py)')
     return ap.parse_args()
 
 
@@ -190,6 +193,68 @@ def cpu_step_rate(log2_pairs, steps, warmup, seed=0):
                                 f'fwd+bwd+RAdam step, median of {steps}'
 
 
+# BASELINE configs 1-4 on the host cores: (factors, dtype, optimizer, nodes, node batch or None, CPU node sample)
+CPU_CONFIGS = {
+    '1': ([('spd', 3)], torch.float64, 'rsgd', 1000, None, 1000),
+    '2a': ([('lorentz', 11)], torch.float32, 'radam', 4941, 512, 512),
+    '2b': ([('stein', 4)], torch.float32, 'radam', 4941, 512, 512),
+    '3a': ([('grassmann', (6, 2))], torch.float64, 'radam', 4039, 512, 512),
+    '3b': ([('spd', 3), ('lorentz', 5)], torch.float32, 'radam', 4039, 512, 512),
+    '4': ([('spd', 6)], torch.float32, 'radam', 21363, None, 1024),
+}
+
+
+def cpu_config_epoch(tag, steps, warmup, seed=0):
+    """Epoch time of BASELINE config `tag` with the reference's CPU implementation (oracle port): times the
+    forward + backward + optimizer step of ONE node batch (configs 1-3: the real batch; config 4: a 1024-node sample of
+    its single 21363-node batch) and scales by pairs per epoch."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import manifolds_oracle as O
+    factors, dtype, opt_name, n, batch, sample = CPU_CONFIGS[tag]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(seed)
+    oracles, xs = [], []
+    for fam, arg in factors:
+        if fam in ('spd', 'stein'):
+            o = O.SpdOracle(arg, stein=(fam == 'stein'))
+            x = o.rand(sample, ir=0.1, dtype=dtype, generator=gen)
+        elif fam == 'lorentz':
+            o = O.LorentzOracle(arg)
+            x = o.rand(sample, ir=1e-2, dtype=dtype, generator=gen)
+        else:
+            o = O.GrassmannOracle(*arg)
+            x = o.rand_uniform(sample, dtype=dtype, generator=gen)
+        oracles.append(o)
+        xs.append(x)
+    P = sample * (sample - 1) // 2
+    t = (torch.randint(1, 9, (P,), generator=gen).to(dtype).pow(2) / 64.0)
+    scales = [torch.tensor(0.5, dtype=dtype) for _ in factors]
+    states = [{} for _ in factors]
+    times = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        xr = [x.clone().requires_grad_() for x in xs]
+        m = O.product_dist2(oracles, xr, scales, lambda o, x: o.pdist2(x))
+        loss = O.quotient_loss(t, m, 1.0, 1)
+        loss.backward()
+        for f, (o, x, g, st) in enumerate(zip(oracles, xs, xr, states)):
+            if opt_name == 'rsgd':
+                xs[f] = O.rsgd_step(o, x, g.grad, st, lr=1e-3, max_grad_norm=20, exact=True).detach()
+            else:
+                xs[f] = O.radam_step(o, x, g.grad, st, lr=1e-3, max_grad_norm=100, exact=True).detach()
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+    med = float(np.median(times))
+    bs = n if batch is None else batch
+    pairs_epoch = sum(b * (b - 1) // 2 for b in (min(bs, n - i) for i in range(0, n, bs)) if b >= 50)
+    rate = P / med
+    return dict(config=tag, nodes=n, dtype='f32' if dtype == torch.float32 else 'f64', cores=cores,
+                sample=f'one batch of {sample} nodes = {P} pairs, fwd+bwd+{opt_name} step, median of {steps}',
+                pairs_per_s=rate, pairs_per_epoch=pairs_epoch, epoch_ms=pairs_epoch / rate * 1e3, kind='port')
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port: identical torch/LAPACK calls;
     the Python reference itself cannot travel to the GPU box) on all host cores."""
@@ -197,6 +262,10 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    if args.workload != '5':  # secondary: CPU epoch time of BASELINE configs 1-4, one JSON line each
+        for tag in ([t for t in CPU_CONFIGS] if args.workload == 'all' else args.workload.split(',')):
+            print(json.dumps(dict(impl='reference', **cpu_config_epoch(tag, min(steps, 3), 1))), flush=True)
+        return
     rate, med, cores, sample = cpu_step_rate(args.cpu_pairs_log2, steps, warmup)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,

@@ -105,6 +105,21 @@ class ManifoldEmbedding(EmbeddingBase):
         return self.n
 
 
+_SOFTPLUS_CACHE = {}
+
+
+def _softplus_value(scale):
+    """float(softplus(scale)) without a device->host read per step: the value is cached until the parameter is
+    modified in place (tensor._version changes), i.e. until a curvature optimizer actually steps it."""
+    key = id(scale)
+    hit = _SOFTPLUS_CACHE.get(key)
+    if hit is not None and hit[0] is scale and hit[1] == scale._version:
+        return hit[2]
+    value = float(softplus(scale.detach()))
+    _SOFTPLUS_CACHE[key] = (scale, scale._version, value)
+    return value
+
+
 def _curvature_of(manifold):
     """The curvature tensor of a Universal factor (it receives a gradient), None for every other manifold."""
     get_c = getattr(manifold, 'get_c', None)
@@ -122,7 +137,7 @@ class _FusedObjective(torch.autograd.Function):
         xs = params[:F]
         scales = params[F:2 * F] if has_scales else ()
         cs = params[len(params) - F:]
-        sps = [float(softplus(s.detach())) for s in scales] if has_scales else [1.0] * F
+        sps = [_softplus_value(s) for s in scales] if has_scales else [1.0] * F
         grads = [torch.zeros_like(x, memory_format=torch.contiguous_format) for x in xs]
         c_needs = ctx.needs_input_grad[len(ctx.needs_input_grad) - F:]
         cgrads = [torch.zeros(1, dtype=torch.float64, device=xs[0].device) if (c is not None and need) else None

@@ -35,10 +35,13 @@ default_attrs_ = dict(
 
 class ScalarLog:
     """SummaryWriter stand-in that also keeps every scalar in memory: `history[tag] = [(step, value), ...]`.
-    Forwards to a real tensorboard writer when one can be created."""
+    Forwards to a real tensorboard writer when one can be created.  Device tensors are accepted and only converted to
+    Python floats when somebody looks (`history`, `flush()`, `close()`): logging the per-step loss must not force a
+    device synchronisation per step, which is what dominates small node batches (BASELINE configs 2-3)."""
 
     def __init__(self, log_dir=None, tensorboard=True):
-        self.history = {}
+        self._history = {}
+        self._pending = []  # (tag, step, 0-d device tensor) not yet converted
         self._tb = None
         if tensorboard and log_dir is not None:
             try:
@@ -48,15 +51,34 @@ class ScalarLog:
                 self._tb = None
 
     def add_scalar(self, tag, value, step):
-        v = float(value)
-        self.history.setdefault(tag, []).append((int(step), v))
+        if isinstance(value, torch.Tensor) and value.is_cuda:
+            self._pending.append((tag, int(step), value.detach()))
+            return
+        self._store(tag, int(step), float(value))
+
+    def _store(self, tag, step, v):
+        self._history.setdefault(tag, []).append((step, v))
         if self._tb is not None:
             self._tb.add_scalar(tag, v, step)
+
+    def flush(self):
+        """Convert the queued device scalars (one stacked device->host copy) in the order they were logged."""
+        if self._pending:
+            pending, self._pending = self._pending, []
+            values = torch.stack([v.double().reshape(()) for _, _, v in pending]).cpu().tolist()
+            for (tag, step, _), v in zip(pending, values):
+                self._store(tag, step, v)
+
+    @property
+    def history(self):
+        self.flush()
+        return self._history
 
     def add_figure(self, *args, **kwargs):
         pass
 
     def close(self):
+        self.flush()
         if self._tb is not None:
             self._tb.close()
 
@@ -199,24 +221,74 @@ class TrainingEngine:
         n_points = len(graph_dataset)
         bs = n_points if self.batch_size is None else min(n_points, self.batch_size)
         perm = torch.randperm(n_points)  # default device / default generator, as train.py:206
-        total_loss = 0
+        total_loss = None  # summed on the device: one host read per epoch instead of `loss.item()` per step
         for i in range(0, n_points, bs):
             indices = perm[i:(i + bs)]
             if len(indices) < self.drop_last_n:
                 break
-            loss = self.batched_obj(indices, alpha=alpha, epoch=epoch).sum()
-            for optim in self.optimizer:
-                optim.zero_grad()
-            loss.backward()
-            if self._world > 1:
-                loss = self._combine_ranks(loss)
+            if self._lean_ready(graph_dataset):
+                loss = self._lean_step(graph_dataset, indices, alpha, epoch)
+            else:
+                loss = self.batched_obj(indices, alpha=alpha, epoch=epoch).sum()
+                for optim in self.optimizer:
+                    optim.zero_grad()
+                loss.backward()
+                if self._world > 1:
+                    loss = self._combine_ranks(loss)
             for optim in self.optimizer:
                 optim.step()
             self.global_step += 1
-            self.writer.add_scalar(str(self.objective_fn), loss / len(indices), self.global_step)
-            total_loss += loss.item()
+            step_loss = loss.detach()
+            self.writer.add_scalar(str(self.objective_fn), step_loss / len(indices), self.global_step)
+            total_loss = step_loss.double() if total_loss is None else total_loss + step_loss.double()
+        self.writer.flush()
+        total_loss = 0 if total_loss is None else total_loss.item()
         logger.debug('epoch %d, train loss %.5f', epoch, total_loss / n_points)
         return total_loss
+
+    # ---- lean step: the same arithmetic as forward/zero_grad/backward above without the autograd tape -------------------
+    def _lean_ready(self, graph_dataset):
+        """Single GPU, one non-curved manifold, an objective with a fused form and GPU-resident targets: the step is
+        `zero gradient buffer -> gm_pairs_loss_fused -> optimizer kernel` and nothing else.  For node batches of a few
+        hundred nodes (BASELINE configs 2-3) the autograd path spends ~10x the kernel time on the host."""
+        st = getattr(self, '_lean', None)
+        if st is not None and st['dataset'] is graph_dataset:
+            return st['ok']
+        emb = self.embedding
+        pd = getattr(graph_dataset, 'pdists', None)
+        ok = (self._world == 1 and getattr(emb, 'fused_pair_kernels', False) and hasattr(emb, 'scales')
+              and len(emb.xs) == 1 and not hasattr(emb.manifolds[0], 'get_c')
+              and getattr(self.objective_fn, 'loss_spec', None) is not None
+              and self.objective_fn.loss_spec(epoch=1, alpha=1.0) is not None
+              and pd is not None and pd.is_cuda and pd.device == emb.device and pd.dtype == emb.xs[0].dtype
+              and emb.xs[0].is_contiguous() and not torch.is_anomaly_enabled())
+        st = dict(ok=ok, dataset=graph_dataset)
+        if ok:
+            from . import _ops
+            x = emb.xs[0]
+            owned = {id(p) for optim in self.optimizer for g in optim.param_groups for p in g['params']}
+            st.update(grad=torch.zeros_like(x, memory_format=torch.contiguous_format),
+                      acc=torch.zeros(2, dtype=torch.float64, device=x.device), targets=_ops.TargetSpec.dense(pd),
+                      scale_trained=id(emb.scales[0]) in owned)
+        self._lean = st
+        return ok
+
+    def _lean_step(self, graph_dataset, indices, alpha, epoch):
+        from . import _ops
+        from .modules import _softplus_value
+        st, emb = self._lean, self.embedding
+        x, scale, man = emb.xs[0], emb.scales[0], emb.manifolds[0]
+        pairs = _ops.PairSet.triu(len(indices), indices, emb.device)
+        loss_spec = self.objective_fn.loss_spec(epoch=epoch, alpha=alpha)
+        grad, acc = st['grad'], st['acc']
+        grad.zero_()
+        acc.zero_()
+        _ops.pairs_loss_fused(man.spec, x.detach(), pairs, st['targets'], loss_spec, _softplus_value(scale), grad, acc)
+        x.grad = grad  # what loss.backward() leaves behind (x[indices] backward: a dense (N, ...) gradient)
+        scale.grad = None
+        if st['scale_trained'] and scale.requires_grad:  # d loss / d scale = sigmoid(scale) * sum_k l'_k d2_k
+            scale.grad = (acc[1] * torch.sigmoid(scale.detach().double())).to(scale.dtype)
+        return acc[0].to(x.dtype).clone()
 
     def _combine_ranks(self, loss):
         """Sum the per-rank partial gradients and loss (each rank covered a slice of the batch's pairs)."""

@@ -312,3 +312,41 @@ def test_deferred_loss_readback_matches_blocking_steps():
         runs.append((losses, emb.xs[0].detach().clone()))
     assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
     assert rel_err(runs[1][1], runs[0][1]) < 1e-4
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_lean_step_equals_autograd_step(dtype, tmp_path):
+    """TrainingEngine's tape-free step (zero -> gm_pairs_loss_fused -> optimizer kernel) against its own autograd path
+    (BatchedObjective + loss.backward()) on node mini-batches, incl. a trained scale (curvature optimizer): same step
+    losses, metrics, points and scale up to the summation order of the gradient atomics."""
+    from graphembed.data import GraphDataset
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+    from graphembed.train import TrainingEngine
+    from helpers_engine import load_engine_golden
+    g = load_engine_golden()
+    outs = []
+    for lean in (True, False):
+        torch.manual_seed(3)
+        emb = ManifoldEmbedding(63, [SymmetricPositiveDefinite(4)], device=DEV, dtype=dtype)
+        opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
+        copt = torch.optim.SGD(list(emb.curvature_params), lr=1e-3)
+        eng = TrainingEngine(embedding=emb, optimizer=[opt, copt], objective_fn=QuotientLoss(), n_epochs=4,
+                             val_every_epochs=2, alpha=1.0, batch_size=30, drop_last_n=3, save_dir=str(tmp_path),
+                             tensorboard=False)
+        ds = GraphDataset(g['hops_condensed'].to(device=DEV, dtype=dtype))
+        if not lean:
+            eng._lean = dict(ok=False, dataset=ds)
+        torch.manual_seed(1234)
+        eng(ds)
+        assert eng._lean['ok'] == lean
+        h = eng.writer.history
+        outs.append(([v for _, v in h['quotient_loss']], [v for _, v in h['average_distortion']],
+                     emb.xs[0].detach().clone(), emb.scales[0].detach().clone()))
+    t = 1e-11 if dtype == torch.float64 else 1e-5
+    assert len(outs[0][0]) == 12 and np.allclose(outs[0][0], outs[1][0], rtol=t)
+    assert np.allclose(outs[0][1], outs[1][1], rtol=t)
+    assert rel_err(outs[0][2], outs[1][2]) < t and rel_err(outs[0][3], outs[1][3]) < t
+    assert abs(outs[0][3].item() - 0.5) > 1e-6  # the scale really was trained

@@ -144,7 +144,10 @@ def test_products_embedding_config_with_curvature_optimizer(tmp_path):
     assert isinstance(engine, TrainingEngine) and engine.stabilize_every_epochs == 1
     h = _check_run_dir(tmp_path, g, engine)
     losses = [v for _, v in h['quotient_loss']]
-    assert len(losses) == 6 and all(np.isfinite(losses)) and losses[-1] < losses[0]
+    # no monotonicity claim: QuotientLoss' second term divides by m + 1/(epoch+1) (objectives.py:30), so from the default
+    # init (m ~ 1e-4) it GROWS with the epoch until the points have spread out -- in the reference just the same
+    assert len(losses) == 6 and all(np.isfinite(losses))
+    assert all(np.isfinite(v) for _, v in h['average_distortion'])
     cs = [m.c.item() for m in engine.embedding.manifolds]
     assert all(abs(c - 0.3) > 1e-9 for c in cs)  # the curvature optimizer moved both curvatures
     assert [v for _, v in h['curv0']][-1] == pytest.approx(-engine.embedding.manifolds[0].get_c().item())
