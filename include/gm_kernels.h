@@ -153,10 +153,12 @@ int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_
 
 /* Product-manifold loss over F factor distance vectors (modules.py:84-88 + objectives.py):
  *   m_k = sum_f sp[f]*d2[f][k];  acc[0] += sum_k l(g_k, m_k);  acc[1+f] += sum_k l'_k * d2[f][k];  out_g[k] = l'_k.
- * d2_ptrs_host / sp_host are HOST arrays of length F (F <= 8). */
+ * d2_ptrs_host / sp_host are HOST arrays of length F (F <= 8).  `pairs` (LIST / TRIU, pairs->P == P) is needed only
+ * for DENSE targets, whose matrix is indexed by the pair's node ids -- the fused form of
+ * GraphDataset.__getitem__ (data/dataset.py:19-27); pass NULL otherwise. */
 int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
-                    const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc, void* out_g,
-                    gm_stream_t stream);
+                    const gm_pairs_t* pairs, const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc,
+                    void* out_g, gm_stream_t stream);
 
 /* Validation metrics over a pair set, streamed (TrainingEngine._validate, train.py:230-265; metrics.average_distortion
  * and metrics.pearsonr, metrics.py:13-17,46-56) without materialising the N(N-1)/2 distance vectors:

@@ -127,8 +127,8 @@ static int pair_dispatch(const PairArgs& a) {
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-product_loss_kernel(int F, FactorPtrs fp, TargetSpec tg, LossCfg lc, long long P, double* __restrict__ acc,
-                    T* __restrict__ out_g) {
+product_loss_kernel(int F, FactorPtrs fp, TargetSpec tg, PairSpec ps, LossCfg lc, long long P,
+                    double* __restrict__ acc, T* __restrict__ out_g) {
   __shared__ double red[8];
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = k < P;
@@ -144,7 +144,9 @@ product_loss_kernel(int F, FactorPtrs fp, TargetSpec tg, LossCfg lc, long long P
       T term = (T)fp.sp[f] * d2[f];
       m = (f == 0) ? term : m + term;
     }
-    T g = fetch_target<T>(tg, k, 0, 0);
+    long long ra = 0, rb = 0;
+    if (tg.mode == GM_TGT_DENSE) decode_pair(ps, k, ra, rb);  // node ids index the dense target matrix
+    T g = fetch_target<T>(tg, k, ra, rb);
     T dm;
     lv = (double)loss_term<T>(lc, g, m, dm);
     if (out_g) out_g[k] = dm;
@@ -231,12 +233,19 @@ int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_
 }
 
 int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, const double* sp_host,
-                    const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc, void* out_g,
-                    gm_stream_t stream) {
+                    const gm_pairs_t* pairs, const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc,
+                    void* out_g, gm_stream_t stream) {
   if (!d2_ptrs_host || !sp_host || !targets || !loss || !acc) return GM_ENULL;
   if (F < 1 || F > 8 || P < 0) return GM_EINVAL;
   if (dtype != GM_F32 && dtype != GM_F64) return GM_EINVAL;
-  if (targets->mode == GM_TGT_DENSE) return GM_EINVAL;
+  if (targets->mode == GM_TGT_HOPS_PACKED) return GM_EINVAL;
+  PairSpec ps{};
+  if (targets->mode == GM_TGT_DENSE) {  // the pair enumeration gives the node ids that index the target matrix
+    int rc = validate_pairs(pairs);
+    if (rc) return rc;
+    if (pairs->mode == GM_PAIRS_ELEMENTWISE || pairs->P != P) return GM_EINVAL;
+    ps = make_pairs(pairs);
+  }
   if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
   if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
   if (P == 0) return GM_OK;
@@ -252,10 +261,10 @@ int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, c
   TargetSpec tg = make_targets(targets);
   LossCfg lc = make_loss(loss);
   if (dtype == GM_F32)
-    product_loss_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(F, fp, tg, lc, P, acc,
+    product_loss_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(F, fp, tg, ps, lc, P, acc,
                                                                                        (float*)out_g);
   else
-    product_loss_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(F, fp, tg, lc, P, acc,
+    product_loss_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(F, fp, tg, ps, lc, P, acc,
                                                                                         (double*)out_g);
   note_launch();
   return check_launch();

@@ -48,6 +48,20 @@ class ManifoldSpec:
         return k
 
 
+def _no_function_modes(fn):
+    """Run a launcher with torch-function modes off.  `torch.set_default_device('cuda')` (what run.py does, like the
+    reference's set_default_tensor_type) is a TorchFunctionMode: every tensor attribute a launcher touches (data_ptr,
+    is_contiguous, dtype, ...) then costs ~1.5 us instead of ~0.1 us, which dominates the step on small node batches.
+    Everything below passes devices explicitly, so the default-device mode has nothing to contribute here."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with torch._C.DisableTorchFunction():
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _prep(t):
     L.require_cuda(t)
     return t if t.is_contiguous() else t.contiguous()
@@ -117,6 +131,7 @@ class PairSet:
                        nodes=None if self.nodes is None else self.nodes.data_ptr(), k0=self.k0)
 
 
+@_no_function_modes
 def pairs_dist2(spec, xa, xb, pairs, c=None, wmin=None):
     xa, xb = _prep(xa), _prep(xb)
     if xa.dtype != xb.dtype:
@@ -130,6 +145,7 @@ def pairs_dist2(spec, xa, xb, pairs, c=None, wmin=None):
     return out
 
 
+@_no_function_modes
 def pairs_grad(spec, xa, xb, pairs, gout, ga, gb, coef=1.0, c=None, c_grad=None):
     """ga/gb += coef * gout[k] * d(d2_k)/d(rows) (ELEMENTWISE: plain stores).  Universal: c_grad (float64 CUDA
     scalar) += coef * sum_k gout[k] * d(d2_k)/dc."""
@@ -184,6 +200,7 @@ class TargetSpec:
                          ld=self.ld, max_sq=float(self.max_sq))
 
 
+@_no_function_modes
 def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, want_d2=False, c=None, c_grad=None):
     """One kernel: distances, loss and gradient.  Returns (acc, d2 or None); acc is a 2-element float64 tensor
     [sum loss, sum l'(m) * d2] that is accumulated into (pass a zeroed one or None).  Universal: c_grad (float64
@@ -204,8 +221,10 @@ def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, wa
     return acc, d2
 
 
-def product_loss(d2_list, sp_list, targets, loss, want_g=True):
-    """Loss over the product distance m = sum_f sp_f * d2_f.  Returns (acc[1+F] float64, dL/dm per pair)."""
+@_no_function_modes
+def product_loss(d2_list, sp_list, targets, loss, want_g=True, pairs=None):
+    """Loss over the product distance m = sum_f sp_f * d2_f.  Returns (acc[1+F] float64, dL/dm per pair).  DENSE
+    targets (the (N, N) matrix of GraphDataset) need `pairs`, whose node ids index the matrix."""
     F = len(d2_list)
     d2_list = [_prep(d) for d in d2_list]
     dtype, device, P = d2_list[0].dtype, d2_list[0].device, d2_list[0].numel()
@@ -214,8 +233,9 @@ def product_loss(d2_list, sp_list, targets, loss, want_g=True):
     ptrs = (ctypes.c_void_p * F)(*[d.data_ptr() for d in d2_list])
     sps = (ctypes.c_double * F)(*[float(s) for s in sp_list])
     t, l = targets.c_struct(), loss.c_struct()
+    pc = None if pairs is None else ctypes.byref(pairs.c_struct())
     with torch.cuda.device(device):
-        rc = L.lib().gm_product_loss(L.dtype_code(dtype), F, ptrs, sps, ctypes.byref(t), ctypes.byref(l), P,
+        rc = L.lib().gm_product_loss(L.dtype_code(dtype), F, ptrs, sps, pc, ctypes.byref(t), ctypes.byref(l), P,
                                      L.ptr(acc), L.ptr(g), L.stream_ptr(device))
     L.check(rc, 'gm_product_loss')
     return acc, g
@@ -228,6 +248,7 @@ def _factor_args(d2_list, sp_list):
     return F, ptrs, sps
 
 
+@_no_function_modes
 def pairs_metrics(d2_list, sp_list, pairs, targets, squared=True, acc=None):
     """Adds the validation-metric moments of the given pairs to `acc` (8 float64 slots):
     [count, sum |m-g|/g, sum m, sum g, sum m^2, sum g^2, sum m g] with m = sqrt(sum_f sp_f d2_f), g = sqrt(target)
@@ -274,6 +295,7 @@ def sne_kl(d2_list, sp_list, gdists, alpha, inclusive, want_g=True):
     return acc, g
 
 
+@_no_function_modes
 def point_op(spec, op, x, u=None, v=None, scalar=False):
     x = _prep(x)
     u = None if u is None else _prep(u.to(x.dtype))
@@ -294,6 +316,7 @@ def point_op(spec, op, x, u=None, v=None, scalar=False):
     return out
 
 
+@_no_function_modes
 def optim_step(spec, cfg, x, grad, buf1=None, buf2=None):
     """In-place fused optimizer update of the (N, ...) parameter `x`."""
     L.require_cuda(x, grad, buf1, buf2)
@@ -308,6 +331,7 @@ def optim_step(spec, cfg, x, grad, buf1=None, buf2=None):
     L.check(rc, 'gm_optim_step')
 
 
+@_no_function_modes
 def optim_step_peer(spec, cfg, arena, own_rows, buf1=None, buf2=None):
     """Fused reduce-scatter + optimizer update + all-gather over NVLink peer memory (gm_optim_step_peer): updates the
     rows of arena.x this rank owns from the sum of every rank's arena.grad and publishes them to every rank."""

@@ -148,7 +148,7 @@ class _FusedObjective(torch.autograd.Function):
                                            grads[0], c=cvals[0], c_grad=cgrads[0])
         else:
             d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs, c=c) for m, x, c in zip(manifolds, xs, cvals)]
-            acc, g = _ops.product_loss(d2s, sps, targets, loss_spec)
+            acc, g = _ops.product_loss(d2s, sps, targets, loss_spec, pairs=pairs)
             for m, x, gx, sp, c, cg in zip(manifolds, xs, grads, sps, cvals, cgrads):
                 _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, gx, gx, coef=sp, c=c, c_grad=cg)
         dscale = [acc[1 + f] * torch.sigmoid(scales[f].detach().double()) for f in range(len(scales))]
@@ -202,10 +202,9 @@ class BatchedObjective(torch.nn.Module):
             pairs = pairs.slice(*self.shard)
             lo = pairs.k0 - full_k0
         n_factors = len(emb.xs)
-        if n_factors == 1:
-            targets = _ops.TargetSpec.dense(self.dataset.pdists)  # target gather fused into the pair kernel
-        else:
-            targets = _ops.TargetSpec.vector(self.dataset[indices][lo:lo + pairs.P])
+        # the target gather pdists[idx][:, idx] -> triu (data/dataset.py:19-27) is fused into the pair kernel (one
+        # factor) or into the product-loss kernel (several): both index the dense matrix with the pair's node ids
+        targets = _ops.TargetSpec.dense(self.dataset.pdists)
         scales = tuple(getattr(emb, 'scales', ()))  # products.Embedding has none: plain sum of squared distances
         curvatures = [_curvature_of(m) for m in emb.manifolds]
         return _FusedObjective.apply(pairs, targets, loss_spec, list(emb.manifolds), n_factors, bool(scales), *emb.xs,

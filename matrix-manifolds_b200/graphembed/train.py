@@ -227,7 +227,10 @@ class TrainingEngine:
             if len(indices) < self.drop_last_n:
                 break
             if self._lean_ready(graph_dataset):
-                loss = self._lean_step(graph_dataset, indices, alpha, epoch)
+                with torch._C.DisableTorchFunction():  # see _ops._no_function_modes
+                    loss = self._lean_step(graph_dataset, indices, alpha, epoch)
+                    for optim in self.optimizer:
+                        optim.step()
             else:
                 loss = self.batched_obj(indices, alpha=alpha, epoch=epoch).sum()
                 for optim in self.optimizer:
@@ -235,8 +238,8 @@ class TrainingEngine:
                 loss.backward()
                 if self._world > 1:
                     loss = self._combine_ranks(loss)
-            for optim in self.optimizer:
-                optim.step()
+                for optim in self.optimizer:
+                    optim.step()
             self.global_step += 1
             step_loss = loss.detach()
             self.writer.add_scalar(str(self.objective_fn), step_loss / len(indices), self.global_step)
@@ -248,28 +251,43 @@ class TrainingEngine:
 
     # ---- lean step: the same arithmetic as forward/zero_grad/backward above without the autograd tape -------------------
     def _lean_ready(self, graph_dataset):
-        """Single GPU, one non-curved manifold, an objective with a fused form and GPU-resident targets: the step is
-        `zero gradient buffer -> gm_pairs_loss_fused -> optimizer kernel` and nothing else.  For node batches of a few
-        hundred nodes (BASELINE configs 2-3) the autograd path spends ~10x the kernel time on the host."""
+        """Single GPU, an objective with a fused form and GPU-resident targets: the step is `zero the gradient buffer ->
+        pair kernels -> optimizer kernels` and nothing else -- gm_pairs_loss_fused for one (non-curved) manifold,
+        gm_pairs_dist2 x F + gm_product_loss + gm_pairs_grad x F for products and Universal factors.  For node batches
+        of a few hundred nodes (BASELINE configs 2-3) the autograd path spends ~10x the kernel time on the host."""
         st = getattr(self, '_lean', None)
         if st is not None and st['dataset'] is graph_dataset:
             return st['ok']
         emb = self.embedding
         pd = getattr(graph_dataset, 'pdists', None)
-        ok = (self._world == 1 and getattr(emb, 'fused_pair_kernels', False) and hasattr(emb, 'scales')
-              and len(emb.xs) == 1 and not hasattr(emb.manifolds[0], 'get_c')
+        ok = (self._world == 1 and getattr(emb, 'fused_pair_kernels', False) and hasattr(emb, 'manifolds')
+              and 1 <= len(emb.xs) <= 8
               and getattr(self.objective_fn, 'loss_spec', None) is not None
               and self.objective_fn.loss_spec(epoch=1, alpha=1.0) is not None
               and pd is not None and pd.is_cuda and pd.device == emb.device and pd.dtype == emb.xs[0].dtype
-              and emb.xs[0].is_contiguous() and not torch.is_anomaly_enabled())
+              and all(x.is_contiguous() and x.dtype == emb.xs[0].dtype for x in emb.xs)
+              and not torch.is_anomaly_enabled())
         st = dict(ok=ok, dataset=graph_dataset)
         if ok:
             from . import _ops
-            x = emb.xs[0]
+            dev = emb.device
             owned = {id(p) for optim in self.optimizer for g in optim.param_groups for p in g['params']}
-            st.update(grad=torch.zeros_like(x, memory_format=torch.contiguous_format),
-                      acc=torch.zeros(2, dtype=torch.float64, device=x.device), targets=_ops.TargetSpec.dense(pd),
-                      scale_trained=id(emb.scales[0]) in owned)
+            # every factor's gradient table, the step accumulator and the curvature-gradient slots share one
+            # allocation: one memset per step
+            sizes = [(x.numel() * x.element_size() + 15) // 16 * 16 for x in emb.xs]
+            F = len(emb.xs)
+            buf = torch.zeros(sum(sizes) + 16 + 8 * ((F + 1) // 2 * 2), dtype=torch.uint8, device=dev)
+            grads, off = [], 0
+            for x, sz in zip(emb.xs, sizes):
+                grads.append(buf[off:off + x.numel() * x.element_size()].view(x.dtype).view(x.shape))
+                off += sz
+            acc = buf[off:off + 16].view(torch.float64)
+            cgrads = buf[off + 16:off + 16 + 8 * F].view(torch.float64)
+            scales = list(getattr(emb, 'scales', ()))
+            st.update(buf=buf, grads=grads, acc=acc, cgrads=cgrads, targets=_ops.TargetSpec.dense(pd), scales=scales,
+                      scale_trained=[id(s) in owned for s in scales],
+                      curved=[hasattr(m, 'get_c') for m in emb.manifolds],
+                      curv_trained=[hasattr(m, 'get_c') and id(m.c) in owned for m in emb.manifolds])
         self._lean = st
         return ok
 
@@ -277,18 +295,46 @@ class TrainingEngine:
         from . import _ops
         from .modules import _softplus_value
         st, emb = self._lean, self.embedding
-        x, scale, man = emb.xs[0], emb.scales[0], emb.manifolds[0]
+        xs, mans, scales = list(emb.xs), list(emb.manifolds), st['scales']
+        F = len(xs)
         pairs = _ops.PairSet.triu(len(indices), indices, emb.device)
         loss_spec = self.objective_fn.loss_spec(epoch=epoch, alpha=alpha)
-        grad, acc = st['grad'], st['acc']
-        grad.zero_()
-        acc.zero_()
-        _ops.pairs_loss_fused(man.spec, x.detach(), pairs, st['targets'], loss_spec, _softplus_value(scale), grad, acc)
-        x.grad = grad  # what loss.backward() leaves behind (x[indices] backward: a dense (N, ...) gradient)
-        scale.grad = None
-        if st['scale_trained'] and scale.requires_grad:  # d loss / d scale = sigmoid(scale) * sum_k l'_k d2_k
-            scale.grad = (acc[1] * torch.sigmoid(scale.detach().double())).to(scale.dtype)
-        return acc[0].to(x.dtype).clone()
+        grads = st['grads']
+        st['buf'].zero_()
+        sps = [_softplus_value(s) for s in scales] if scales else [1.0] * F
+        if F == 1 and not st['curved'][0]:
+            acc = st['acc']
+            _ops.pairs_loss_fused(mans[0].spec, xs[0].detach(), pairs, st['targets'], loss_spec, sps[0], grads[0], acc)
+            loss = acc[0].to(xs[0].dtype).clone()  # the accumulator is zeroed again next step
+        else:
+            cs = []  # curvature tensors get_c() of the Universal factors (autograd leaves behind them: man.c)
+            for m, curved, trained in zip(mans, st['curved'], st['curv_trained']):
+                if not curved:
+                    cs.append(None)
+                elif trained and m.c.requires_grad:
+                    with torch.enable_grad():
+                        cs.append(m.get_c())
+                else:
+                    cs.append(m.get_c().detach())
+            cdet = [None if c is None else c.detach() for c in cs]
+            d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs, c=c) for m, x, c in zip(mans, xs, cdet)]
+            acc, g = _ops.product_loss(d2s, sps, st['targets'], loss_spec, pairs=pairs)
+            for f, (m, x, c) in enumerate(zip(mans, xs, cdet)):
+                want_c = cs[f] is not None and cs[f].requires_grad
+                _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, grads[f], grads[f], coef=sps[f], c=c,
+                                c_grad=st['cgrads'][f:f + 1] if want_c else None)
+                if curved := st['curved'][f]:
+                    m.c.grad = None
+                    if want_c:  # chain rule through get_c() (sign / softplus parametrisation, universal.py:28-32)
+                        cs[f].backward(st['cgrads'][f:f + 1].to(cs[f].dtype).reshape(cs[f].shape))
+            loss = acc[0].to(xs[0].dtype)
+        for x, gx in zip(xs, grads):
+            x.grad = gx  # what loss.backward() leaves behind (x[indices] backward: a dense (N, ...) gradient)
+        for f, s in enumerate(scales):
+            s.grad = None
+            if st['scale_trained'][f] and s.requires_grad:  # d loss / d scale_f = sigmoid(scale_f) * sum_k l'_k d2_f,k
+                s.grad = (acc[1 + f] * torch.sigmoid(s.detach().double())).to(s.dtype)
+        return loss
 
     def _combine_ranks(self, loss):
         """Sum the per-rank partial gradients and loss (each rank covered a slice of the batch's pairs)."""

@@ -350,3 +350,49 @@ def test_lean_step_equals_autograd_step(dtype, tmp_path):
     assert np.allclose(outs[0][1], outs[1][1], rtol=t)
     assert rel_err(outs[0][2], outs[1][2]) < t and rel_err(outs[0][3], outs[1][3]) < t
     assert abs(outs[0][3].item() - 0.5) > 1e-6  # the scale really was trained
+
+
+@pytest.mark.parametrize('kind', ['manifold_product', 'universal_product'])
+def test_lean_step_equals_autograd_step_for_products(kind, tmp_path):
+    """Same as above for several factors: a ManifoldEmbedding product with trained scales (SGD on the scales) and a
+    products.Embedding of Universal factors with trained curvatures -- the lean path runs gm_pairs_dist2 per factor,
+    gm_product_loss on the dense targets, gm_pairs_grad per factor (with the curvature gradient)."""
+    from graphembed.data import GraphDataset
+    from graphembed.manifolds import Lorentz, SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+    from graphembed.products import Embedding
+    from graphembed.train import TrainingEngine
+    from helpers_engine import load_engine_golden
+    g = load_engine_golden()
+    outs = []
+    for lean in (True, False):
+        torch.manual_seed(3)
+        if kind == 'manifold_product':
+            emb = ManifoldEmbedding(63, [SymmetricPositiveDefinite(3), Lorentz(5)], device=DEV, dtype=torch.float64)
+        else:
+            emb = Embedding(63, [3, 2], c_init=0.4, device=DEV, dtype=torch.float64)
+            with torch.no_grad():
+                emb.manifolds[1].c.fill_(-0.6)
+                for x in emb.xs:
+                    x.mul_(30.0)
+        opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
+        copt = torch.optim.SGD(list(emb.curvature_params), lr=1e-4)
+        eng = TrainingEngine(embedding=emb, optimizer=[opt, copt], objective_fn=QuotientLoss(), n_epochs=3,
+                             val_every_epochs=3, alpha=1.0, batch_size=30, drop_last_n=3, save_dir=str(tmp_path),
+                             tensorboard=False)
+        ds = GraphDataset(g['hops_condensed'].to(device=DEV, dtype=torch.float64))
+        if not lean:
+            eng._lean = dict(ok=False, dataset=ds)
+        torch.manual_seed(1234)
+        eng(ds)
+        assert eng._lean['ok'] == lean
+        h = eng.writer.history
+        outs.append(([v for _, v in h['quotient_loss']], [x.detach().clone() for x in emb.xs],
+                     [p.detach().clone() for p in emb.curvature_params]))
+    assert len(outs[0][0]) == 9 and np.allclose(outs[0][0], outs[1][0], rtol=1e-11)
+    for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
+        assert rel_err(a, b) < 1e-10
+    start = 0.5 if kind == 'manifold_product' else 0.4
+    assert abs(outs[0][2][0].item() - start) > 1e-7  # scale / curvature parameters really were trained

@@ -4,6 +4,7 @@ throughput of BASELINE.json configs 1-4 on one B200, through the public training
 RiemannianSGD|Adam), on synthetic graphs of the named sizes (the reference's edge lists do not travel to the GPU box).
 
     python tools/bench_configs.py [--epochs 3] [--only 1,2a,...] > profiles/rNN_configs.json
+    torchrun --nproc-per-node G tools/bench_configs.py --only 4      # pair-sharded over G GPUs
 
 One JSON line per config: pairs per epoch, steps per epoch, median epoch ms (CUDA-synchronised wall clock around
 TrainingEngine._train, validation off), pairs/s, the pair kernel's share measured with CUDA events, and the algorithmic
@@ -62,13 +63,13 @@ def bytes_per_pair(E_list, s):
     return sum(4 * E * s for E in E_list) + s + 8
 
 
-def run_config(name, n, mk_manifolds, dtype, opt_name, batch_nodes, epochs, dev, E_list):
+def run_config(name, n, mk_manifolds, dtype, opt_name, batch_nodes, epochs, dev, E_list, pg=None):
     from graphembed import _ops
     from graphembed.modules import ManifoldEmbedding
     from graphembed.objectives import QuotientLoss
     from graphembed.optim import RiemannianAdam, RiemannianSGD
     from graphembed.train import TrainingEngine
-    os.makedirs('/tmp/bench_configs', exist_ok=True)
+    os.makedirs(f"/tmp/bench_configs/r{0 if pg is None else torch.distributed.get_rank(pg)}", exist_ok=True)
     torch.manual_seed(42)
     ds = DenseDataset(graph_targets(n, dev, dtype))
     emb = ManifoldEmbedding(n, mk_manifolds(), device=dev, dtype=dtype)
@@ -76,8 +77,11 @@ def run_config(name, n, mk_manifolds, dtype, opt_name, batch_nodes, epochs, dev,
         opt = RiemannianSGD(emb.xs, lr=1e-3, max_grad_norm=20, exact=True)
     else:
         opt = RiemannianAdam(emb.xs, lr=1e-3, max_grad_norm=100, exact=True)
+    world = 1 if pg is None else torch.distributed.get_world_size(pg)
+    rank = 0 if pg is None else torch.distributed.get_rank(pg)
     eng = TrainingEngine(embedding=emb, optimizer=opt, objective_fn=QuotientLoss(), n_epochs=epochs, alpha=1.0,
-                         batch_size=batch_nodes, tensorboard=False, save_dir='/tmp/bench_configs')
+                         batch_size=batch_nodes, tensorboard=False, save_dir=f'/tmp/bench_configs/r{rank}',
+                         process_group=pg)
     # time the pair kernels inside the epochs
     kernel_events = []
 
@@ -114,11 +118,17 @@ def run_config(name, n, mk_manifolds, dtype, opt_name, batch_nodes, epochs, dev,
     pairs = sum(b * (b - 1) // 2 for b in (min(bs, n - i) for i in range(0, n, bs)) if b >= 50)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / max(len(epoch_ms), 1)
     med = float(np.median(epoch_ms[1:] if len(epoch_ms) > 1 else epoch_ms))
+    if pg is not None:  # every rank evaluates its slice of each batch's pair triangle; report the slowest rank
+        t = torch.tensor([med], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=pg)
+        med = float(t.item())
+        if rank != 0:
+            return
     s = 4 if dtype == torch.float32 else 8
-    line = dict(config=name, nodes=n, dtype='f32' if s == 4 else 'f64', optimizer=opt_name, batch_nodes=batch_nodes,
+    line = dict(config=name, n_gpus=world, nodes=n, dtype='f32' if s == 4 else 'f64', optimizer=opt_name,
+                batch_nodes=batch_nodes,
                 steps_per_epoch=steps, pairs_per_epoch=pairs, epoch_ms=med, pairs_per_s=pairs / (med * 1e-3),
-                pair_kernels_ms_per_epoch=kernel_ms, bytes_per_pair=bytes_per_pair(E_list, s),
-                algorithmic_gbs_in_pair_kernels=pairs * bytes_per_pair(E_list, s) / (kernel_ms * 1e-3) / 1e9,
+                pair_kernels_ms_per_epoch_rank0=kernel_ms, bytes_per_pair=bytes_per_pair(E_list, s),
                 final_loss=float(eng.writer.history['quotient_loss'][-1][1]))
     print(json.dumps(line), flush=True)
     del eng, emb, ds
@@ -131,8 +141,13 @@ def main():
     ap.add_argument('--only', default='')
     args = ap.parse_args()
     from graphembed.manifolds import Grassmann, Lorentz, SymmetricPositiveDefinite as SPD
-    dev = torch.device('cuda', 0)
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
+    pg = None
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:  # torchrun: every batch's pair triangle is sharded over the ranks
+        torch.distributed.init_process_group('nccl', device_id=dev)
+        pg = torch.distributed.group.WORLD
     torch.set_default_device(dev)  # as run.py does: the per-epoch randperm and its slices stay on the GPU
     f32, f64 = torch.float32, torch.float64
     configs = [
@@ -152,7 +167,9 @@ def main():
     for name, n, mk, dtype, opt, bn, E in configs:
         if only and name.split(':')[0] not in only:
             continue
-        run_config(name, n, mk, dtype, opt, bn, args.epochs, dev, E)
+        run_config(name, n, mk, dtype, opt, bn, args.epochs, dev, E, pg)
+    if pg is not None:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':
