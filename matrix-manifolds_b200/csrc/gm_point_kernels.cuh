@@ -131,28 +131,30 @@ __device__ __forceinline__ V vec_add(V a, V b) {
   return a;
 }
 
-// tile <- sum over ranks of g[r][off .. off + nvec) in units of V; U vectors in flight per thread and rank
+// tile <- sum over ranks of g[r][off .. off + nvec) in units of V.  A remote load takes microseconds over NVLink, so the
+// loads of ALL ranks (U vectors each) are issued before the first sum: kMaxPeers * U independent 16-byte requests in
+// flight per thread instead of U (the rank loop is fully unrolled and predicated on r < world); the sum itself stays in
+// rank order, so the result does not depend on the number of loads in flight.
 template <typename T, typename V>
 __device__ __forceinline__ void peer_pull_sum(const PeerTable& pt, size_t byte_off, int nvec, V* tile, int tid) {
-  constexpr int U = 4;
+  constexpr int U = 2;
   for (int c0 = tid; c0 < nvec; c0 += 128 * U) {
-    V acc[U];
-    GM_UNROLL for (int u = 0; u < U; ++u) {
-      int c = c0 + u * 128;
-      acc[u] = (c < nvec) ? reinterpret_cast<const V*>((const char*)pt.g[0] + byte_off)[c] : V{};
-    }
-    for (int r = 1; r < pt.world; ++r) {
-      const V* src = reinterpret_cast<const V*>((const char*)pt.g[r] + byte_off);
-      V v[U];
-      GM_UNROLL for (int u = 0; u < U; ++u) {
-        int c = c0 + u * 128;
-        v[u] = (c < nvec) ? src[c] : V{};
+    V v[kMaxPeers][U];
+    GM_UNROLL for (int r = 0; r < kMaxPeers; ++r) {
+      if (r < pt.world) {
+        const V* src = reinterpret_cast<const V*>((const char*)pt.g[r] + byte_off);
+        GM_UNROLL for (int u = 0; u < U; ++u) {
+          int c = c0 + u * 128;
+          v[r][u] = (c < nvec) ? src[c] : V{};
+        }
       }
-      GM_UNROLL for (int u = 0; u < U; ++u) acc[u] = vec_add<T, V>(acc[u], v[u]);
     }
     GM_UNROLL for (int u = 0; u < U; ++u) {
+      V acc = v[0][u];
+      GM_UNROLL for (int r = 1; r < kMaxPeers; ++r)
+        if (r < pt.world) acc = vec_add<T, V>(acc, v[r][u]);
       int c = c0 + u * 128;
-      if (c < nvec) tile[c] = acc[u];
+      if (c < nvec) tile[c] = acc;
     }
   }
 }

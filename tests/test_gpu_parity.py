@@ -254,15 +254,15 @@ def test_dataset_targets_match_oracle():
     assert torch.equal(ds[idx.to(DEV)].cpu(), O.batch_targets(dense, idx))
 
 
-@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
-def test_full_size_properties_spd4(dtype):
+@pytest.mark.parametrize('dtype,N,P', [(torch.float32, 1 << 16, 1 << 20), (torch.float64, 1 << 16, 1 << 20),
+                                       (torch.float32, 2_000_000, 1 << 24)])  # the last: BASELINE config 5's full size
+def test_full_size_properties_spd4(dtype, N, P):
     """BASELINE-sized invariants that need no oracle: symmetry, affine invariance, fused == unfused, the sum of
     all gradient rows equals the gradient computed pair-by-pair."""
     from graphembed import _ops, _lib as L
     from graphembed.manifolds import SymmetricPositiveDefinite
     torch.manual_seed(0)
     man = SymmetricPositiveDefinite(4)
-    N, P = 1 << 16, 1 << 20
     x = man.rand(N, out=torch.empty(0, device=DEV, dtype=dtype), ir=1.0)
     I = torch.randint(N, (P,), device=DEV, dtype=torch.int32)
     J = (I + 1 + torch.randint(N - 1, (P,), device=DEV, dtype=torch.int32)) % N
