@@ -105,18 +105,15 @@ class ManifoldEmbedding(EmbeddingBase):
         return self.n
 
 
-_SOFTPLUS_CACHE = {}
-
-
 def _softplus_value(scale):
-    """float(softplus(scale)) without a device->host read per step: the value is cached until the parameter is
+    """float(softplus(scale)) without a device->host read per step: the value is cached on the parameter until it is
     modified in place (tensor._version changes), i.e. until a curvature optimizer actually steps it."""
-    key = id(scale)
-    hit = _SOFTPLUS_CACHE.get(key)
-    if hit is not None and hit[0] is scale and hit[1] == scale._version:
-        return hit[2]
+    key = (scale._version, scale.data_ptr())  # in-place updates bump the version, `.data = ...` moves the storage
+    hit = getattr(scale, '_gm_softplus', None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
     value = float(softplus(scale.detach()))
-    _SOFTPLUS_CACHE[key] = (scale, scale._version, value)
+    scale._gm_softplus = (key, value)
     return value
 
 
