@@ -197,15 +197,17 @@ typedef struct gm_optim {
   int32_t has_momentum; /* RSGD: momentum > 0                                                      */
   int32_t first_step; /* RSGD+momentum: buffer is initialised to the Euclidean grad (rsgd.py:53-54) */
   int32_t grassmann_retr_qr; /* Grassmann(retr='qr')                                               */
-  int32_t reserved;
+  int32_t zero_grad;  /* gm_optim_step only: 1 = overwrite every gradient row with zeros once it has been read, i.e.
+                         fold the next step's `zero_grad()` (train.py:214) into this kernel -- saves one full pass
+                         over the gradient table per step; `grad` must then be writable.  0: grad is left untouched */
   double lr, beta1, beta2, momentum, dampening, max_grad_norm, eps;
 } gm_optim_t;
 
 /* One fused in-place optimizer update over all N points (optim/radam.py:43-98, optim/rsgd.py:40-82 and the
  * manifold callees egrad2rgrad / norm / exp|retr / transp of SURVEY 8a A14-A16).
  *   RAdam: buf1 = exp_avg, buf2 = exp_avg_sq (both full parameter shape).  RSGD: buf1 = momentum buffer or NULL. */
-int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, const void* grad, void* buf1,
-                  void* buf2, int64_t N, gm_stream_t stream);
+int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, void* grad, void* buf1, void* buf2,
+                  int64_t N, gm_stream_t stream);
 
 /* ---- multi-GPU: fused reduce-scatter + optimizer update + all-gather over NVLink peer memory ---------------------
  * New capability (the reference's only multi-GPU mechanism is nn.DataParallel, train.py:107-109,203-204).  Pairs are

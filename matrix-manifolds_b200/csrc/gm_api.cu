@@ -270,8 +270,8 @@ int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, c
   return check_launch();
 }
 
-int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, const void* grad, void* buf1,
-                  void* buf2, int64_t N, gm_stream_t stream) {
+int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, void* grad, void* buf1, void* buf2,
+                  int64_t N, gm_stream_t stream) {
   int rc = manifold_ok(man);
   if (rc) return rc;
   if (!opt) return GM_ENULL;

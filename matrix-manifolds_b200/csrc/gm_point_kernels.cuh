@@ -46,7 +46,7 @@ struct PointArgs {
 
 template <class Man, typename T>
 __global__ void __launch_bounds__(128)
-optim_kernel(Man man, OptimCfg oc, T* __restrict__ x, const T* __restrict__ grad, T* __restrict__ buf1,
+optim_kernel(Man man, OptimCfg oc, T* __restrict__ x, T* __restrict__ grad, T* __restrict__ buf1,
              T* __restrict__ buf2, long long N) {
   constexpr int CAP = Man::CAP;
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,6 +67,15 @@ optim_kernel(Man man, OptimCfg oc, T* __restrict__ x, const T* __restrict__ grad
       gs[e] = grad[base + e];
       b1[e] = buf1 ? buf1[base + e] : (T)0;
       b2[e] = buf2 ? buf2[base + e] : (T)0;
+    }
+  }
+  if (oc.zero_grad) {  // the next step's zero_grad(), folded in: the row was just read, hand it back cleared
+    if constexpr (Man::kStatic) {
+      T z[CAP];
+      GM_UNROLL for (int e = 0; e < CAP; ++e) z[e] = (T)0;
+      store_row<T, CAP>(grad, k, z);
+    } else {
+      for (int e = 0; e < cnt; ++e) grad[base + e] = (T)0;
     }
   }
   optim_update<Man, T>(man, oc, xs, gs, b1, b2);
@@ -337,8 +346,8 @@ static int launch_point(const Man& man, const PointArgs& a) {
     peer_optim_kernel<Man, T><<<(unsigned)blocks, threads, use_tile ? tile_bytes : 0, a.stream>>>(
         man, a.oc, *a.peer, (T*)a.buf1, (T*)a.buf2, a.N, use_tile);
   } else if (a.op < 0)
-    optim_kernel<Man, T><<<(unsigned)blocks, threads, 0, a.stream>>>(man, a.oc, (T*)a.x, (const T*)a.u, (T*)a.buf1,
-                                                                     (T*)a.buf2, a.N);
+    optim_kernel<Man, T><<<(unsigned)blocks, threads, 0, a.stream>>>(man, a.oc, (T*)a.x, (T*)const_cast<void*>(a.u),
+                                                                     (T*)a.buf1, (T*)a.buf2, a.N);
   else
     point_op_kernel<Man, T><<<(unsigned)blocks, threads, 0, a.stream>>>(man, a.op, (const T*)a.x, (const T*)a.u,
                                                                         (const T*)a.v, (T*)a.out, a.N);

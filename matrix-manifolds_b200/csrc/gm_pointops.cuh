@@ -542,7 +542,7 @@ struct GrassmannPt {
 // Optimizer update of one point (optim/radam.py:43-98, optim/rsgd.py:40-82).
 // ===========================================================================
 struct OptimCfg {
-  int kind, exact, has_clip, step, has_momentum, first_step;
+  int kind, exact, has_clip, step, has_momentum, first_step, zero_grad;
   double lr, beta1, beta2, momentum, dampening, max_grad_norm, eps;
   double alpha;  // RAdam step size lr * (1 - beta2^t)^0.5 / (1 - beta1^t), evaluated once on the host (radam.py:89-91)
 };
@@ -550,7 +550,7 @@ struct OptimCfg {
 inline OptimCfg make_optim_cfg(const gm_optim_t* opt) {
   OptimCfg c;
   c.kind = opt->kind; c.exact = opt->exact; c.has_clip = opt->has_clip; c.step = opt->step;
-  c.has_momentum = opt->has_momentum; c.first_step = opt->first_step;
+  c.has_momentum = opt->has_momentum; c.first_step = opt->first_step; c.zero_grad = opt->zero_grad;
   c.lr = opt->lr; c.beta1 = opt->beta1; c.beta2 = opt->beta2; c.momentum = opt->momentum;
   c.dampening = opt->dampening; c.max_grad_norm = opt->max_grad_norm; c.eps = opt->eps;
   c.alpha = opt->lr * ::sqrt(1.0 - ::pow(opt->beta2, (double)opt->step)) / (1.0 - ::pow(opt->beta1, (double)opt->step));

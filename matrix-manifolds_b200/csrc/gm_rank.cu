@@ -137,18 +137,39 @@ rank_metrics_kernel(const T* __restrict__ mpdists, const unsigned char* __restri
       int Lj = __shfl_sync(0xffffffffu, L, j);
       if (j < lane) { le += (Lj <= L); eq += (Lj == L); }
     }
-    if (valid && L >= 1 && L < n_layers) {
+    const bool scored = valid && L >= 1 && L < n_layers;
+    double f1 = 0.0;
+    if (scored) {
       le += cum[L];
       eq += cum[L] - cum[L - 1];
       const double nodes_before = (double)(le + 1);                 // precision.cpp:361 (+1: self)
       const double precision = nodes_before / (double)pos;          // :365, i == pos
       const double actual_before = (double)((gcum[L - 1] - 1) + eq + 1);  // :367-375
       const double recall = nodes_before / actual_before;           // :379
-      const double f1 = 2.0 * precision * recall / (precision + recall);
-      atomicAdd(&s_m1[L - 1], f1);
-      atomicAdd(&s_m2[L - 1], f1 * f1);
-      atomicAdd(&s_cnt[L - 1], 1);
+      f1 = 2.0 * precision * recall / (precision + recall);
       if (L == 1) ap_local += (double)(eq + 1) / (double)pos;       // :282-287: n_correct / i at every neighbour
+    }
+    // Per-layer sums.  fp64 shared-memory atomics are compare-and-swap loops, and consecutive sorted positions sit on
+    // one or two layers: a lane-per-atomic version spent 62 % of its stall samples spinning on ~8 addresses
+    // (profiles/r01_v11_aux_kernels_full.txt).  So: one reduction per DISTINCT layer of the chunk, one atomic each.
+    unsigned todo = __ballot_sync(0xffffffffu, scored);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int Lc = __shfl_sync(0xffffffffu, L, leader);
+      const bool mine = scored && L == Lc;
+      const unsigned group = __ballot_sync(0xffffffffu, mine);
+      double s1 = mine ? f1 : 0.0, s2 = mine ? f1 * f1 : 0.0;
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == leader) {
+        atomicAdd(&s_m1[Lc - 1], s1);
+        atomicAdd(&s_m2[Lc - 1], s2);
+        atomicAdd(&s_cnt[Lc - 1], __popc(group));
+      }
+      todo &= ~group;
     }
     __syncwarp();
     // advance the cumulative counts past this chunk: cum[l] += #{j in chunk : L_j <= l}

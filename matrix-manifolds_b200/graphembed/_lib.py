@@ -53,7 +53,7 @@ class Targets(ctypes.Structure):
 class Optim(ctypes.Structure):
     _fields_ = [('kind', ctypes.c_int32), ('exact', ctypes.c_int32), ('has_clip', ctypes.c_int32),
                 ('step', ctypes.c_int32), ('has_momentum', ctypes.c_int32), ('first_step', ctypes.c_int32),
-                ('grassmann_retr_qr', ctypes.c_int32), ('reserved', ctypes.c_int32), ('lr', ctypes.c_double),
+                ('grassmann_retr_qr', ctypes.c_int32), ('zero_grad', ctypes.c_int32), ('lr', ctypes.c_double),
                 ('beta1', ctypes.c_double), ('beta2', ctypes.c_double), ('momentum', ctypes.c_double),
                 ('dampening', ctypes.c_double), ('max_grad_norm', ctypes.c_double), ('eps', ctypes.c_double)]
 

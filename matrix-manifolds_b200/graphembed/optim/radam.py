@@ -39,7 +39,7 @@ class RiemannianAdam(torch.optim.Optimizer):
                 t = state['step']
                 b2 = 1 - 1 / t if group['nc'] else beta2  # AdamNc (radam.py:82-83)
                 cfg = L.Optim(kind=L.GM_OPT_RADAM, exact=int(bool(group['exact'])), has_clip=int(clip is not None),
-                              step=t, has_momentum=0, first_step=int(t == 1), grassmann_retr_qr=0, reserved=0,
+                              step=t, has_momentum=0, first_step=int(t == 1), grassmann_retr_qr=0, zero_grad=0,
                               lr=group['lr'], beta1=beta1, beta2=b2, momentum=0.0, dampening=0.0,
                               max_grad_norm=float(clip) if clip is not None else 0.0, eps=1e-8)
                 fused_step(x, x.grad, cfg, state['exp_avg'], state['exp_avg_sq'])

@@ -35,7 +35,7 @@ class RiemannianSGD(torch.optim.Optimizer):
                     first = True
                 cfg = L.Optim(kind=L.GM_OPT_RSGD, exact=int(bool(group['exact'])), has_clip=int(clip is not None),
                               step=0, has_momentum=int(mom > 0), first_step=int(first), grassmann_retr_qr=0,
-                              reserved=0, lr=group['lr'], beta1=0.0, beta2=0.0, momentum=float(mom),
+                              zero_grad=0, lr=group['lr'], beta1=0.0, beta2=0.0, momentum=float(mom),
                               dampening=float(group['dampening']),
                               max_grad_norm=float(clip) if clip is not None else 0.0, eps=1e-8)
                 fused_step(x, x.grad, cfg, state.get('momentum_buffer'))

@@ -396,3 +396,46 @@ def test_lean_step_equals_autograd_step_for_products(kind, tmp_path):
         assert rel_err(a, b) < 1e-10
     start = 0.5 if kind == 'manifold_product' else 0.4
     assert abs(outs[0][2][0].item() - start) > 1e-7  # scale / curvature parameters really were trained
+
+
+def test_pair_trainer_folded_zero_grad_matches_explicit_memset(monkeypatch):
+    """PairTrainer lets the optimizer kernel clear every gradient row it has read (gm_optim_t.zero_grad) instead of
+    zeroing the table at the top of the next step: 4 steps against the explicit zero -> pairs -> update sequence."""
+    from graphembed import _ops, _lib as L
+    from graphembed.engine import PairTrainer
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+    n, P = 3000, 50000
+    monkeypatch.setenv('GM_FOLD_ZERO_GRAD', '1')
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for _ in range(4):
+        I = torch.randint(n, (P,), generator=g, dtype=torch.int32)
+        J = (I + 1 + torch.randint(n - 1, (P,), generator=g, dtype=torch.int32)) % n
+        batches.append((I.to(DEV), J.to(DEV), torch.randint(1, 9, (P,), generator=g, dtype=torch.uint8).to(DEV)))
+    torch.manual_seed(5)
+    emb = ManifoldEmbedding(n, [SymmetricPositiveDefinite(4)], device=DEV, dtype=torch.float64)
+    x_ref = emb.xs[0].detach().clone()
+    tr = PairTrainer(emb, RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True), QuotientLoss(), max_hops_sq=64.0)
+    assert tr._fold_zero_grad
+    losses = [tr.step(*b, epoch=k + 1).item() for k, b in enumerate(batches)]
+    assert float(tr.grad.abs().max().item()) == 0.0  # handed back cleared
+    # explicit sequence on a copy
+    man = emb.manifolds[0]
+    m, v = torch.zeros_like(x_ref), torch.zeros_like(x_ref)
+    sp = float(torch.nn.functional.softplus(torch.tensor(0.5)))
+    ref_losses = []
+    for k, (I, J, H) in enumerate(batches):
+        grad = torch.zeros_like(x_ref)
+        acc, _ = _ops.pairs_loss_fused(man.spec, x_ref, _ops.PairSet.from_lists(I, J, DEV), _ops.TargetSpec.hops(H, 64.0),
+                                       QuotientLoss().loss_spec(epoch=k + 1, alpha=1.0), sp, grad)
+        cfg = L.Optim(kind=L.GM_OPT_RADAM, exact=1, has_clip=1, step=k + 1, has_momentum=0, first_step=int(k == 0),
+                      grassmann_retr_qr=0, zero_grad=0, lr=0.01, beta1=0.9, beta2=0.999, momentum=0.0, dampening=0.0,
+                      max_grad_norm=100.0, eps=1e-8)
+        _ops.optim_step(man.spec, cfg, x_ref, grad, m, v)
+        assert float(grad.abs().max().item()) > 0.0  # zero_grad=0 leaves the gradient alone
+        ref_losses.append(acc[0].item())
+    assert np.allclose(losses, ref_losses, rtol=1e-9)  # fp64 loss atomics: summation order differs
+    assert rel_err(emb.xs[0].detach(), x_ref) < 1e-10

@@ -141,7 +141,7 @@ def test_universal_optimizer_update(hc, name, oname, tag):
     for k in range(3):
         opt = L.Optim(kind=L.GM_OPT_RADAM if radam else L.GM_OPT_RSGD, exact=int(kw.get('exact', False)),
                       has_clip=int('max_grad_norm' in kw), step=k + 1, has_momentum=int(kw.get('momentum', 0) > 0),
-                      first_step=int(k == 0), grassmann_retr_qr=0, reserved=0, lr=kw['lr'], beta1=0.9, beta2=0.999,
+                      first_step=int(k == 0), grassmann_retr_qr=0, zero_grad=0, lr=kw['lr'], beta1=0.9, beta2=0.999,
                       momentum=kw.get('momentum', 0.0), dampening=kw.get('dampening', 0.0),
                       max_grad_norm=kw.get('max_grad_norm', 0.0), eps=1e-8)
         _hc_point(hc, g, -1, x, g['opt_grads'][k].contiguous(), opt=opt, b1=b1, b2=b2)
