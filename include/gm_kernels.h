@@ -209,6 +209,22 @@ typedef struct gm_optim {
 int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, void* grad, void* buf1, void* buf2,
                   int64_t N, gm_stream_t stream);
 
+/* One whole training epoch over node mini-batches in ONE call (TrainingEngine._train, train.py:198-228, for a single
+ * manifold): for every slice `perm[i : i + batch_nodes]` of the node permutation (slices shorter than drop_last_n end
+ * the epoch, train.py:209-211) launch  zero(grad) -> gm_pairs_loss_fused over all pairs of the slice (TRIU order,
+ * DENSE targets indexed by node id) -> gm_optim_step  back to back on `stream`, with no host work in between.  A
+ * 512-node batch is 130 816 pairs: its kernels take ~50 us, a Python-driven step ~200 us -- this entry point is what
+ * makes BASELINE configs 2-3 kernel-bound.
+ *   opt   : optimizer settings; opt->step is RAdam's state['step'] BEFORE the first update (it is advanced by one per
+ *           slice), opt->first_step applies to the first slice only
+ *   acc   : [max_steps][2] doubles, zeroed by the caller; slice k accumulates into acc[2k] (loss) and acc[2k+1]
+ *           (sum l' d2, for the scale gradient)
+ *   returns the number of slices processed in *n_steps (host), or a negative / CUDA error code */
+int gm_train_epoch(const gm_manifold_t* man, const gm_optim_t* opt, void* x, void* grad, void* buf1, void* buf2,
+                   int64_t N, const void* perm, int32_t perm_is_int64, int64_t n_perm, int64_t batch_nodes,
+                   int64_t drop_last_n, const gm_targets_t* targets, const gm_loss_t* loss, double scale_sp, double* acc,
+                   int64_t max_steps, int64_t* n_steps, gm_stream_t stream);
+
 /* ---- multi-GPU: fused reduce-scatter + optimizer update + all-gather over NVLink peer memory ---------------------
  * New capability (the reference's only multi-GPU mechanism is nn.DataParallel, train.py:107-109,203-204).  Pairs are
  * sharded over ranks; every rank accumulates a full (N, ...) table of partial gradients.  Rank r owns rows

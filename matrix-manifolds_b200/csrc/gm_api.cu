@@ -294,6 +294,54 @@ int gm_optim_step(const gm_manifold_t* man, const gm_optim_t* opt, void* x, void
   return point_dispatch(a);
 }
 
+int gm_train_epoch(const gm_manifold_t* man, const gm_optim_t* opt, void* x, void* grad, void* buf1, void* buf2,
+                   int64_t N, const void* perm, int32_t perm_is_int64, int64_t n_perm, int64_t batch_nodes,
+                   int64_t drop_last_n, const gm_targets_t* targets, const gm_loss_t* loss, double scale_sp, double* acc,
+                   int64_t max_steps, int64_t* n_steps, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  if (!opt || !targets || !loss || !n_steps) return GM_ENULL;
+  *n_steps = 0;
+  if (man->kind == GM_UNIVERSAL) return GM_EUNSUPPORTED;  // the curvature gradient needs the autograd-side chain rule
+  if (N <= 0 || n_perm < 0 || batch_nodes < 2 || max_steps < 0) return GM_EINVAL;
+  if (targets->mode != GM_TGT_DENSE || !targets->data) return GM_EINVAL;
+  if (opt->kind != GM_OPT_RSGD && opt->kind != GM_OPT_RADAM) return GM_EINVAL;
+  if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
+  if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
+  if (!x || !grad || !perm || !acc) return GM_ENULL;
+  if (opt->kind == GM_OPT_RADAM && (!buf1 || !buf2 || opt->step < 1)) return GM_EINVAL;
+  if (opt->kind == GM_OPT_RSGD && opt->has_momentum && !buf1) return GM_ENULL;
+  int64_t elems = 1;  // scalars per point
+  switch (man->kind) {
+    case GM_SPD_AI: case GM_SPD_STEIN: elems = (int64_t)man->n * man->n; break;
+    case GM_GRASSMANN: elems = (int64_t)man->n * man->p; break;
+    default: elems = man->n;
+  }
+  const size_t grad_bytes = (size_t)N * elems * (man->dtype == GM_F32 ? 4 : 8);
+  const size_t idx_bytes = perm_is_int64 ? 8 : 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  gm_optim_t o = *opt;
+  int64_t k = 0;
+  for (int64_t i = 0; i < n_perm; i += batch_nodes, ++k) {
+    const int64_t b = (n_perm - i < batch_nodes) ? (n_perm - i) : batch_nodes;
+    if (b < drop_last_n || b < 2) break;
+    if (k >= max_steps) return GM_EINVAL;
+    cudaError_t e = cudaMemsetAsync(grad, 0, grad_bytes, st);
+    if (e != cudaSuccess) return (int)e;
+    gm_pairs_t pr{};
+    pr.mode = GM_PAIRS_TRIU; pr.idx64 = perm_is_int64; pr.P = b * (b - 1) / 2; pr.B = b;
+    pr.nodes = (const char*)perm + (size_t)i * idx_bytes; pr.k0 = 0;
+    rc = gm_pairs_loss_fused(man, x, &pr, targets, loss, scale_sp, nullptr, acc + 2 * k, grad, stream);
+    if (rc) return rc;
+    rc = gm_optim_step(man, &o, x, grad, buf1, buf2, N, stream);
+    if (rc) return rc;
+    o.step += 1;       // RAdam: state['step'] += 1 (radam.py:98)
+    o.first_step = 0;  // RSGD momentum buffer exists from now on
+  }
+  *n_steps = k;
+  return GM_OK;
+}
+
 int gm_peer_alloc(size_t bytes, void** ptr) {
   if (!ptr) return GM_ENULL;
   if (bytes == 0) return GM_EINVAL;

@@ -15,6 +15,26 @@ class RiemannianSGD(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, momentum=momentum, dampening=dampening, max_grad_norm=max_grad_norm,
                                       exact=exact))
 
+    def _kernel_args(self, group, x):
+        """(gm_optim_t, momentum buffer or None, None) for the next update of `x`; creates the state on first use."""
+        clip = group['max_grad_norm']
+        mom = group['momentum']
+        state = self.state[x]
+        first = False
+        if mom > 0 and 'momentum_buffer' not in state:
+            # the kernel seeds it with the Euclidean gradient on the first step (rsgd.py:53-54)
+            state['momentum_buffer'] = torch.empty_like(x, memory_format=torch.contiguous_format)
+            first = True
+        cfg = L.Optim(kind=L.GM_OPT_RSGD, exact=int(bool(group['exact'])), has_clip=int(clip is not None),
+                      step=0, has_momentum=int(mom > 0), first_step=int(first), grassmann_retr_qr=0,
+                      zero_grad=0, lr=group['lr'], beta1=0.0, beta2=0.0, momentum=float(mom),
+                      dampening=float(group['dampening']),
+                      max_grad_norm=float(clip) if clip is not None else 0.0, eps=1e-8)
+        return cfg, state.get('momentum_buffer'), None
+
+    def _advance(self, x, n_steps=1):
+        pass  # no step counter (rsgd.py:40-82)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -22,21 +42,9 @@ class RiemannianSGD(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
-            clip = group['max_grad_norm']
-            mom = group['momentum']
             for x in group['params']:
                 if x.grad is None:
                     continue
-                state = self.state[x]
-                first = False
-                if mom > 0 and 'momentum_buffer' not in state:
-                    # the kernel seeds it with the Euclidean gradient on the first step (rsgd.py:53-54)
-                    state['momentum_buffer'] = torch.empty_like(x, memory_format=torch.contiguous_format)
-                    first = True
-                cfg = L.Optim(kind=L.GM_OPT_RSGD, exact=int(bool(group['exact'])), has_clip=int(clip is not None),
-                              step=0, has_momentum=int(mom > 0), first_step=int(first), grassmann_retr_qr=0,
-                              zero_grad=0, lr=group['lr'], beta1=0.0, beta2=0.0, momentum=float(mom),
-                              dampening=float(group['dampening']),
-                              max_grad_norm=float(clip) if clip is not None else 0.0, eps=1e-8)
-                fused_step(x, x.grad, cfg, state.get('momentum_buffer'))
+                cfg, buf, _ = self._kernel_args(group, x)
+                fused_step(x, x.grad, cfg, buf)
         return loss

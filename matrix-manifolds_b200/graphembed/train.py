@@ -221,6 +221,8 @@ class TrainingEngine:
         n_points = len(graph_dataset)
         bs = n_points if self.batch_size is None else min(n_points, self.batch_size)
         perm = torch.randperm(n_points)  # default device / default generator, as train.py:206
+        if self._epoch_kernel_ready(graph_dataset):
+            return self._train_epoch_kernel(graph_dataset, perm, bs, alpha, epoch)
         total_loss = None  # summed on the device: one host read per epoch instead of `loss.item()` per step
         for i in range(0, n_points, bs):
             indices = perm[i:(i + bs)]
@@ -335,6 +337,69 @@ class TrainingEngine:
             if st['scale_trained'][f] and s.requires_grad:  # d loss / d scale_f = sigmoid(scale_f) * sum_k l'_k d2_f,k
                 s.grad = (acc[1 + f] * torch.sigmoid(s.detach().double())).to(s.dtype)
         return loss
+
+    # ---- whole epoch in one native call (gm_train_epoch) -------------------------------------------------------------------
+    def _epoch_kernel_ready(self, graph_dataset):
+        """The lean step's preconditions plus: ONE manifold that is not Universal, ONE Riemannian optimizer holding just
+        that parameter (no trained scale, no AdamNc).  Then the slices of the epoch need no host work between them and
+        the whole loop of train.py:207-226 runs inside gm_train_epoch."""
+        if not self._lean_ready(graph_dataset):
+            return False
+        st = self._lean
+        if 'epoch_ok' not in st:
+            from .optim import RiemannianAdam, RiemannianSGD
+            emb = self.embedding
+            ok = (len(emb.xs) == 1 and not st['curved'][0] and not any(st['scale_trained'])
+                  and len(self.optimizer) == 1 and isinstance(self.optimizer[0], (RiemannianAdam, RiemannianSGD))
+                  and len(self.optimizer[0].param_groups) == 1
+                  and len(self.optimizer[0].param_groups[0]['params']) == 1
+                  and self.optimizer[0].param_groups[0]['params'][0] is emb.xs[0]
+                  and not self.optimizer[0].param_groups[0].get('nc', False)
+                  and os.environ.get('GM_EPOCH_KERNEL', '1') == '1')
+            st['epoch_ok'] = ok
+        return st['epoch_ok']
+
+    def _train_epoch_kernel(self, graph_dataset, perm, bs, alpha, epoch):
+        import ctypes
+        from . import _lib as L
+        from .modules import _softplus_value
+        with torch._C.DisableTorchFunction():
+            st, emb, opt = self._lean, self.embedding, self.optimizer[0]
+            x, man = emb.xs[0], emb.manifolds[0]
+            if perm.device != x.device or perm.dtype not in (torch.int32, torch.int64) or not perm.is_contiguous():
+                perm = perm.to(device=x.device, dtype=torch.int64).contiguous()  # drawn on the default device
+            n_points = perm.numel()
+            max_steps = (n_points + bs - 1) // bs
+            acc = torch.zeros(max_steps, 2, dtype=torch.float64, device=x.device)
+            group = opt.param_groups[0]
+            x.grad = st['grads'][0]
+            cfg, buf1, buf2 = opt._kernel_args(group, x)
+            cfg.grassmann_retr_qr = int(getattr(man, 'retr_kind', 'svd') == 'qr')
+            m = man.spec.c_struct(x.dtype, x.device)
+            t = st['targets'].c_struct()
+            l = self.objective_fn.loss_spec(epoch=epoch, alpha=alpha).c_struct()
+            n_steps = ctypes.c_int64(0)
+            with torch.cuda.device(x.device):
+                rc = L.lib().gm_train_epoch(ctypes.byref(m), ctypes.byref(cfg), L.ptr(x.data), L.ptr(x.grad), L.ptr(buf1),
+                                            L.ptr(buf2), x.shape[0], L.ptr(perm), int(perm.dtype == torch.int64),
+                                            n_points, bs, self.drop_last_n, ctypes.byref(t), ctypes.byref(l),
+                                            _softplus_value(emb.scales[0]), L.ptr(acc), max_steps,
+                                            ctypes.byref(n_steps), L.stream_ptr(x.device))
+            L.check(rc, 'gm_train_epoch')
+            k = int(n_steps.value)
+            opt._advance(x, k)
+            # per-step scalars exactly as the step loop logs them: loss / len(indices), in x's dtype
+            losses = acc[:k, 0].to(x.dtype)
+            sizes = torch.tensor([min(bs, n_points - i * bs) for i in range(k)], dtype=x.dtype, device=x.device)
+            per_node = losses / sizes
+            tag = str(self.objective_fn)
+            for i in range(k):
+                self.global_step += 1
+                self.writer.add_scalar(tag, per_node[i], self.global_step)
+            self.writer.flush()
+            total_loss = float(losses.double().sum().item()) if k else 0
+        logger.debug('epoch %d, train loss %.5f', epoch, total_loss / n_points)
+        return total_loss
 
     def _combine_ranks(self, loss):
         """Sum the per-rank partial gradients and loss (each rank covered a slice of the batch's pairs)."""

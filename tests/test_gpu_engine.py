@@ -439,3 +439,54 @@ def test_pair_trainer_folded_zero_grad_matches_explicit_memset(monkeypatch):
         ref_losses.append(acc[0].item())
     assert np.allclose(losses, ref_losses, rtol=1e-9)  # fp64 loss atomics: summation order differs
     assert rel_err(emb.xs[0].detach(), x_ref) < 1e-10
+
+
+@pytest.mark.parametrize('case', ['spd4_radam_f32', 'lorentz_rsgd_momentum_f64', 'grassmann_qr_radam_f64'])
+def test_epoch_kernel_equals_step_loop(case, tmp_path, monkeypatch):
+    """gm_train_epoch (all slices of an epoch launched from one native call) against the Python step loop (lean step
+    per slice, GM_EPOCH_KERNEL=0): same per-step losses, metrics, points and optimizer state, incl. the dropped tail
+    slice, RSGD's momentum seeding on the very first step and the Grassmann qr retraction flag."""
+    from graphembed.data import GraphDataset
+    from graphembed.manifolds import Grassmann, Lorentz, SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss, StressLoss
+    from graphembed.optim import RiemannianAdam, RiemannianSGD
+    from graphembed.train import TrainingEngine
+    from helpers_engine import load_engine_golden
+    g = load_engine_golden()
+    dtype = torch.float32 if case.endswith('f32') else torch.float64
+    outs = []
+    for native in ('1', '0'):
+        monkeypatch.setenv('GM_EPOCH_KERNEL', native)
+        torch.manual_seed(3)
+        if case.startswith('spd4'):
+            emb = ManifoldEmbedding(63, [SymmetricPositiveDefinite(4)], device=DEV, dtype=dtype)
+            opt, obj = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True), QuotientLoss()
+        elif case.startswith('lorentz'):
+            emb = ManifoldEmbedding(63, [Lorentz(6)], device=DEV, dtype=dtype)
+            opt, obj = RiemannianSGD(emb.xs, lr=1e-3, momentum=0.9, dampening=0.1, max_grad_norm=10), StressLoss()
+        else:
+            man = Grassmann(6, 2, retr='qr')
+            emb = ManifoldEmbedding(63, [man], device=DEV, dtype=dtype)
+            with torch.no_grad():
+                emb.xs[0].copy_(man.rand_uniform(63, out=torch.empty(0, device=DEV, dtype=dtype)))
+            opt, obj = RiemannianAdam(emb.xs, lr=0.01), QuotientLoss()
+        eng = TrainingEngine(embedding=emb, optimizer=opt, objective_fn=obj, n_epochs=3, val_every_epochs=3, alpha=1.0,
+                             batch_size=20, drop_last_n=5, save_dir=str(tmp_path), tensorboard=False)
+        ds = GraphDataset(g['hops_condensed'].to(device=DEV, dtype=dtype))
+        torch.manual_seed(1234)
+        eng(ds)
+        assert eng._lean['ok'] and eng._lean['epoch_ok'] == (native == '1')
+        h = eng.writer.history
+        state = opt.state[emb.xs[0]]
+        outs.append(([v for _, v in h[str(obj)]], [v for _, v in h['average_distortion']], emb.xs[0].detach().clone(),
+                     emb.xs[0].grad.detach().clone(), {k: (v.clone() if torch.is_tensor(v) else v) for k, v in state.items()}))
+    t = 1e-10 if dtype == torch.float64 else 2e-5
+    assert len(outs[0][0]) == 9  # 63 nodes = 3 slices of 20 + a tail of 3 < drop_last_n, 3 epochs
+    assert np.allclose(outs[0][0], outs[1][0], rtol=t) and np.allclose(outs[0][1], outs[1][1], rtol=t)
+    assert rel_err(outs[0][2], outs[1][2]) < t and rel_err(outs[0][3], outs[1][3]) < t * 10
+    for key, val in outs[1][4].items():
+        if torch.is_tensor(val):
+            assert rel_err(outs[0][4][key], val) < t * 10
+        else:
+            assert outs[0][4][key] == val  # RAdam's step counter advanced once per slice
