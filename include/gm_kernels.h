@@ -225,6 +225,18 @@ int gm_train_epoch(const gm_manifold_t* man, const gm_optim_t* opt, void* x, voi
                    int64_t drop_last_n, const gm_targets_t* targets, const gm_loss_t* loss, double scale_sp, double* acc,
                    int64_t max_steps, int64_t* n_steps, gm_stream_t stream);
 
+/* gm_train_epoch for a PRODUCT of F manifolds (modules.py:84-88: m = sum_f sp[f] * d2_f): per slice
+ * zero(grad_f) x F -> gm_pairs_dist2 x F -> gm_product_loss -> gm_pairs_grad x F -> gm_optim_step x F, all enqueued from
+ * this one call.  Host arrays of length F: mans, opts (opts[f].step / first_step as in gm_train_epoch), x, grad, buf1,
+ * buf2, sp, d2_ws (device workspaces of >= batch_nodes*(batch_nodes-1)/2 elements of the dtype each); g_ws is one more
+ * such workspace.  acc: [max_steps][1 + F] doubles, zeroed by the caller (slice k: loss, then sum l' d2_f per factor).
+ * All factors share dtype and N.  Universal factors are not supported here (see gm_train_epoch). */
+int gm_train_epoch_product(int32_t F, const gm_manifold_t* mans, const gm_optim_t* opts, void* const* x,
+                           void* const* grad, void* const* buf1, void* const* buf2, int64_t N, const void* perm,
+                           int32_t perm_is_int64, int64_t n_perm, int64_t batch_nodes, int64_t drop_last_n,
+                           const gm_targets_t* targets, const gm_loss_t* loss, const double* sp, void* const* d2_ws,
+                           void* g_ws, double* acc, int64_t max_steps, int64_t* n_steps, gm_stream_t stream);
+
 /* ---- multi-GPU: fused reduce-scatter + optimizer update + all-gather over NVLink peer memory ---------------------
  * New capability (the reference's only multi-GPU mechanism is nn.DataParallel, train.py:107-109,203-204).  Pairs are
  * sharded over ranks; every rank accumulates a full (N, ...) table of partial gradients.  Rank r owns rows

@@ -160,6 +160,14 @@ product_loss_kernel(int F, FactorPtrs fp, TargetSpec tg, PairSpec ps, LossCfg lc
 
 using namespace gm;
 
+static int64_t point_elems(const gm_manifold_t* man) {
+  switch (man->kind) {
+    case GM_SPD_AI: case GM_SPD_STEIN: return (int64_t)man->n * man->n;
+    case GM_GRASSMANN: return (int64_t)man->n * man->p;
+    default: return man->n;
+  }
+}
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -311,13 +319,7 @@ int gm_train_epoch(const gm_manifold_t* man, const gm_optim_t* opt, void* x, voi
   if (!x || !grad || !perm || !acc) return GM_ENULL;
   if (opt->kind == GM_OPT_RADAM && (!buf1 || !buf2 || opt->step < 1)) return GM_EINVAL;
   if (opt->kind == GM_OPT_RSGD && opt->has_momentum && !buf1) return GM_ENULL;
-  int64_t elems = 1;  // scalars per point
-  switch (man->kind) {
-    case GM_SPD_AI: case GM_SPD_STEIN: elems = (int64_t)man->n * man->n; break;
-    case GM_GRASSMANN: elems = (int64_t)man->n * man->p; break;
-    default: elems = man->n;
-  }
-  const size_t grad_bytes = (size_t)N * elems * (man->dtype == GM_F32 ? 4 : 8);
+  const size_t grad_bytes = (size_t)N * point_elems(man) * (man->dtype == GM_F32 ? 4 : 8);
   const size_t idx_bytes = perm_is_int64 ? 8 : 4;
   cudaStream_t st = (cudaStream_t)stream;
   gm_optim_t o = *opt;
@@ -337,6 +339,60 @@ int gm_train_epoch(const gm_manifold_t* man, const gm_optim_t* opt, void* x, voi
     if (rc) return rc;
     o.step += 1;       // RAdam: state['step'] += 1 (radam.py:98)
     o.first_step = 0;  // RSGD momentum buffer exists from now on
+  }
+  *n_steps = k;
+  return GM_OK;
+}
+
+int gm_train_epoch_product(int32_t F, const gm_manifold_t* mans, const gm_optim_t* opts, void* const* x,
+                           void* const* grad, void* const* buf1, void* const* buf2, int64_t N, const void* perm,
+                           int32_t perm_is_int64, int64_t n_perm, int64_t batch_nodes, int64_t drop_last_n,
+                           const gm_targets_t* targets, const gm_loss_t* loss, const double* sp, void* const* d2_ws,
+                           void* g_ws, double* acc, int64_t max_steps, int64_t* n_steps, gm_stream_t stream) {
+  if (!mans || !opts || !x || !grad || !buf1 || !buf2 || !targets || !loss || !sp || !d2_ws || !n_steps) return GM_ENULL;
+  *n_steps = 0;
+  if (F < 1 || F > 8 || N <= 0 || n_perm < 0 || batch_nodes < 2 || max_steps < 0) return GM_EINVAL;
+  if (targets->mode != GM_TGT_DENSE || !targets->data || !perm || !acc || !g_ws) return GM_EINVAL;
+  for (int f = 0; f < F; ++f) {
+    int rc = manifold_ok(&mans[f]);
+    if (rc) return rc;
+    if (mans[f].kind == GM_UNIVERSAL) return GM_EUNSUPPORTED;
+    if (mans[f].dtype != mans[0].dtype) return GM_EINVAL;
+    if (!x[f] || !grad[f] || !d2_ws[f]) return GM_ENULL;
+    if (opts[f].kind != GM_OPT_RSGD && opts[f].kind != GM_OPT_RADAM) return GM_EINVAL;
+    if (opts[f].kind == GM_OPT_RADAM && (!buf1[f] || !buf2[f] || opts[f].step < 1)) return GM_EINVAL;
+    if (opts[f].kind == GM_OPT_RSGD && opts[f].has_momentum && !buf1[f]) return GM_ENULL;
+  }
+  const size_t s_bytes = mans[0].dtype == GM_F32 ? 4 : 8;
+  const size_t idx_bytes = perm_is_int64 ? 8 : 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  gm_optim_t o[8];
+  for (int f = 0; f < F; ++f) o[f] = opts[f];
+  int64_t k = 0;
+  for (int64_t i = 0; i < n_perm; i += batch_nodes, ++k) {
+    const int64_t b = (n_perm - i < batch_nodes) ? (n_perm - i) : batch_nodes;
+    if (b < drop_last_n || b < 2) break;
+    if (k >= max_steps) return GM_EINVAL;
+    gm_pairs_t pr{};
+    pr.mode = GM_PAIRS_TRIU; pr.idx64 = perm_is_int64; pr.P = b * (b - 1) / 2; pr.B = b;
+    pr.nodes = (const char*)perm + (size_t)i * idx_bytes; pr.k0 = 0;
+    for (int f = 0; f < F; ++f) {
+      cudaError_t e = cudaMemsetAsync(grad[f], 0, (size_t)N * point_elems(&mans[f]) * s_bytes, st);
+      if (e != cudaSuccess) return (int)e;
+      int rc = gm_pairs_dist2(&mans[f], x[f], x[f], &pr, d2_ws[f], stream);
+      if (rc) return rc;
+    }
+    int rc = gm_product_loss(mans[0].dtype, F, (const void* const*)d2_ws, sp, &pr, targets, loss, pr.P,
+                             acc + (1 + F) * k, g_ws, stream);
+    if (rc) return rc;
+    for (int f = 0; f < F; ++f) {
+      rc = gm_pairs_grad(&mans[f], x[f], x[f], &pr, g_ws, sp[f], grad[f], grad[f], stream);
+      if (rc) return rc;
+      rc = gm_optim_step(&mans[f], &o[f], x[f], grad[f], buf1[f], buf2[f], N, stream);
+      if (rc) return rc;
+      o[f].step += 1;
+      o[f].first_step = 0;
+    }
   }
   *n_steps = k;
   return GM_OK;

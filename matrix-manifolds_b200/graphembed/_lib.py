@@ -92,6 +92,11 @@ _PROTOTYPES = {
     'gm_train_epoch': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(Optim), _vp, _vp, _vp, _vp, _i64, _vp, _i32,
                                       _i64, _i64, _i64, ctypes.POINTER(Targets), ctypes.POINTER(Loss), _dbl, _vp, _i64,
                                       ctypes.POINTER(_i64), _vp]),
+    'gm_train_epoch_product': (ctypes.c_int, [_i32, ctypes.POINTER(Manifold), ctypes.POINTER(Optim), ctypes.POINTER(_vp),
+                                              ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _vp, _i32,
+                                              _i64, _i64, _i64, ctypes.POINTER(Targets), ctypes.POINTER(Loss),
+                                              ctypes.POINTER(_dbl), ctypes.POINTER(_vp), _vp, _vp, _i64,
+                                              ctypes.POINTER(_i64), _vp]),
     'gm_optim_step_peer': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(Optim), ctypes.POINTER(Peers), _vp,
                                           _vp, _i64, _vp]),
     'gm_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),

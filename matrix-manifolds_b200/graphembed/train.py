@@ -338,22 +338,23 @@ class TrainingEngine:
                 s.grad = (acc[1 + f] * torch.sigmoid(s.detach().double())).to(s.dtype)
         return loss
 
-    # ---- whole epoch in one native call (gm_train_epoch) -------------------------------------------------------------------
+    # ---- whole epoch in one native call (gm_train_epoch / gm_train_epoch_product) ----------------------------------------
     def _epoch_kernel_ready(self, graph_dataset):
-        """The lean step's preconditions plus: ONE manifold that is not Universal, ONE Riemannian optimizer holding just
-        that parameter (no trained scale, no AdamNc).  Then the slices of the epoch need no host work between them and
-        the whole loop of train.py:207-226 runs inside gm_train_epoch."""
+        """The lean step's preconditions plus: no Universal factor, ONE Riemannian optimizer whose single parameter group
+        holds exactly the embedding's point tensors (no trained scale, no AdamNc).  Then the slices of the epoch need no
+        host work between them and the whole loop of train.py:207-226 runs inside one native call."""
         if not self._lean_ready(graph_dataset):
             return False
         st = self._lean
         if 'epoch_ok' not in st:
             from .optim import RiemannianAdam, RiemannianSGD
             emb = self.embedding
-            ok = (len(emb.xs) == 1 and not st['curved'][0] and not any(st['scale_trained'])
+            ok = (not any(st['curved']) and not any(st['scale_trained'])
                   and len(self.optimizer) == 1 and isinstance(self.optimizer[0], (RiemannianAdam, RiemannianSGD))
                   and len(self.optimizer[0].param_groups) == 1
-                  and len(self.optimizer[0].param_groups[0]['params']) == 1
-                  and self.optimizer[0].param_groups[0]['params'][0] is emb.xs[0]
+                  and len(self.optimizer[0].param_groups[0]['params']) == len(emb.xs)
+                  and all(p is x for p, x in zip(self.optimizer[0].param_groups[0]['params'], emb.xs))
+                  and all(x.shape[0] == emb.xs[0].shape[0] for x in emb.xs)
                   and not self.optimizer[0].param_groups[0].get('nc', False)
                   and os.environ.get('GM_EPOCH_KERNEL', '1') == '1')
             st['epoch_ok'] = ok
@@ -365,32 +366,56 @@ class TrainingEngine:
         from .modules import _softplus_value
         with torch._C.DisableTorchFunction():
             st, emb, opt = self._lean, self.embedding, self.optimizer[0]
-            x, man = emb.xs[0], emb.manifolds[0]
-            if perm.device != x.device or perm.dtype not in (torch.int32, torch.int64) or not perm.is_contiguous():
-                perm = perm.to(device=x.device, dtype=torch.int64).contiguous()  # drawn on the default device
+            xs, mans = list(emb.xs), list(emb.manifolds)
+            F, x0 = len(xs), xs[0]
+            dev, dtype = x0.device, x0.dtype
+            if perm.device != dev or perm.dtype not in (torch.int32, torch.int64) or not perm.is_contiguous():
+                perm = perm.to(device=dev, dtype=torch.int64).contiguous()  # drawn on the default device
             n_points = perm.numel()
             max_steps = (n_points + bs - 1) // bs
-            acc = torch.zeros(max_steps, 2, dtype=torch.float64, device=x.device)
             group = opt.param_groups[0]
-            x.grad = st['grads'][0]
-            cfg, buf1, buf2 = opt._kernel_args(group, x)
-            cfg.grassmann_retr_qr = int(getattr(man, 'retr_kind', 'svd') == 'qr')
-            m = man.spec.c_struct(x.dtype, x.device)
+            scales = st['scales']
+            sps = [_softplus_value(s) for s in scales] if scales else [1.0] * F
+            cfgs, b1s, b2s = [], [], []
+            for x, man, gx in zip(xs, mans, st['grads']):
+                x.grad = gx
+                cfg, b1, b2 = opt._kernel_args(group, x)
+                cfg.grassmann_retr_qr = int(getattr(man, 'retr_kind', 'svd') == 'qr')
+                cfgs.append(cfg)
+                b1s.append(b1)
+                b2s.append(b2)
             t = st['targets'].c_struct()
             l = self.objective_fn.loss_spec(epoch=epoch, alpha=alpha).c_struct()
             n_steps = ctypes.c_int64(0)
-            with torch.cuda.device(x.device):
-                rc = L.lib().gm_train_epoch(ctypes.byref(m), ctypes.byref(cfg), L.ptr(x.data), L.ptr(x.grad), L.ptr(buf1),
-                                            L.ptr(buf2), x.shape[0], L.ptr(perm), int(perm.dtype == torch.int64),
-                                            n_points, bs, self.drop_last_n, ctypes.byref(t), ctypes.byref(l),
-                                            _softplus_value(emb.scales[0]), L.ptr(acc), max_steps,
-                                            ctypes.byref(n_steps), L.stream_ptr(x.device))
-            L.check(rc, 'gm_train_epoch')
+            acc = torch.zeros(max_steps, 1 + F, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                if F == 1:
+                    m = mans[0].spec.c_struct(dtype, dev)
+                    rc = L.lib().gm_train_epoch(ctypes.byref(m), ctypes.byref(cfgs[0]), L.ptr(x0.data), L.ptr(x0.grad),
+                                                L.ptr(b1s[0]), L.ptr(b2s[0]), x0.shape[0], L.ptr(perm),
+                                                int(perm.dtype == torch.int64), n_points, bs, self.drop_last_n,
+                                                ctypes.byref(t), ctypes.byref(l), sps[0], L.ptr(acc), max_steps,
+                                                ctypes.byref(n_steps), L.stream_ptr(dev))
+                    L.check(rc, 'gm_train_epoch')
+                else:
+                    bmax = min(bs, n_points)
+                    ws = torch.empty(F + 1, bmax * (bmax - 1) // 2, dtype=dtype, device=dev)  # d2 per factor + dL/dm
+                    vp = ctypes.c_void_p
+                    arr = lambda ts: (vp * F)(*[None if t_ is None else t_.data_ptr() for t_ in ts])  # noqa: E731
+                    m_arr = (L.Manifold * F)(*[man.spec.c_struct(dtype, dev) for man in mans])
+                    o_arr = (L.Optim * F)(*cfgs)
+                    rc = L.lib().gm_train_epoch_product(
+                        F, m_arr, o_arr, arr([x.data for x in xs]), arr([x.grad for x in xs]), arr(b1s), arr(b2s),
+                        x0.shape[0], L.ptr(perm), int(perm.dtype == torch.int64), n_points, bs, self.drop_last_n,
+                        ctypes.byref(t), ctypes.byref(l), (ctypes.c_double * F)(*sps), arr([ws[f] for f in range(F)]),
+                        L.ptr(ws[F]), L.ptr(acc), max_steps, ctypes.byref(n_steps), L.stream_ptr(dev))
+                    L.check(rc, 'gm_train_epoch_product')
             k = int(n_steps.value)
-            opt._advance(x, k)
-            # per-step scalars exactly as the step loop logs them: loss / len(indices), in x's dtype
-            losses = acc[:k, 0].to(x.dtype)
-            sizes = torch.tensor([min(bs, n_points - i * bs) for i in range(k)], dtype=x.dtype, device=x.device)
+            for x in xs:
+                opt._advance(x, k)
+            # per-step scalars exactly as the step loop logs them: loss / len(indices), in the embedding's dtype
+            losses = acc[:k, 0].to(dtype)
+            sizes = torch.tensor([min(bs, n_points - i * bs) for i in range(k)], dtype=dtype, device=dev)
             per_node = losses / sizes
             tag = str(self.objective_fn)
             for i in range(k):

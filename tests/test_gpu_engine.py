@@ -441,7 +441,8 @@ def test_pair_trainer_folded_zero_grad_matches_explicit_memset(monkeypatch):
     assert rel_err(emb.xs[0].detach(), x_ref) < 1e-10
 
 
-@pytest.mark.parametrize('case', ['spd4_radam_f32', 'lorentz_rsgd_momentum_f64', 'grassmann_qr_radam_f64'])
+@pytest.mark.parametrize('case', ['spd4_radam_f32', 'lorentz_rsgd_momentum_f64', 'grassmann_qr_radam_f64',
+                                  'product_spd3_lorentz5_radam_f64', 'product_stein2_sphere4_rsgd_f32'])
 def test_epoch_kernel_equals_step_loop(case, tmp_path, monkeypatch):
     """gm_train_epoch (all slices of an epoch launched from one native call) against the Python step loop (lean step
     per slice, GM_EPOCH_KERNEL=0): same per-step losses, metrics, points and optimizer state, incl. the dropped tail
@@ -465,6 +466,14 @@ def test_epoch_kernel_equals_step_loop(case, tmp_path, monkeypatch):
         elif case.startswith('lorentz'):
             emb = ManifoldEmbedding(63, [Lorentz(6)], device=DEV, dtype=dtype)
             opt, obj = RiemannianSGD(emb.xs, lr=1e-3, momentum=0.9, dampening=0.1, max_grad_norm=10), StressLoss()
+        elif case.startswith('product_spd3'):  # gm_train_epoch_product
+            emb = ManifoldEmbedding(63, [SymmetricPositiveDefinite(3), Lorentz(5)], device=DEV, dtype=dtype)
+            opt, obj = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True), QuotientLoss()
+        elif case.startswith('product_stein2'):
+            from graphembed.manifolds import Sphere
+            sph = Sphere(4)
+            emb = ManifoldEmbedding(63, [SymmetricPositiveDefinite(2, use_stein_div=True), sph], device=DEV, dtype=dtype)
+            opt, obj = RiemannianSGD(emb.xs, lr=1e-3, momentum=0.5, max_grad_norm=10), QuotientLoss(inc_l2=False)
         else:
             man = Grassmann(6, 2, retr='qr')
             emb = ManifoldEmbedding(63, [man], device=DEV, dtype=dtype)
@@ -478,13 +487,17 @@ def test_epoch_kernel_equals_step_loop(case, tmp_path, monkeypatch):
         eng(ds)
         assert eng._lean['ok'] and eng._lean['epoch_ok'] == (native == '1')
         h = eng.writer.history
-        state = opt.state[emb.xs[0]]
-        outs.append(([v for _, v in h[str(obj)]], [v for _, v in h['average_distortion']], emb.xs[0].detach().clone(),
-                     emb.xs[0].grad.detach().clone(), {k: (v.clone() if torch.is_tensor(v) else v) for k, v in state.items()}))
+        state = {f'{f}.{k}': (v.clone() if torch.is_tensor(v) else v) for f, x in enumerate(emb.xs)
+                 for k, v in opt.state[x].items()}
+        outs.append(([v for _, v in h[str(obj)]], [v for _, v in h['average_distortion']],
+                     [x.detach().clone() for x in emb.xs], [x.grad.detach().clone() for x in emb.xs], state))
     t = 1e-10 if dtype == torch.float64 else 2e-5
     assert len(outs[0][0]) == 9  # 63 nodes = 3 slices of 20 + a tail of 3 < drop_last_n, 3 epochs
     assert np.allclose(outs[0][0], outs[1][0], rtol=t) and np.allclose(outs[0][1], outs[1][1], rtol=t)
-    assert rel_err(outs[0][2], outs[1][2]) < t and rel_err(outs[0][3], outs[1][3]) < t * 10
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert rel_err(a, b) < t
+    for a, b in zip(outs[0][3], outs[1][3]):
+        assert rel_err(a, b) < t * 10
     for key, val in outs[1][4].items():
         if torch.is_tensor(val):
             assert rel_err(outs[0][4][key], val) < t * 10
