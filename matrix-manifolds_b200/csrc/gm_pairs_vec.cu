@@ -91,123 +91,6 @@ vec_pair_kernel(VecMan<T, KIND> op, int n, PairSpec ps, const T* __restrict__ xa
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Node mini-batches (TrainingEngine with batch_size ~ 512, BASELINE configs 2-3): ALL pairs of a few hundred rows.  The
-// generic kernel above sends two scalar reductions per element and pair to ~B*n global addresses -- 1.4 M atomics onto 5632
-// words for Lorentz(11), B = 512 -- and gathers every row from L2 three times.  Here a CTA stages the whole batch (rows +
-// node ids) in shared memory once, walks its share of the pair triangle out of shared memory, accumulates the gradients of
-// all B rows in a shared-memory table (fp32/fp64 shared atomics, the `a` side warp-aggregated as above) and sends ONE
-// global reduction per touched (row, element) at the end.  Used for the fused mode when the batch fits (vec_tile_fits).
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kTileThreads = 512;
-
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kTileThreads)
-vec_pair_tile_kernel(VecMan<T, KIND> op, int n, PairSpec ps, const T* __restrict__ x, T* __restrict__ grad,
-                     T* __restrict__ out_d2, TargetSpec tg, LossCfg lc, T scale_sp, double* __restrict__ acc,
-                     double* __restrict__ c_grad) {
-  extern __shared__ __align__(16) unsigned char tile_raw[];
-  const int B = (int)ps.B;
-  T* xs = reinterpret_cast<T*>(tile_raw);           // [B][n] staged rows
-  T* gs = xs + (size_t)B * n;                       // [B][n] gradient table
-  long long* ids = reinterpret_cast<long long*>(gs + (size_t)B * n + ((((size_t)B * n * 2) & 1) ? 1 : 0));  // [B] node ids
-  __shared__ double red[3][kTileThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int b = tid; b < B; b += kTileThreads) ids[b] = ps.nodes ? load_index(ps.nodes, b, ps.idx64) : (long long)b;
-  __syncthreads();
-  for (int t = tid; t < B * n; t += kTileThreads) {
-    int b = t / n, e = t - b * n;
-    xs[t] = x[ids[b] * n + e];
-    gs[t] = (T)0;
-  }
-  __syncthreads();
-  // this CTA's contiguous share of the local pair range [0, P)
-  const long long per = (ps.P + gridDim.x - 1) / gridDim.x;
-  const long long lo = (long long)blockIdx.x * per;
-  const long long hi = (lo + per < ps.P) ? lo + per : ps.P;
-  double loss_v = 0.0, gd2_v = 0.0, dc_v = 0.0;
-  for (long long k0 = lo; k0 < hi; k0 += kTileThreads) {  // warp-uniform trip count inside a CTA
-    const long long k = k0 + tid;
-    const bool active = k < hi;
-    long long a = -1, b = -1;
-    VecCoef<T> c{};
-    T w = (T)0;
-    if (active) {
-      triu_decode(k + ps.k0, ps.B, a, b);
-      const T* px = xs + a * n;
-      const T* py = xs + b * n;
-      T d2 = op.value(px, py, n, c);
-      T g = fetch_target<T>(tg, k, ids[a], ids[b]);
-      T m = scale_sp * d2;
-      T dm;
-      T lv = loss_term<T>(lc, g, m, dm);
-      loss_v += (double)lv;
-      gd2_v += (double)dm * (double)d2;
-      w = dm * scale_sp;
-      if constexpr (KIND == VEC_UNIVERSAL) dc_v += (double)w * (double)c.dc;
-      if (out_d2) out_d2[k] = d2;
-    }
-    const unsigned full = 0xffffffffu;
-    const long long a0 = __shfl_sync(full, a, 0);
-    const bool uni_a = __all_sync(full, a == a0) && a0 >= 0;  // consecutive pairs share the row a
-    for (int e = 0; e < n; ++e) {
-      T gxe = (T)0, gye = (T)0;
-      if (active) {
-        op.grad_elem(e, xs[a * n + e], xs[b * n + e], c, gxe, gye);
-        gxe *= w; gye *= w;
-      }
-      if (uni_a) {
-        gxe = warp_sum(gxe);
-        if (lane == 0) atomicAdd(gs + a0 * n + e, gxe);
-      } else if (active) {
-        atomicAdd(gs + a * n + e, gxe);
-      }
-      if (active) atomicAdd(gs + b * n + e, gye);
-    }
-  }
-  __syncthreads();
-  for (int t = tid; t < B * n; t += kTileThreads) {
-    T v = gs[t];
-    if (v != (T)0) {
-      int b = t / n, e = t - b * n;
-      atomicAdd(grad + ids[b] * n + e, v);
-    }
-  }
-  block_accumulate(loss_v, acc, red[0]);
-  block_accumulate(gd2_v, acc + 1, red[1]);
-  if constexpr (KIND == VEC_UNIVERSAL) {
-    if (c_grad) block_accumulate(dc_v, c_grad, red[2]);
-  }
-}
-
-// shared-memory bytes of the tile kernel for a batch of B rows of n elements (0: does not fit / not worth it)
-template <typename T>
-static size_t vec_tile_bytes(const PairArgs& a) {
-  if (a.kmode != K_FUSED || a.ps.mode != GM_PAIRS_TRIU || a.xa != a.xb || a.ga != a.gb) return 0;
-  if (a.ps.B < 2 || a.ps.B > 4096 || a.ps.P > (1LL << 23)) return 0;
-  size_t elems = (size_t)a.ps.B * a.n * 2;
-  size_t bytes = (elems + (elems & 1)) * sizeof(T) + (size_t)a.ps.B * sizeof(long long);
-  bytes = (bytes + 15) / 16 * 16;
-  return bytes <= 160 * 1024 ? bytes : 0;
-}
-
-template <typename T, int KIND>
-static int vec_tile_launch(const VecMan<T, KIND>& op, const PairArgs& a, size_t bytes) {
-  auto kern = vec_pair_tile_kernel<T, KIND>;
-  if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return (int)e;
-  }
-  // enough CTAs to fill the machine, few enough that the per-CTA flush (B*n reductions) stays small next to the pairs
-  long long ctas = (a.ps.P + 8LL * kTileThreads - 1) / (8LL * kTileThreads);
-  if (ctas < 1) ctas = 1;
-  if (ctas > 148) ctas = 148;
-  kern<<<(unsigned)ctas, kTileThreads, bytes, a.stream>>>(op, a.n, a.ps, (const T*)a.xa, (T*)a.ga, (T*)a.out_d2, a.tg, a.lc,
-                                                         (T)a.scale_sp, a.acc, a.c_grad);
-  note_launch();
-  return check_launch();
-}
-
 template <typename T, int P, bool FAST, int KMODE>
 __global__ void __launch_bounds__(128)
 grassmann_pair_kernel(GrassmannCore<T, P, FAST> op, int n, PairSpec ps, const T* __restrict__ xa,
@@ -324,22 +207,17 @@ static int vec_launch_typed(const PairArgs& a) {
   const T* xa = (const T*)a.xa;
   const T* xb = (const T*)a.xb;
   const T eps = (T)1e-8;
-  const size_t tile_bytes = vec_tile_bytes<T>(a);
   if (a.kind == GM_LORENTZ) {
     VecMan<T, VEC_LORENTZ> op{eps, one_minus_eps2<T>(), nullptr};
-    if (tile_bytes) return vec_tile_launch<T, VEC_LORENTZ>(op, a, tile_bytes);
     GM_LAUNCH3(vec_pair_kernel, op, T, VEC_LORENTZ)
   } else if (a.kind == GM_SPHERE) {
     VecMan<T, VEC_SPHERE> op{eps, one_minus_eps2<T>(), nullptr};
-    if (tile_bytes) return vec_tile_launch<T, VEC_SPHERE>(op, a, tile_bytes);
     GM_LAUNCH3(vec_pair_kernel, op, T, VEC_SPHERE)
   } else if (a.kind == GM_EUCLIDEAN) {
     VecMan<T, VEC_EUCLIDEAN> op{eps, one_minus_eps2<T>(), nullptr};
-    if (tile_bytes) return vec_tile_launch<T, VEC_EUCLIDEAN>(op, a, tile_bytes);
     GM_LAUNCH3(vec_pair_kernel, op, T, VEC_EUCLIDEAN)
   } else if (a.kind == GM_UNIVERSAL) {
     VecMan<T, VEC_UNIVERSAL> op{(T)a.wmin, one_minus_eps2<T>(), (const T*)a.c_dev};  // value floor: wmin
-    if (tile_bytes) return vec_tile_launch<T, VEC_UNIVERSAL>(op, a, tile_bytes);
     GM_LAUNCH3(vec_pair_kernel, op, T, VEC_UNIVERSAL)
   } else if (a.kind == GM_GRASSMANN) {
     const bool fast = (a.flags & GM_FAST_SVD) != 0;

@@ -396,3 +396,49 @@ def test_two_gpu_owner_update_matches_single_gpu():
         l, x = res[mode]
         assert abs(l - l0) <= 1e-10 * abs(l0), mode
         assert np.abs(x - x0).max() <= 1e-10 * np.abs(x0).max(), mode
+
+
+@pytest.mark.parametrize('kind,n,dtype', [('lorentz', 11, torch.float32), ('lorentz', 11, torch.float64),
+                                          ('sphere', 8, torch.float32), ('euclidean', 5, torch.float64),
+                                          ('universal', 6, torch.float64)])
+@pytest.mark.parametrize('B', [512, 1500])
+def test_node_batch_enumeration_matches_explicit_pair_list(kind, n, dtype, B):
+    """Fused step of the vector manifolds over a node batch (TRIU enumeration, targets gathered from the dense matrix
+    by node id) against the same pairs given as an explicit (i, j) LIST: same d2, loss, gradient (and curvature
+    gradient)."""
+    from graphembed import _ops, _lib as L
+    from graphembed.manifolds import Euclidean, Lorentz, Sphere, Universal
+    torch.manual_seed(1)
+    N = 5000
+    hint = torch.empty(0, device=DEV, dtype=dtype)
+    if kind == 'lorentz':
+        man = Lorentz(n)
+        x = man.rand(N, out=hint, ir=0.5)
+    elif kind == 'sphere':
+        man = Sphere(n)
+        x = man.rand_uniform(N, out=hint)
+    elif kind == 'euclidean':
+        man = Euclidean(n)
+        x = man.rand(N, out=hint, ir=1.0)
+    else:
+        man = Universal(n, c_init=0.3, device=DEV, dtype=dtype)
+        x = man.rand(N, ir=0.5)
+    x = x.contiguous()
+    nodes = torch.randperm(N, device=DEV)[:B]
+    dense = torch.rand(N, N, device=DEV, dtype=dtype) * 0.9 + 0.1
+    iu = torch.triu_indices(B, B, 1, device=DEV)
+    I, J = nodes[iu[0]], nodes[iu[1]]
+    spec = _ops.LossSpec(L.GM_LOSS_QUOTIENT, True, True, alpha=1.3, eps=0.25)
+    outs = []
+    for pairs in (_ops.PairSet.triu(B, nodes, DEV), _ops.PairSet.from_lists(I, J, DEV)):
+        grad = torch.zeros_like(x)
+        cg = torch.zeros(1, dtype=torch.float64, device=DEV) if kind == 'universal' else None
+        acc, d2 = _ops.pairs_loss_fused(man.spec, x, pairs, _ops.TargetSpec.dense(dense), spec, 0.9, grad, want_d2=True,
+                                        c_grad=cg)
+        outs.append((acc.clone(), d2, grad, cg))
+    t = 1e-11 if dtype == torch.float64 else 2e-5
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert rel_err(outs[0][0], outs[1][0]) < (1e-12 if dtype == torch.float64 else 1e-6)
+    assert rel_err(outs[0][2], outs[1][2]) < t
+    if kind == 'universal':
+        assert rel_err(outs[0][3], outs[1][3]) < 1e-10
