@@ -245,3 +245,45 @@ def test_universal_has_no_cpu_path_and_mirrors_the_reference_surface():
     assert L.lib().gm_supported(ctypes.byref(m)) == 0  # c_dev missing
     m.c_dev = 16
     assert L.lib().gm_supported(ctypes.byref(m)) == 1
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    """gm_rank_metrics / gm_train_epoch / gm_train_epoch_product reject bad arguments with error codes before touching
+    the device (nothing is launched on this GPU-less box)."""
+    from graphembed import _lib as L
+    lib = L.lib()
+    # gm_rank_metrics: sizes, layer count, empty root range, NULL buffers
+    args = lambda **kw: [kw.get('dtype', L.GM_F32), None, None, kw.get('N', 100), kw.get('lo', 0), kw.get('hi', 100), 1,  # noqa: E731
+                         9, kw.get('layers', 5), None, None, None, None, None, None, None, None]
+    assert lib.gm_rank_metrics(*args(dtype=7)) == -1
+    assert lib.gm_rank_metrics(*args(N=1)) == -1
+    assert lib.gm_rank_metrics(*args(hi=101)) == -1
+    assert lib.gm_rank_metrics(*args(layers=1)) == -1 and lib.gm_rank_metrics(*args(layers=257)) == -1
+    assert lib.gm_rank_metrics(*args(lo=40, hi=40)) == 0  # nothing to do
+    assert lib.gm_rank_metrics(*args()) == -3
+    # gm_train_epoch
+    man = L.Manifold(kind=L.GM_LORENTZ, dtype=L.GM_F32, n=5, p=0, flags=0, reserved=0, wmin=1e-8, wmax=1e8)
+    opt = L.Optim(kind=L.GM_OPT_RADAM, exact=1, has_clip=0, step=1, has_momentum=0, first_step=1, grassmann_retr_qr=0,
+                  zero_grad=0, lr=0.01, beta1=0.9, beta2=0.999, momentum=0.0, dampening=0.0, max_grad_norm=0.0, eps=1e-8)
+    tgt = L.Targets(mode=L.GM_TGT_DENSE, reserved=0, data=64, ld=10, max_sq=1.0)
+    loss = L.Loss(kind=L.GM_LOSS_QUOTIENT, inc_l1=1, inc_l2=1, reserved=0, alpha=1.0, eps=0.5)
+    n_steps = ctypes.c_int64(-1)
+    call = lambda m=man, t=tgt, batch=4, x=None: lib.gm_train_epoch(  # noqa: E731
+        ctypes.byref(m), ctypes.byref(opt), x, None, None, None, 10, None, 1, 10, batch, 2, ctypes.byref(t),
+        ctypes.byref(loss), 1.0, None, 3, ctypes.byref(n_steps), None)
+    assert call() == -3 and n_steps.value == 0  # NULL tables
+    assert call(batch=1) == -1
+    vec_tgt = L.Targets(mode=L.GM_TGT_VECTOR, reserved=0, data=64, ld=0, max_sq=1.0)
+    assert call(t=vec_tgt) == -1  # node batches index the DENSE target matrix
+    uni = L.Manifold(kind=L.GM_UNIVERSAL, dtype=L.GM_F32, n=5, p=0, flags=0, reserved=0, wmin=1e-8, wmax=1e8, c_dev=64)
+    assert call(m=uni) == -2  # curvature gradients need the autograd-side chain rule
+    # gm_train_epoch_product: F range and NULL arrays
+    mans = (L.Manifold * 2)(man, man)
+    opts = (L.Optim * 2)(opt, opt)
+    null2 = (ctypes.c_void_p * 2)(None, None)
+    sp = (ctypes.c_double * 2)(1.0, 1.0)
+    prod = lambda F: lib.gm_train_epoch_product(F, mans, opts, null2, null2, null2, null2, 10, None, 1, 10, 4, 2,  # noqa: E731
+                                                 ctypes.byref(tgt), ctypes.byref(loss), sp, null2, None, None, 3,
+                                                 ctypes.byref(n_steps), None)
+    assert prod(0) == -1 and prod(9) == -1
+    assert prod(2) in (-1, -3)
