@@ -407,7 +407,78 @@ def make_precision():
     return out
 
 
+def make_products_engine_run():
+    """The reference's products.TrainingEngine (graphembed/products/train.py) for 3 epochs with validation every epoch:
+    products.Embedding of a hyperbolic and a spherical Universal factor on the 63-node tree, QuotientLoss, node
+    mini-batches of 40, RAdam(exact) on the points + SGD on the curvatures, stabilize() after every epoch."""
+    import tempfile
+    import networkx as nx
+    from scipy.sparse.csgraph import shortest_path
+    import graphembed.train as T
+    from graphembed.products import Embedding, TrainingEngine
+    class _Anything:  # the per-manifold monitors draw matplotlib figures (monitor.py:53-90): swallow all of it
+        def __call__(self, *a, **k):
+            return self
+
+        def __getattr__(self, name):
+            return self
+
+    plt = sys.modules['matplotlib.pyplot']
+    for name in ('figure', 'scatter', 'gcf', 'close', 'subplots', 'plot'):
+        setattr(plt, name, _Anything())
+    T.SummaryWriter = _Recorder
+    torch.set_default_dtype(torch.float64)
+    g = nx.balanced_tree(2, 5)
+    n = g.number_of_nodes()
+    hops = shortest_path(nx.to_scipy_sparse_array(g), unweighted=True)
+    cond = torch.tensor(hops[np.triu_indices(n, 1)])
+    out = dict(edges=np.array(g.edges()), hops_condensed=cond.numpy())
+    torch.manual_seed(42)
+    with torch.no_grad():
+        emb = Embedding(n, [3, 2], c_init=0.4)
+        emb.manifolds[1].c.fill_(-0.6)
+        for x in emb.xs:
+            x.mul_(30.0)
+            x.proj_()
+    out['c0'] = np.array([m.c.item() for m in emb.manifolds])
+    for i, x in enumerate(emb.xs):
+        out[f'x0_{i}'] = x.data.clone().numpy()
+    opt = RiemannianAdam(emb.xs, lr=0.02, max_grad_norm=100, exact=True)
+    copt = torch.optim.SGD(list(emb.curvature_params), lr=1e-4)
+    # the reference optimizers update parameters in place outside no_grad(); wrap their step like torch >= 1.x needs
+    for o in (opt,):
+        step = o.step
+        o.step = (lambda st: (lambda *a, **k: _no_grad_call(st, *a, **k)))(step)
+    obj = QuotientLoss()
+    with tempfile.TemporaryDirectory() as tmp:
+        eng = TrainingEngine(embedding=emb, optimizer=[opt, copt], objective_fn=obj, n_epochs=3, val_every_epochs=1,
+                             alpha=1.0, batch_size=40, drop_last_n=5, save_dir=tmp)
+        torch.manual_seed(1234)
+        eng(GraphDataset(cond.clone()))
+        out['files'] = np.array(sorted(os.listdir(tmp)))
+        sd = torch.load(os.path.join(tmp, 'best_embedding.pth'))
+        out['state_keys'] = np.array(sorted(sd.keys()))
+    rec = _Recorder.last.scalars
+    out['step_loss'] = np.array([v for _, v in rec[str(obj)]])
+    out['pearsonr'] = np.array([v for _, v in rec['pearsonr']])
+    out['average_distortion'] = np.array([v for _, v in rec['average_distortion']])
+    out['curv0'] = np.array([v for _, v in rec['curv0']])
+    out['curv1'] = np.array([v for _, v in rec['curv1']])
+    out['cT'] = np.array([m.c.item() for m in emb.manifolds])
+    for i, x in enumerate(emb.xs):
+        out[f'xT_{i}'] = x.data.clone().numpy()
+    return out
+
+
+def _no_grad_call(fn, *a, **k):
+    with torch.no_grad():
+        return fn(*a, **k)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'products_engine':
+        np.savez_compressed(os.path.join(HERE, 'products_engine_run_f64.npz'), **make_products_engine_run())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'precision':  # SURVEY 8f-4 fixture only
         np.savez_compressed(os.path.join(HERE, 'precision_map.npz'), **make_precision())
         return
@@ -434,6 +505,7 @@ def main():
             np.savez_compressed(os.path.join(HERE, f'{name}_{tag}.npz'), **make_universal(name, dtype, seed=7))
     np.savez_compressed(os.path.join(HERE, 'universal_training_run_f64.npz'), **make_universal_training_run())
     np.savez_compressed(os.path.join(HERE, 'precision_map.npz'), **make_precision())
+    np.savez_compressed(os.path.join(HERE, 'products_engine_run_f64.npz'), **make_products_engine_run())
     print('wrote', len(os.listdir(HERE)) - 1, 'fixtures to', HERE)
 
 

@@ -205,3 +205,41 @@ def test_universal_at_scale_properties():
         h = 1e-6
         fd = (loss_at(c + h) - loss_at(c - h)) / (2 * h)
         assert abs(cg.item() - fd) < 1e-6 * abs(fd)
+
+
+def test_products_training_engine_vs_reference_engine(tmp_path):
+    """graphembed.products.TrainingEngine (3 epochs, node batches of 40, RAdam on the points + SGD on the two
+    curvatures, stabilize every epoch, validation every epoch) against the reference's own products.TrainingEngine
+    (tests/golden/products_engine_run_f64.npz): step losses, pearsonr / average_distortion, the logged curvatures,
+    final curvature parameters and points, files written."""
+    import os
+    from graphembed.data import GraphDataset
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+    from graphembed.products import Embedding, TrainingEngine
+    g = load_golden('products_engine_run', 'f64')
+    n = g['x0_0'].shape[0]
+    emb = Embedding(n, [3, 2], c_init=0.4, device=DEV, dtype=torch.float64)
+    with torch.no_grad():
+        emb.manifolds[1].c.fill_(-0.6)
+        for i, x in enumerate(emb.xs):
+            x.copy_(g[f'x0_{i}'].to(DEV))
+    opt = RiemannianAdam(emb.xs, lr=0.02, max_grad_norm=100, exact=True)
+    copt = torch.optim.SGD(list(emb.curvature_params), lr=1e-4)
+    obj = QuotientLoss()
+    eng = TrainingEngine(embedding=emb, optimizer=[opt, copt], objective_fn=obj, n_epochs=3, val_every_epochs=1,
+                         alpha=1.0, batch_size=40, drop_last_n=5, save_dir=str(tmp_path), tensorboard=False)
+    ds = GraphDataset(g['hops_condensed'].to(device=DEV, dtype=torch.float64))
+    torch.manual_seed(1234)  # one CPU randperm per epoch, as in the fixture
+    eng(ds)
+    assert eng._lean['ok'] and not eng._lean['epoch_ok']  # trained curvatures: lean step per slice, not the epoch kernel
+    h = eng.writer.history
+    for key, tag in (('step_loss', str(obj)), ('pearsonr', 'pearsonr'), ('average_distortion', 'average_distortion'),
+                     ('curv0', 'curv0'), ('curv1', 'curv1')):
+        got = np.array([v for _, v in h[tag]])
+        assert np.allclose(got, g[key].numpy(), rtol=1e-8), (key, got, g[key])
+    assert np.allclose([m.c.item() for m in emb.manifolds], g['cT'].numpy(), rtol=1e-9)
+    for i, x in enumerate(emb.xs):
+        assert rel_err(x.data, g[f'xT_{i}']) < 1e-9
+    assert sorted(os.listdir(tmp_path)) == list(g['files'])
+    assert sorted(torch.load(tmp_path / 'best_embedding.pth').keys()) == list(g['state_keys'])

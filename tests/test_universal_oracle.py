@@ -131,3 +131,61 @@ def test_products_embedding_training_run():
     for i in range(2):
         assert rel_err(out['grad0'][i], g[f'grad0_{i}']) < 1e-10
         assert rel_err(out['xs'][i], g[f'xT_{i}']) < 1e-10
+
+
+def products_engine_oracle(g, n_epochs=3, batch=40, drop_last_n=5):
+    """Restatement of the reference's products.TrainingEngine run recorded in tests/golden/products_engine_run_f64.npz
+    (make_golden.py::make_products_engine_run): train.py:198-228 step loop, stabilize after every epoch
+    (products/train.py:13-14, products/embedding.py:36-46), validation metrics (train.py:230-265) and the curvature
+    scalars `curv{i}` = get_K() (products/embedding.py:48-50)."""
+    ns = [g['x0_0'].shape[1], g['x0_1'].shape[1]]
+    xs = [g['x0_0'].clone(), g['x0_1'].clone()]
+    c_params = [torch.tensor([float(c)], dtype=torch.float64) for c in g['c0']]
+    n = xs[0].shape[0]
+    t_cond = O.dataset_targets(g['hops_condensed'], torch.float64)
+    dense = torch.zeros(n, n, dtype=torch.float64)
+    iu = torch.triu_indices(n, n, 1)
+    dense[iu[0], iu[1]] = t_cond
+    dense = dense + dense.T
+    states = [{}, {}]
+    out = dict(step_loss=[], pearsonr=[], average_distortion=[], curv0=[], curv1=[])
+    torch.manual_seed(1234)
+    for epoch in range(1, n_epochs + 1):
+        perm = torch.randperm(n)
+        for i in range(0, n, batch):
+            idx = perm[i:i + batch]
+            if len(idx) < drop_last_n:
+                break
+            cps = [c.clone().requires_grad_() for c in c_params]
+            mans = [O.UniversalOracle(d, O.universal_get_c(cp)) for d, cp in zip(ns, cps)]
+            xr = [x.clone().requires_grad_() for x in xs]
+            m = sum(man.pdist2(x[idx]) for man, x in zip(mans, xr))
+            loss = O.quotient_loss(O.batch_targets(dense, idx), m, 1.0, epoch)
+            loss.backward()
+            with torch.no_grad():
+                plain = [O.UniversalOracle(d, O.universal_get_c(cp.detach())) for d, cp in zip(ns, c_params)]
+                xs = [O.radam_step(man, x, xg.grad, st, lr=0.02, max_grad_norm=100, exact=True)
+                      for man, x, xg, st in zip(plain, xs, xr, states)]
+                c_params = [cp - 1e-4 * cg.grad for cp, cg in zip(c_params, cps)]
+            out['step_loss'].append(loss.item() / len(idx))
+        with torch.no_grad():
+            mans = [O.UniversalOracle(d, O.universal_get_c(cp)) for d, cp in zip(ns, c_params)]
+            xs = [man.projx(x / (x.norm(p=2, dim=-1, keepdim=True) / 5.0).clamp(min=1)) for man, x in zip(mans, xs)]
+            md = sum(man.pdist2(x) for man, x in zip(mans, xs)).sqrt()
+            gd = t_cond.sqrt()
+            out['pearsonr'].append(O.pearsonr(md, gd).item())
+            out['average_distortion'].append(O.average_distortion(md, gd).item())
+            out['curv0'].append(-O.universal_get_c(c_params[0]).item())
+            out['curv1'].append(-O.universal_get_c(c_params[1]).item())
+    out.update(xs=xs, cT=[cp.item() for cp in c_params])
+    return out
+
+
+def test_products_training_engine_run():
+    g = load_golden('products_engine_run', 'f64')
+    out = products_engine_oracle(g)
+    for key in ('step_loss', 'pearsonr', 'average_distortion', 'curv0', 'curv1'):
+        assert np.allclose(out[key], g[key].numpy(), rtol=1e-9), key
+    assert np.allclose(out['cT'], g['cT'].numpy(), rtol=1e-10)
+    for i in range(2):
+        assert rel_err(out['xs'][i], g[f'xT_{i}']) < 1e-10
