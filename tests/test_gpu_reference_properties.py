@@ -118,7 +118,7 @@ def test_spd_stein_pdiv_equals_div(seed, d):
     assert close(spd.dist(xs[m[0]], xs[m[1]], squared=True), spd.pdist(xs, squared=True))
 
 
-@pytest.mark.parametrize('n,p', product(range(5, 10), [2, 3, 4]))
+@pytest.mark.parametrize('n,p', list(product(range(5, 10), [2, 3, 4])))
 def test_grassmann_log_and_gradient(seed, n, p):
     from graphembed.manifolds import Grassmann
     gras = Grassmann(n, p)
@@ -158,7 +158,7 @@ def test_sphere_antipodal_distance():
     assert close(man.dist(x, y), math.pi, atol=1e-3)  # fp32 acos near -1
 
 
-@pytest.mark.parametrize('n,which', product([3, 4, 5], ['rsgd', 'radam']))
+@pytest.mark.parametrize('n,which', list(product([3, 4, 5], ['rsgd', 'radam'])))
 def test_optimizers_find_the_dominant_eigenvector(seed, n, which):
     from graphembed.manifolds import Sphere
     from graphembed.modules import ManifoldParameter
