@@ -1,0 +1,107 @@
+"""CPU tests of host-side pieces that carry semantics of their own: the lazy scalar log of TrainingEngine, the cached
+softplus(scale), the optimizer argument builders that gm_train_epoch relies on, and the reference-facing structure of
+products.Embedding / graphembed.pyx."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_scalar_log_is_lazy_for_device_values_only():
+    from graphembed.train import ScalarLog
+    log = ScalarLog(None, tensorboard=False)
+    log.add_scalar('a', 1.5, 1)
+    log.add_scalar('a', torch.tensor(2.5), 2)  # CPU tensor: converted at once
+    assert log._pending == [] and log.history['a'] == [(1, 1.5), (2, 2.5)]
+
+    class FakeCuda(torch.Tensor):  # a tensor that claims to live on the device: must be queued, not synchronised on
+        @property
+        def is_cuda(self):
+            return True
+
+    v = torch.tensor(3.25).as_subclass(FakeCuda)
+    log.add_scalar('a', v, 3)
+    assert len(log._pending) == 1 and len(log._history['a']) == 2
+    assert log.history['a'][-1] == (3, 3.25) and log._pending == []  # looking at it flushes, in logging order
+    log.add_scalar('b', torch.tensor(7.0).as_subclass(FakeCuda), 1)
+    log.close()
+    assert log._history['b'] == [(1, 7.0)]
+
+
+def test_softplus_cache_follows_in_place_updates_and_storage_swaps():
+    from graphembed.modules import _softplus_value
+    p = torch.nn.Parameter(torch.tensor(0.5, dtype=torch.float64))
+    sp = lambda v: float(torch.nn.functional.softplus(torch.tensor(v, dtype=torch.float64)))  # noqa: E731
+    assert _softplus_value(p) == pytest.approx(sp(0.5), rel=1e-15)
+    with torch.no_grad():
+        p.add_(1.0)
+    assert _softplus_value(p) == pytest.approx(sp(1.5), rel=1e-15)
+    p.data = torch.tensor(0.1, dtype=torch.float64)  # no version bump: the storage pointer is part of the key
+    assert _softplus_value(p) == pytest.approx(sp(0.1), rel=1e-15)
+    assert _softplus_value(p) is not None and getattr(p, '_gm_softplus')[1] == _softplus_value(p)
+
+
+def test_optimizer_kernel_args_mirror_reference_hyperparameters():
+    """RiemannianAdam / RiemannianSGD._kernel_args: what step() and the one-call epoch hand to the kernels
+    (optim/radam.py:43-98, optim/rsgd.py:40-82)."""
+    from graphembed import _lib as L
+    from graphembed.manifolds import Lorentz
+    from graphembed.modules import ManifoldParameter
+    from graphembed.optim import RiemannianAdam, RiemannianSGD
+    x = ManifoldParameter(torch.zeros(4, 5), manifold=Lorentz(5))
+    adam = RiemannianAdam([x], lr=0.02, betas=(0.8, 0.99), max_grad_norm=7.0, exact=True)
+    cfg, m, v = adam._kernel_args(adam.param_groups[0], x)
+    assert (cfg.kind, cfg.exact, cfg.has_clip, cfg.step, cfg.zero_grad) == (L.GM_OPT_RADAM, 1, 1, 1, 0)
+    assert (cfg.lr, cfg.beta1, cfg.beta2, cfg.max_grad_norm, cfg.eps) == (0.02, 0.8, 0.99, 7.0, 1e-8)
+    assert m.shape == x.shape and v.shape == x.shape and float(m.abs().sum() + v.abs().sum()) == 0.0
+    adam._advance(x, 3)
+    assert adam.state[x]['step'] == 4 and adam._kernel_args(adam.param_groups[0], x)[0].step == 4
+    nc = RiemannianAdam([x], lr=0.02, nc=True)
+    nc._kernel_args(nc.param_groups[0], x)
+    nc._advance(x, 4)
+    assert nc._kernel_args(nc.param_groups[0], x)[0].beta2 == pytest.approx(1 - 1 / 5)  # AdamNc: 1 - 1/t
+    sgd = RiemannianSGD([x], lr=0.1, momentum=0.9, dampening=0.2)
+    cfg, buf, none = sgd._kernel_args(sgd.param_groups[0], x)
+    assert (cfg.kind, cfg.has_momentum, cfg.first_step, cfg.has_clip, none) == (L.GM_OPT_RSGD, 1, 1, 0, None)
+    assert (cfg.momentum, cfg.dampening, cfg.lr) == (0.9, 0.2, 0.1) and buf.shape == x.shape
+    assert sgd._kernel_args(sgd.param_groups[0], x)[0].first_step == 0  # the buffer exists from now on
+    plain = RiemannianSGD([x], lr=0.1)
+    cfg, buf, _ = plain._kernel_args(plain.param_groups[0], x)
+    assert cfg.has_momentum == 0 and buf is None
+    with pytest.raises(ValueError):
+        RiemannianSGD([x], lr=0.1, momentum=-1.0)
+
+
+def test_products_embedding_structure_without_gpu():
+    """products.Embedding (products/embedding.py:8-61): Universal factors as sub-modules, curvature parameters, the
+    state-dict keys agg_grid_results.py reads, and the r_max norm constraint of stabilize() -- tensor-only parts."""
+    from graphembed.products import Embedding
+    emb = Embedding.__new__(Embedding)
+    torch.nn.Module.__init__(emb)
+    from graphembed.manifolds import Universal
+    from graphembed.modules import ManifoldParameter
+    emb.n, emb.ds, emb.r_max = 6, [3, 2], 5.0
+    emb.manifolds = torch.nn.ModuleList([Universal(d, c_init=c) for d, c in zip(emb.ds, (0.4, -0.6))])
+    emb.xs = torch.nn.ParameterList([ManifoldParameter(torch.randn(6, d), manifold=m)
+                                     for d, m in zip(emb.ds, emb.manifolds)])
+    assert sorted(emb.state_dict().keys()) == ['manifolds.0.c', 'manifolds.1.c', 'xs.0', 'xs.1']
+    assert [p.item() for p in emb.curvature_params] == pytest.approx([0.4, -0.6])
+    emb.burnin(True)
+    assert not any(p.requires_grad for p in emb.curvature_params)
+    emb.burnin(False)
+    assert all(p.requires_grad for p in emb.curvature_params)
+    assert len(emb) == 6 and emb.fused_pair_kernels and not hasattr(emb, 'scales')
+    assert emb.manifolds[0].get_c().item() == pytest.approx(0.401) and emb.manifolds[1].get_c().item() == pytest.approx(-0.601)
+
+
+def test_fast_precision_surface_and_csr_construction():
+    """graphembed.pyx exposes the reference's class under both of its names; edges_to_csr builds the symmetric CSR
+    the BFS and rank kernels expect (sorted neighbours, no duplicates or self loops)."""
+    import graphembed.pyx as pyx
+    from graphembed.data import edges_to_csr
+    assert pyx.PyFastPrecision is pyx.FastPrecision
+    for name in ('mean_average_precision', 'layer_mean_f1_scores', 'layer_mean_average_f1_scores', 'nodes_per_layer'):
+        assert callable(getattr(pyx.FastPrecision, name))
+    rowptr, colidx = edges_to_csr(5, np.array([[0, 1], [1, 0], [1, 2], [3, 3], [4, 1], [1, 2]]))
+    assert rowptr.tolist() == [0, 1, 4, 5, 5, 6] and colidx.tolist() == [1, 0, 2, 4, 1, 1]
+    rowptr, colidx = edges_to_csr(3, np.array([[0, 1], [1, 2]]), directed=True)  # in-neighbours of every node
+    assert rowptr.tolist() == [0, 0, 1, 2] and colidx.tolist() == [0, 1]
