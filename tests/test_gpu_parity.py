@@ -442,3 +442,33 @@ def test_node_batch_enumeration_matches_explicit_pair_list(kind, n, dtype, B):
     assert rel_err(outs[0][2], outs[1][2]) < t
     if kind == 'universal':
         assert rel_err(outs[0][3], outs[1][3]) < 1e-10
+
+
+@pytest.mark.parametrize('kind,n', [('lorentz', 8), ('sphere', 4), ('euclidean', 12)])
+def test_vector_reduction_rows_match_oracle(kind, n):
+    """fp32 rows of 16-byte multiples (n % 4 == 0) accumulate their gradients with 128-bit reductions; the sampled-pair
+    gradient (incl. many pairs hitting the same row, and a warp whose lanes all share the first endpoint) against the
+    oracle's autograd."""
+    from graphembed.manifolds import Euclidean, Lorentz, Sphere
+    torch.manual_seed(4)
+    N, P = 300, 6000
+    g = torch.Generator().manual_seed(4)
+    if kind == 'lorentz':
+        man, orc = Lorentz(n), O.LorentzOracle(n)
+        x = orc.rand(N, ir=0.7, dtype=torch.float32, generator=g)
+    elif kind == 'sphere':
+        man, orc = Sphere(n), O.SphereOracle(n)
+        x = orc.rand_uniform(N, dtype=torch.float32, generator=g)
+    else:
+        man, orc = Euclidean(n), O.EuclideanOracle(n)
+        x = torch.randn(N, n, generator=g)
+    I = torch.randint(N, (P,), generator=g)
+    I[:64] = 7  # two warps whose lanes share the `i` row: the warp-aggregated branch
+    J = (I + 1 + torch.randint(N - 1, (P,), generator=g)) % N
+    w = torch.rand(P, generator=g) + 0.5
+    xr = x.clone().requires_grad_()
+    (orc.dist2(xr[I], xr[J]) * w).sum().backward()
+    xd = x.to(DEV).requires_grad_()
+    d2 = man.pair_dist2(xd, I.to(DEV), J.to(DEV))
+    (d2 * w.to(DEV)).sum().backward()
+    assert rel_err(xd.grad, xr.grad) < 2e-5
