@@ -5,7 +5,6 @@ graphembed/data/graph.py:15-63 (edge-list / .npy input, `.cached_pdists` cache,
 returns (condensed distance tensor, networkx graph)); the distances themselves
 come from the bit-parallel multi-source BFS kernel (csrc/gm_graph.cu) instead of
 networkit's APSP plus an O(N^2) Python loop (graph.py:66-87)."""
-import ctypes
 import logging
 import os
 

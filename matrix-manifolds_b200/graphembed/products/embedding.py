@@ -3,7 +3,6 @@ graphembed/products/embedding.py:8-61.  The squared product distance is the plai
 distances (no learnable scales, unlike modules.ManifoldEmbedding)."""
 import torch
 
-from .. import _ops
 from ..manifolds import Universal
 from ..modules import EmbeddingBase, ManifoldParameter
 

@@ -4,8 +4,6 @@ the shortest-path-tree layers come from the multi-source BFS kernel (gm_bfs_mult
 from gm_rank_metrics (csrc/gm_rank.cu): one CTA per root sorts that root's manifold distances in shared memory and
 turns the reference's ordered-multiset walk into prefix counts.  Unweighted graphs only (the hot path's targets are
 hop counts); there is no CPU fallback."""
-import ctypes
-
 import numpy as np
 import torch
 

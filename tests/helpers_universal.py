@@ -1,7 +1,5 @@
 """Fixtures / factories for the Universal (kappa-stereographic) manifold tests.  The golden files come
 from the real reference: tests/golden/make_golden.py::make_universal, make_universal_training_run."""
-import torch
-
 from helpers import load_golden
 
 UNIVERSAL_CASES = {
