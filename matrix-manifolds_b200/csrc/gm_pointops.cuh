@@ -525,9 +525,55 @@ struct GrassmannPt {
         b[r * P + j] = s;
       }
     }
-    T g[P * P], c[P * P];
-    gram(b, b, g);
-    gram_fn<3>(g, c);
+    // b = us diag(s) vs^T by one-sided (Hestenes) Jacobi on the columns of b -- every singular value to relative
+    // accuracy.  (Going through the Gram matrix b^T b squares the condition number: with tan(angle) ~ 30 for nearly
+    // orthogonal subspaces the small singular values, and with them atan(s)/s, lose 3 digits in fp32.)
+    T v[P * P];
+    GM_UNROLL for (int i = 0; i < P * P; ++i) v[i] = (i / P == i % P) ? (T)1 : (T)0;
+    for (int sweep = 0; sweep < JacobiCfg<T>::max_sweeps + 4; ++sweep) {
+      bool rotated = false;
+      GM_UNROLL for (int p = 0; p < P - 1; ++p) {
+        GM_UNROLL for (int q = p + 1; q < P; ++q) {
+          T alpha = (T)0, beta = (T)0, gamma = (T)0;
+          for (int r = 0; r < n; ++r) {
+            alpha += b[r * P + p] * b[r * P + p];
+            beta += b[r * P + q] * b[r * P + q];
+            gamma += b[r * P + p] * b[r * P + q];
+          }
+          if (Num<T>::abs(gamma) > (Num<T>::eps * (T)0.25) * Num<T>::sqrt(alpha * beta) &&
+              Num<T>::abs(gamma) > Num<T>::tiny) {
+            rotated = true;
+            // exact (not MUFU-approximate) rotation: this is an API op, not the training hot path
+            T zeta = (beta - alpha) / (gamma + gamma);
+            T t = Num<T>::copysign((T)1, zeta) / (Num<T>::abs(zeta) + Num<T>::sqrt((T)1 + zeta * zeta));
+            T cs = (T)1 / Num<T>::sqrt((T)1 + t * t), sn = t * cs;
+            for (int r = 0; r < n; ++r) {
+              T bp = b[r * P + p], bq = b[r * P + q];
+              b[r * P + p] = cs * bp - sn * bq;
+              b[r * P + q] = sn * bp + cs * bq;
+            }
+            GM_UNROLL for (int r = 0; r < P; ++r) {
+              T vp = v[r * P + p], vq = v[r * P + q];
+              v[r * P + p] = cs * vp - sn * vq;
+              v[r * P + q] = sn * vp + cs * vq;
+            }
+          }
+        }
+      }
+      if (!rotated) break;
+    }
+    // out = sum_k (b_k / s_k) atan(s_k) v_k^T  with b_k = u_k s_k the rotated columns
+    T f[P];
+    const T tiny = Num<T>::sqrt(Num<T>::tiny);
+    GM_UNROLL for (int k = 0; k < P; ++k) {
+      T n2 = (T)0;
+      for (int r = 0; r < n; ++r) n2 += b[r * P + k] * b[r * P + k];
+      T sk = Num<T>::sqrt(n2);
+      f[k] = sk > tiny ? Num<T>::atan(sk) / sk : (T)1;
+    }
+    T c[P * P];  // c = diag(f) v^T
+    GM_UNROLL for (int k = 0; k < P; ++k)
+      GM_UNROLL for (int j = 0; j < P; ++j) c[k * P + j] = f[k] * v[j * P + k];
     mulr(b, c, out);
   }
   GM_HD void transp(const T* x, const T* y, const T* u, T* out) const { proju(y, u, out); }  // base.py:65-66

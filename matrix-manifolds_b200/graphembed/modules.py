@@ -107,7 +107,8 @@ class ManifoldEmbedding(EmbeddingBase):
 
 def _softplus_value(scale):
     """float(softplus(scale)) without a device->host read per step: the value is cached on the parameter until it is
-    modified in place (tensor._version changes), i.e. until a curvature optimizer actually steps it."""
+    modified in place (tensor._version changes: torch optimizers) or stepped by RiemannianAdam / RiemannianSGD, whose
+    kernels write through the raw pointer and drop the cache themselves (optim/_common.py::fused_step)."""
     key = (scale._version, scale.data_ptr())  # in-place updates bump the version, `.data = ...` moves the storage
     hit = getattr(scale, '_gm_softplus', None)
     if hit is not None and hit[0] == key:

@@ -30,3 +30,7 @@ def fused_step(param, grad, cfg, buf1=None, buf2=None):
             _ops.optim_step_peer(spec, cfg, arena, param.shape[0], buf1, buf2)
         else:
             _ops.optim_step(spec, cfg, param.data, grad, buf1, buf2)
+    # The kernel wrote through the raw pointer: neither tensor._version nor data_ptr() changed, so anything cached
+    # against them (modules._softplus_value: the host copy of softplus(scale)) must be dropped explicitly.
+    if getattr(param, '_gm_softplus', None) is not None:
+        param._gm_softplus = None

@@ -91,41 +91,62 @@ class PeerArena:
     """
 
     def __init__(self, x, n_acc, group):
+        """Runs all three construction phases back to back (every rank must succeed).  `try_peer_arena` drives the
+        phases one at a time with a status vote in between, so that a failure on ONE rank makes ALL ranks fall back
+        through the same sequence of collectives."""
+        self._init_fields(x, n_acc, group)
+        self.phase_alloc_export(x)
+        self.phase_open(self.exchange_handles())
+        self.phase_finish()
+
+    def _init_fields(self, x, n_acc, group):
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if self.world > L.GM_MAX_PEERS:
-            raise RuntimeError(f'peer update supports up to {L.GM_MAX_PEERS} ranks (one NVLink domain)')
-        if x.shape[0] % self.world != 0:
-            raise RuntimeError(f'{x.shape[0]} rows do not split evenly over {self.world} ranks')
-        self.rows = x.shape[0] // self.world
+        self.base, self._opened, self.peer_base, self._handle = None, [], [], None
+        self.rows = x.shape[0] // max(self.world, 1)
         self.lo, self.hi = self.rank * self.rows, (self.rank + 1) * self.rows
         self.n_acc = n_acc
-        dev = x.device
+        self.dev = x.device
         xb = _align(x.numel() * x.element_size())
         ab = _align(8 * n_acc)
         self.off_x, self.off_g, self.off_acc, self.off_out, self.off_flags = 0, xb, 2 * xb, 2 * xb + ab, 2 * xb + 2 * ab
         self.nbytes = self.off_flags + _align(L.GM_PEER_FLAG_BYTES)
+
+    def phase_alloc_export(self, x):
+        """Phase 1 (local, no collective): allocate the arena, export its IPC handle, move the points in."""
+        if self.world > L.GM_MAX_PEERS:
+            raise RuntimeError(f'peer update supports up to {L.GM_MAX_PEERS} ranks (one NVLink domain)')
+        if x.shape[0] % self.world != 0:
+            raise RuntimeError(f'{x.shape[0]} rows do not split evenly over {self.world} ranks')
         lib = L.lib()
         base = ctypes.c_void_p()
-        with torch.cuda.device(dev):
+        with torch.cuda.device(self.dev):
             L.check(lib.gm_peer_alloc(self.nbytes, ctypes.byref(base)), 'gm_peer_alloc')
             self.base = base.value
             handle = ctypes.create_string_buffer(L.GM_PEER_HANDLE_BYTES)
             L.check(lib.gm_peer_export(ctypes.c_void_p(self.base), handle), 'gm_peer_export')
-        raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=dev)
+        self._handle = handle.raw
+        raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=self.dev)
         self._raw = raw
         nb = x.numel() * x.element_size()
+        n_acc = self.n_acc
         self.x = raw[self.off_x:self.off_x + nb].view(x.dtype).view(x.shape)
         self.grad = raw[self.off_g:self.off_g + nb].view(x.dtype).view(x.shape)
         self.acc = raw[self.off_acc:self.off_acc + 8 * n_acc].view(torch.float64)
         self.acc_out = raw[self.off_out:self.off_out + 8 * n_acc].view(torch.float64)
         self.x.copy_(x)
-        # exchange the IPC handles and map every peer's arena
+
+    def exchange_handles(self):
+        """The one collective between phase 1 and 2; only called once every rank has passed phase 1."""
         handles = [None] * self.world
-        dist.all_gather_object(handles, (os.getpid(), handle.raw), group=group)
+        dist.all_gather_object(handles, (os.getpid(), self._handle), group=self.group)
+        return handles
+
+    def phase_open(self, handles):
+        """Phase 2 (local): map every peer's arena through CUDA IPC and fill the table the kernel walks."""
+        lib = L.lib()
         self.peer_base = []
-        self._opened = []
-        with torch.cuda.device(dev):
+        with torch.cuda.device(self.dev):
             for r, (pid, h) in enumerate(handles):
                 if r == self.rank:
                     self.peer_base.append(self.base)
@@ -138,7 +159,7 @@ class PeerArena:
                 self._opened.append(p.value)
         self.table = L.Peers()
         self.table.world, self.table.rank, self.table.row_lo = self.world, self.rank, self.lo
-        self.table.n_acc = n_acc
+        self.table.n_acc = self.n_acc
         self.table.acc_out = self.base + self.off_out
         for r, b in enumerate(self.peer_base):
             self.table.x[r] = b + self.off_x
@@ -146,8 +167,11 @@ class PeerArena:
             self.table.flags[r] = b + self.off_flags
             self.table.acc[r] = b + self.off_acc
         self.epoch = 0
-        torch.cuda.synchronize(dev)
-        dist.barrier(group=group)  # every arena is zero-filled and mapped before anyone raises a flag
+
+    def phase_finish(self):
+        """Phase 3: only after global success -- every arena is zero-filled and mapped before anyone raises a flag."""
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.group)
 
     def own(self, t):
         return t[self.lo:self.hi]
@@ -168,6 +192,27 @@ class PeerArena:
             self.base = None
 
 
+def run_phases(group, device, phases):
+    """Runs `phases` = [(local_fn, collective_fn or None), ...] in lock step over the ranks of `group`: after every
+    local_fn a MIN all-reduce of a status flag decides whether ALL ranks continue (then collective_fn, if any, runs on
+    all of them) or ALL ranks stop.  A rank whose local_fn raised still takes part in that vote, so every rank
+    executes the same sequence of collectives whether or not it failed.  Returns (ok, first local exception)."""
+    err = None
+    for local_fn, collective_fn in phases:
+        ok = True
+        try:
+            local_fn()
+        except Exception as e:  # noqa: BLE001 -- any failure on any rank => all ranks fall back together
+            err, ok = e, False
+        flag = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            return False, err
+        if collective_fn is not None:
+            collective_fn()
+    return True, None
+
+
 def try_peer_arena(x, n_acc, group):
     """PeerArena if EVERY rank of `group` could allocate, export and map the arenas (NCCL backend, CUDA IPC between
     the processes, at most GM_MAX_PEERS ranks); otherwise None on every rank, and the caller keeps the NCCL
@@ -177,19 +222,17 @@ def try_peer_arena(x, n_acc, group):
     world = dist.get_world_size(group)
     if world < 2 or os.environ.get('GM_PEER_UPDATE', '1') == '0':
         return None
-    arena, err = None, None
-    ok = world <= L.GM_MAX_PEERS and x.shape[0] % world == 0
+    arena = PeerArena.__new__(PeerArena)
+    arena._init_fields(x, n_acc, group)
+    box = {}
+    ok, err = run_phases(group, x.device, [
+        (lambda: arena.phase_alloc_export(x), lambda: box.update(handles=arena.exchange_handles())),
+        (lambda: arena.phase_open(box['handles']), None),
+    ])
     if ok:
-        try:
-            arena = PeerArena(x, n_acc, group)
-        except Exception as e:  # noqa: BLE001 -- any failure on any rank => all ranks fall back together
-            err, ok = e, False
-    flag = torch.tensor([1 if ok else 0], device=x.device, dtype=torch.int32)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    if int(flag.item()) == 1:
+        arena.phase_finish()  # barrier only after global success
         return arena
-    if arena is not None:
-        arena.close()
+    arena.close()
     if err is not None and dist.get_rank(group) == 0:
         import logging
         logging.getLogger(__name__).warning('peer-memory owner update unavailable (%s); using NCCL collectives', err)

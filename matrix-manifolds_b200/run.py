@@ -108,7 +108,14 @@ def main(argv=None):
     engine_cls = TrainingEngine
     if not hasattr(embedding, 'scales'):  # products.Embedding: stabilise every epoch (run.py:74-75)
         from graphembed.products import TrainingEngine as engine_cls
-    if g is not None and n_nodes <= 32768 and not g.is_directed():
+    # gm_rank_metrics sorts one root's N distances inside one SM's shared memory: N <= 32768 with 4-byte keys, 16384
+    # with 8-byte keys (include/gm_kernels.h).  A graph it cannot hold trains without the lazy metric (a warning, not
+    # an abort at the first validation epoch).
+    fp_limit = 32768 if torch.get_default_dtype() == torch.float32 else 16384
+    if g is not None and n_nodes > fp_limit and not g.is_directed():
+        logging.warning('Layer_Mean_F1 skipped: %d nodes exceed the %d-node limit of the GPU ranking kernel for %s',
+                        n_nodes, fp_limit, torch.get_default_dtype())
+    if g is not None and n_nodes <= fp_limit and not g.is_directed():
         from concurrent.futures import Future
         from graphembed.pyx import FastPrecision
         with Timer('constructing FastPrecision', loglevel=logging.INFO):

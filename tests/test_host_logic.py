@@ -105,3 +105,30 @@ def test_fast_precision_surface_and_csr_construction():
     assert rowptr.tolist() == [0, 1, 4, 5, 5, 6] and colidx.tolist() == [1, 0, 2, 4, 1, 1]
     rowptr, colidx = edges_to_csr(3, np.array([[0, 1], [1, 2]]), directed=True)  # in-neighbours of every node
     assert rowptr.tolist() == [0, 0, 1, 2] and colidx.tolist() == [0, 1]
+
+
+def test_softplus_cache_dropped_when_a_riemannian_optimizer_steps_the_scale(monkeypatch):
+    """RiemannianAdam / RiemannianSGD update parameters through a raw-pointer kernel write: neither `_version` nor
+    `data_ptr()` changes, so fused_step itself must invalidate the cached softplus(scale) (round-1 advisor finding:
+    with run_grid.py's `RiemannianAdam([{params: xs}, {params: emb.curvature_params}])` the kernels kept using
+    softplus(0.5) while the scale drifted)."""
+    from graphembed import _ops
+    from graphembed.modules import _softplus_value
+    from graphembed.optim import RiemannianSGD
+
+    def fake_optim_step(spec, cfg, x, grad, buf1, buf2):  # what the kernel does: write through the pointer
+        ptr_before = x.data_ptr()
+        x.view(-1).numpy()[...] -= cfg.lr * grad.view(-1).numpy()
+        assert x.data_ptr() == ptr_before
+
+    monkeypatch.setattr(_ops, 'optim_step', fake_optim_step)
+    s = torch.nn.Parameter(torch.tensor(0.5, dtype=torch.float64))
+    v0 = _softplus_value(s)
+    assert _softplus_value(s) == v0 and s._gm_softplus is not None
+    opt = RiemannianSGD([s], lr=0.1)
+    s.grad = torch.tensor(2.0, dtype=torch.float64)
+    version = s._version
+    opt.step()
+    assert s._version == version  # the update really is invisible to torch's version counter
+    assert abs(float(s) - 0.3) < 1e-12
+    assert abs(_softplus_value(s) - float(torch.nn.functional.softplus(torch.tensor(0.3, dtype=torch.float64)))) < 1e-15

@@ -99,3 +99,65 @@ def test_row_shards_reduce_scatter_all_gather_world2():
         assert p.exitcode == 0
     assert [g[4] for g in got] == [(0, 6), (6, 12)]
     assert all(g[1] and g[2] and g[3] for g in got)
+
+
+def _phases_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, 'matrix-manifolds_b200'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from graphembed.parallel import run_phases
+    log = []
+
+    def fail_on(r, tag):
+        def fn():
+            log.append(tag)
+            if rank == r:
+                raise RuntimeError(f'{tag} failed on rank {rank}')
+        return fn
+
+    def coll(tag):
+        def fn():
+            t = torch.tensor([rank])
+            dist.all_reduce(t)  # a real collective: hangs or mismatches if only some ranks get here
+            log.append(tag)
+        return fn
+
+    res = []
+    # (a) everybody succeeds; (b) rank 1 fails in phase 2 AFTER the first collective; (c) rank 0 fails in phase 1
+    for fail_rank, fail_phase in ((-1, 0), (1, 2), (0, 1)):
+        log.clear()
+        ok, err = run_phases(dist.group.WORLD, torch.device('cpu'), [
+            (fail_on(fail_rank if fail_phase == 1 else -1, 'p1'), coll('c1')),
+            (fail_on(fail_rank if fail_phase == 2 else -1, 'p2'), coll('c2')),
+        ])
+        res.append((ok, None if err is None else str(err), list(log)))
+    t = torch.tensor([1.0])
+    dist.all_reduce(t)  # the group is still in step afterwards
+    out.put((rank, res, float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_phase_vote_keeps_ranks_in_lock_step_when_one_fails():
+    """parallel.run_phases (used by try_peer_arena): a failure on one rank after a collective must not leave the other
+    ranks inside a barrier -- every rank votes after every phase and all of them stop at the same point."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 977) % 2000
+    procs = [ctx.Process(target=_phases_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        rank, res, total = q.get(timeout=120)
+        got[rank] = (res, total)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        res, total = got[rank]
+        assert total == 2.0
+        assert res[0] == (True, None, ['p1', 'c1', 'p2', 'c2'])
+        assert res[1][0] is False and res[1][2] == ['p1', 'c1', 'p2']       # both ranks stop before c2
+        assert (res[1][1] is not None) == (rank == 1)
+        assert res[2][0] is False and res[2][2] == ['p1']                    # both ranks stop before c1
+        assert (res[2][1] is not None) == (rank == 0)
