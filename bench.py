@@ -14,9 +14,14 @@ step     : zero grad -> ONE fused pair kernel (gather + distance + loss + gradie
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs-log2 24] [--nodes 2000000]
 
 `value`  : whole-job pairs/s with the pair batches resident in HBM (CUDA events, max over ranks).
-`e2e`    : same metric through the public API (graphembed.engine.PairTrainer.step_host_grouped) from PINNED HOST
-           buffers: every step uploads its source-grouped (sources, offsets, j | hops << 24) batch -- 4 bytes per
-           pair -- and reads the loss back.
+`e2e`    : same metric through the public API from PINNED HOST buffers.  Default: PairTrainer.step_sampled_host --
+           the step's input is its 1024 BFS source ids (4 KB upload); the 16384 targets per source are DRAWN INSIDE the
+           pair kernel (counter hash of (seed, pair number), GM_PAIRS_SAMPLED) and their hop counts read from the BFS
+           level matrix of those sources, which stays resident in HBM (the landmark set is fixed, BFS once); the loss is
+           read back every step.  --e2e-lists: the round-1 path instead (every step uploads its explicit source-grouped
+           (sources, offsets, j | hops << 24) pair list, 4 bytes per pair).
+`secondary`: (N=1) epoch time of BASELINE configs 1-4 through TrainingEngine on the shipped graphs, each with its
+           roofline and the CPU reference beside it, and the multi-source BFS kernel with a fresh BFS every step.
 `roofline`: fused pair kernel, algorithmic bytes (268 B/pair) / its CUDA-event duration vs the
            measured HBM copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline`: the oracle port (same torch/LAPACK calls as the reference) on the host cores, bounded sample.
@@ -56,9 +61,15 @@ def parse():
                     'of the fused peer-memory kernel (A/B)')
     ap.add_argument('--unpacked', action='store_true', help='separate uint8 hop-count vector instead of the packed '
                     '(j | hops << 24) pair format')
-    ap.add_argument('--workload', default='5', help="--impl reference only: '5' (default, the bench line) or one of "
-                    "1, 2a, 2b, 3a, 3b, 4 -- the CPU epoch time of that BASELINE config (the GPU side of those is "
-                    'tools/bench_configs.py)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='weak: 2^pairs_log2 pairs per GPU per '
+                    'step; strong: 2^pairs_log2 pairs per step in total, split over the GPUs (BASELINE config 5 as '
+                    'written)')
+    ap.add_argument('--e2e-lists', action='store_true', help='end-to-end leg uploads explicit pair lists (4 B/pair) '
+                    'instead of drawing the pairs on the device from the uploaded source ids')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the secondary lines (configs 1-4, BFS)')
+    ap.add_argument('--workload', default='5', help="'5' (default, the bench line) or one of 1, 2a, 2b, 3a, 3b, 4 (or a "
+                    "comma list / 'all'): epoch time of that BASELINE config -- on the GPU through TrainingEngine, or "
+                    "with --impl reference on the host CPU")
     return ap.parse_args()
 
 
@@ -86,7 +97,7 @@ def scale_free_edges(n, m, seed):
     return np.stack([t, target], axis=1)
 
 
-def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
+def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, keep_levels=False, graph=None):
     """[(I int32, J int32, hops uint8, sources int32, offsets int64, J|hops<<24 int32)] pinned host tensors + max
     hop^2; hop targets come from the multi-source BFS kernel.  (sources, offsets) is the source-grouped form of I, the
     last entry the packed 4-byte-per-pair form of (J, hops)."""
@@ -95,13 +106,15 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
     from graphembed import _lib as L
     P = 1 << log2_pairs
     per_src = max(1, P // N_SOURCES)
-    n_src = P // per_src
-    edges = scale_free_edges(n_nodes, 4, seed)
-    rowptr, colidx = edges_to_csr(n_nodes, edges)
-    rp = torch.as_tensor(rowptr, device=device)
-    ci = torch.as_tensor(colidx, device=device)
+    if n_src is None:
+        n_src = P // per_src
+    if graph is None:
+        edges = scale_free_edges(n_nodes, 4, 1234)  # ONE graph for every rank; the ranks differ in what they sample
+        rowptr, colidx = edges_to_csr(n_nodes, edges)
+        graph = (torch.as_tensor(rowptr, device=device), torch.as_tensor(colidx, device=device))
+    rp, ci = graph
     gen = torch.Generator(device='cpu').manual_seed(seed)
-    batches, max_h = [], 0
+    batches, max_h, kept = [], 0, []
     for b in range(n_batches):
         src = torch.randperm(n_nodes, generator=gen)[:n_src].int()
         levels = bfs_levels(rp, ci, sources=src.to(device), device=device, level_bytes=1)  # (n_src, N) uint8
@@ -120,7 +133,11 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed):
         hops_h = hops.cpu()
         batches.append((I.pin_memory(), J.pin_memory(), hops_h.pin_memory(), src.contiguous().pin_memory(),
                         offsets.pin_memory(), pack_hops(J, hops_h).pin_memory()))
+        if keep_levels:
+            kept.append(levels)  # (n_src, N) uint8, resident: the hop counts of this batch's landmark sources
         del levels
+    if keep_levels:
+        return batches, float(max_h * max_h), kept, per_src, graph
     return batches, float(max_h * max_h)
 
 
@@ -158,6 +175,45 @@ class ClockSampler:
         reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].startswith('Active')})
         return {'sm_mhz': int(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': reasons, 'samples': len(sm)}
+
+
+class NvlinkCounter:
+    """NVLink payload bytes of one GPU over a timed region, from the driver's own counters (NVML field
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX summed over the links, KiB): the measured traffic of the fused
+    peer-memory owner update (ncu cannot replay a kernel that handshakes with other ranks)."""
+
+    def __init__(self, index):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.fields = [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
+        except Exception:  # noqa: BLE001 -- counters are optional evidence
+            self.h = None
+
+    def _read(self):
+        try:
+            vals = self.nv.nvmlDeviceGetFieldValues(self.h, [(f, 0xFFFFFFFF) for f in self.fields])  # scope: all links
+            return [int(v.value.ullVal) for v in vals]
+        except Exception:  # noqa: BLE001
+            try:
+                vals = self.nv.nvmlDeviceGetFieldValues(self.h, self.fields)
+                return [int(v.value.ullVal) for v in vals]
+            except Exception:  # noqa: BLE001
+                return None
+
+    def start(self):
+        self.t0 = self._read() if self.h is not None else None
+
+    def stop(self, steps):
+        t1 = self._read() if self.h is not None else None
+        if not self.t0 or not t1:
+            return {'available': False}
+        tx, rx = (t1[0] - self.t0[0]) * 1024, (t1[1] - self.t0[1]) * 1024
+        return {'available': True, 'tx_bytes_per_step': tx / steps, 'rx_bytes_per_step': rx / steps,
+                'source': 'NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX over the device-timed region'}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -281,6 +337,192 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs 1-4 on the GPU: epoch time through the public training API on the shipped graphs
+# ---------------------------------------------------------------------------------------------------------------------
+GPU_CONFIGS = {
+    # tag: (graph, factors, dtype, optimizer, node batch or None, E per factor, flops per pair (SURVEY 8d estimate))
+    '1': ('tree1000', [('spd', dict(n=3))], torch.float64, 'rsgd', None, [9], 900),
+    '2a': ('power', [('lorentz', dict(n=11))], torch.float32, 'radam', 512, [11], None),
+    '2b': ('power', [('spd', dict(n=4, use_stein_div=True))], torch.float32, 'radam', 512, [16], None),
+    '3a': ('facebook', [('grassmann', dict(n=6, p=2))], torch.float64, 'radam', 512, [12], None),
+    '3b': ('facebook', [('spd', dict(n=3)), ('lorentz', dict(n=5))], torch.float32, 'radam', 512, [9, 5], None),
+    '4': ('condmat', [('spd', dict(n=6))], torch.float32, 'radam', None, [36], 7500),
+}
+GRAPH_SIZES = {'tree1000': 1000, 'power': 4941, 'facebook': 4039, 'condmat': 21363}
+# non-tensor vector-pipe peaks of one B200 (148 SMs x 128 FP32 lanes (64 FP64) x 2 flop x 1.965 GHz): the bound of the
+# all-pairs configs, whose traffic per pair is one target value
+FP32_PEAK_TFLOPS, FP64_PEAK_TFLOPS = 74.4, 37.2
+
+
+def load_graph(name):
+    """(n, edges, source): the shipped edge list as the reference's loader numbers it (tests/golden/graphs/*.npz, made
+    from /root/reference/data/<name>.edges.gz by tests/golden/make_golden_r2.py), else a synthetic scale-free graph
+    of the same size -- and says which."""
+    path = os.path.join(ROOT, 'tests', 'golden', 'graphs', f'{name}.npz')
+    if os.path.isfile(path):
+        with np.load(path) as z:
+            return int(z['n']), z['edges'].astype(np.int64), f'data/{name}.edges.gz'
+    n = GRAPH_SIZES[name]
+    return n, scale_free_edges(n, 3, 0), f'synthetic scale-free graph of {n} nodes (shipped edge list not found)'
+
+
+def gpu_config_epoch(tag, epochs, dev, with_cpu=True):
+    """One BASELINE config through TrainingEngine on one GPU: median epoch ms (CUDA-synchronised wall clock around
+    TrainingEngine._train, validation off), pairs/s, the pair kernels' share (CUDA events) and a roofline."""
+    from graphembed import _lib as L, _ops
+    from graphembed import manifolds as M
+    from graphembed.data import bfs_levels, edges_to_csr
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam, RiemannianSGD
+    from graphembed.train import TrainingEngine
+    gname, factors, dtype, opt_name, batch_nodes, E_list, flops_pair = GPU_CONFIGS[tag]
+    n, edges, gsrc = load_graph(gname)
+    prev_dev = torch.empty(0).device
+    torch.set_default_device(dev)  # as run.py does: the per-epoch randperm and its slices stay on the GPU
+    try:
+        torch.manual_seed(42)
+        rowptr, colidx = edges_to_csr(n, edges)
+        levels = bfs_levels(rowptr, colidx, device=dev, level_bytes=1)
+        max_sq = float(levels.max().item()) ** 2
+        dense = torch.empty(n, n, dtype=dtype, device=dev)
+        L.check(L.lib().gm_levels_to_dense_targets(1, L.ptr(levels), n, max_sq, L.dtype_code(dtype), L.ptr(dense),
+                                                   L.stream_ptr(dev)), 'gm_levels_to_dense_targets')
+        del levels
+
+        class DenseDataset:  # GraphDataset (data/dataset.py:9-27) over the already normalised dense target matrix
+            pdists = dense
+            device = dense.device
+
+            def __len__(self):
+                return n
+
+        def mk(fam, kw):
+            return (M.SymmetricPositiveDefinite(**kw) if fam == 'spd' else M.Lorentz(kw['n']) if fam == 'lorentz'
+                    else M.Grassmann(kw['n'], kw['p']))
+
+        emb = ManifoldEmbedding(n, [mk(f, kw) for f, kw in factors], device=dev, dtype=dtype)
+        if opt_name == 'rsgd':
+            opt = RiemannianSGD(emb.xs, lr=0.01, max_grad_norm=20, exact=True)   # run_grid.py:30-33
+        else:
+            opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)  # run_grid.py:25-28
+        os.makedirs('/tmp/bench_configs', exist_ok=True)
+        eng = TrainingEngine(embedding=emb, optimizer=opt, objective_fn=QuotientLoss(), n_epochs=epochs, alpha=1.0,
+                             batch_size=batch_nodes, tensorboard=False, save_dir='/tmp/bench_configs')
+        kernel_events, epoch_ms = [], []
+
+        def timed(fn):
+            def wrapper(*a, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **kw)
+                e1.record()
+                kernel_events.append((e0, e1))
+                return r
+            return wrapper
+
+        saved = (_ops.pairs_loss_fused, _ops.pairs_dist2, _ops.pairs_grad)
+        _ops.pairs_loss_fused, _ops.pairs_dist2, _ops.pairs_grad = (timed(f) for f in saved)
+        orig_train = eng._train
+
+        def timed_train(*a, **kw):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            r = orig_train(*a, **kw)
+            torch.cuda.synchronize(dev)
+            epoch_ms.append((time.perf_counter() - t0) * 1e3)
+            return r
+
+        eng._train = timed_train
+        launches0 = L.launch_count()
+        try:
+            eng(DenseDataset())
+        finally:
+            _ops.pairs_loss_fused, _ops.pairs_dist2, _ops.pairs_grad = saved
+        launches = L.launch_count() - launches0
+        final_loss = float(eng.writer.history['quotient_loss'][-1][1])
+    finally:
+        torch.set_default_device(prev_dev)
+    bs = n if batch_nodes is None else min(n, batch_nodes)
+    sizes = [b for b in (min(bs, n - i) for i in range(0, n, bs)) if b >= 50]
+    pairs = sum(b * (b - 1) // 2 for b in sizes)
+    med = float(np.median(epoch_ms[1:] if len(epoch_ms) > 1 else epoch_ms))
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / max(len(epoch_ms), 1)
+    kernel_basis = 'pair kernel time (CUDA events)'
+    if not kernel_events:  # the whole epoch ran inside ONE native call (gm_train_epoch): kernels back to back
+        kernel_ms, kernel_basis = med, 'epoch time (pair + optimizer kernels enqueued back to back by gm_train_epoch)'
+    s_ = 4 if dtype == torch.float32 else 8
+    bpp = sum(4 * E * s_ for E in E_list) + s_ + 8
+    peak, _ = hbm_peak()
+    hbm = pairs * bpp / (med * 1e-3) / 1e9
+    line = {
+        'workload': f'BASELINE config {tag}', 'graph': gsrc, 'nodes': n, 'dtype': 'f32' if s_ == 4 else 'f64',
+        'factors': [f'{f}{tuple(kw.values())}' for f, kw in factors], 'optimizer': opt_name, 'batch_nodes': batch_nodes,
+        'steps_per_epoch': len(sizes), 'pairs_per_epoch': pairs, 'epoch_ms': med, 'pairs_per_s': pairs / (med * 1e-3),
+        'pair_kernels_ms_per_epoch': kernel_ms, 'gpu_launches_per_epoch': launches / max(len(epoch_ms), 1),
+        'final_loss': final_loss,
+        'roofline': {'bound': 'hbm', 'achieved': hbm, 'peak': peak, 'unit': 'GB/s', 'frac': hbm / peak,
+                     'bytes_per_pair': bpp, 'basis': 'whole epoch (pair + optimizer kernels + launch gaps)'},
+    }
+    if flops_pair:  # all-pairs configs: the vector pipe is the bound (SURVEY 8d), flops per pair are SURVEY's estimate
+        vpeak = FP32_PEAK_TFLOPS if s_ == 4 else FP64_PEAK_TFLOPS
+        ach = pairs * flops_pair / (kernel_ms * 1e-3) / 1e12
+        line['roofline_vector_pipe'] = {'bound': 'fp32_pipe' if s_ == 4 else 'fp64_pipe', 'achieved': ach, 'peak': vpeak,
+                                        'unit': 'TFLOP/s', 'frac': ach / vpeak, 'flops_per_pair_estimate': flops_pair,
+                                        'basis': kernel_basis}
+    if with_cpu:
+        c = cpu_config_epoch(tag, 1, 1 if tag in ('1', '2a', '3a', '3b') else 0)
+        line['cpu_baseline'] = {'value': c['epoch_ms'], 'unit': 'ms/epoch', 'cores': c['cores'], 'kind': 'port',
+                                'sample': c['sample']}
+        line['speedup_vs_cpu'] = c['epoch_ms'] / med
+    del eng, emb, dense
+    torch.cuda.empty_cache()
+    return line
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(peaks_path):
+        return json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def bfs_secondary(graph, n_nodes, dev, reps=5):
+    """The multi-source BFS kernel with a FRESH BFS every step: 1024 new random sources of the 2 M-node bench graph
+    per call, CUDA events around each call."""
+    from graphembed.data import bfs_levels
+    rp, ci = graph
+    gen = torch.Generator().manual_seed(99)
+    times, depth = [], 0
+    for k in range(reps + 1):
+        src = torch.randperm(n_nodes, generator=gen)[:N_SOURCES].int().to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lv = bfs_levels(rp, ci, sources=src, device=dev, level_bytes=1)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if k:
+            times.append(e0.elapsed_time(e1))
+        depth = max(depth, int(lv.max().item()))
+        del lv
+    ms = float(np.median(times))
+    m_edges = int(ci.numel())
+    # algorithmic bytes of one BFS of S sources: the (S, N) uint8 level matrix written once, plus per level one pass
+    # over the CSR arrays and the W = S/64 frontier words of every node read + the visited/next words read-modify-written
+    W = N_SOURCES // 64
+    per_level = m_edges * 4 + (n_nodes + 1) * 4 + n_nodes * W * 8 * 3
+    alg = N_SOURCES * n_nodes + (depth + 1) * per_level
+    peak, src_ = hbm_peak()
+    return {'workload': f'multi-source BFS, {N_SOURCES} fresh sources per call on the {n_nodes}-node bench graph '
+                        f'({m_edges} directed edges, depth {depth})', 'ms_per_call': ms,
+            'source_node_levels_per_s': N_SOURCES * n_nodes / (ms * 1e-3),
+            'roofline': {'bound': 'hbm', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': alg / (ms * 1e-3) / 1e9 / peak, 'algorithmic_bytes_per_call': alg,
+                         'basis': 'level matrix written once + per level: CSR read, frontier words read, visited and '
+                                  'next words updated'}}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -292,6 +534,14 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
+    if args.workload != '5':  # one JSON line per requested BASELINE config (GPU arm), rank 0 only
+        if rank == 0:
+            tags = list(GPU_CONFIGS) if args.workload == 'all' else args.workload.split(',')
+            for tag in tags:
+                print(json.dumps({'metric': 'epoch_time', 'unit': 'ms', 'higher_is_better': False, 'n_gpus': 1,
+                                  **gpu_config_epoch(tag, max(3, min(args.steps, 6)), dev,
+                                                     with_cpu=not args.no_cpu_baseline)}), flush=True)
+        return
     pg = None
     if args.no_peer:
         os.environ['GM_PEER_UPDATE'] = '0'
@@ -308,12 +558,16 @@ def main():
     from graphembed.optim import RiemannianAdam
 
     torch.manual_seed(42)  # identical replicas on every rank
-    N, P = args.nodes, 1 << args.pairs_log2
+    N, P_full = args.nodes, 1 << args.pairs_log2
+    strong = args.scaling == 'strong' and world > 1
+    n_src = N_SOURCES // world if strong else N_SOURCES  # strong: the step's 1024 sources are split over the ranks
     man = SymmetricPositiveDefinite(4)
     emb = ManifoldEmbedding(N, [man], device=dev, dtype=torch.float32)
     opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
-    # weak scaling: every rank draws its own 2^24-pair batches (different seed), embeddings replicated
-    batches, max_sq = make_pair_batches(N, args.pairs_log2, args.batches, dev, seed=1234 + rank)
+    # every rank draws its own batches (different seed) on the same graph; embeddings replicated
+    batches, max_sq, levels, per_src, graph = make_pair_batches(N, args.pairs_log2, args.batches, dev, seed=1234 + rank,
+                                                                n_src=n_src, keep_levels=True)
+    P = n_src * per_src  # pairs per step on this rank
     if pg is not None:
         m = torch.tensor([max_sq], device=dev)
         torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MAX)
@@ -362,10 +616,13 @@ def main():
     if world > 1:
         trainer.opt.step = timed_update
     clocks = ClockSampler(local)
+    nvl = NvlinkCounter(local) if world > 1 else None
     barrier()
     if rank == 0:
         clocks.start()
     launches0 = _lib.launch_count()
+    if nvl:
+        nvl.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     loss = None
@@ -373,6 +630,7 @@ def main():
         loss = trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
     t1.record()
     barrier()
+    nvlink = nvl.stop(args.steps) if nvl else None
     launches = _lib.launch_count() - launches0
     _ops.pairs_loss_fused = orig
     trainer.opt.step = opt_step
@@ -382,28 +640,43 @@ def main():
     final_loss = float(loss.item())
 
     # ---- end-to-end timing from pinned host buffers ----------------------------------------------------------------
-    # source-grouped upload (sources, offsets, j, hops): 5 B/pair over PCIe; the next batch is uploaded on a second
-    # stream while this one computes; every step ends with a device->host read of the loss
-    def grouped(b):
-        return (b[3], b[4], b[1], b[2]) if args.unpacked else (b[3], b[4], b[5], None)
-
     nb = len(batches)
+    if args.e2e_lists:
+        # source-grouped upload (sources, offsets, j, hops): 4-5 B/pair over PCIe; the next batch is uploaded on a
+        # second stream while this one computes; every step ends with a device->host read of the loss
+        def grouped(b):
+            return (b[3], b[4], b[1], b[2]) if args.unpacked else (b[3], b[4], b[5], None)
+
+        def e2e_step(k):
+            return trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1,
+                                             next_batch=grouped(batches[(k + 1) % nb]), defer_loss=True)
+        h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
+        e2e_api = ('graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
+                   + ('int32 j, uint8 hops' if args.unpacked else 'int32 j | hops << 24') + '; per rank); next batch '
+                   'uploaded on a second stream, loss read back through pinned memory one step late')
+    else:
+        # the step's input is its list of BFS sources: 4 KB from pinned host memory per step; targets are drawn inside
+        # the pair kernel, hop counts come from the resident level matrix of the batch's landmark sources
+        def e2e_step(k):
+            return trainer.step_sampled_host(batches[k % nb][3], levels[k % nb], per_src, seed=(0xB200 << 32) + k,
+                                             epoch=1, defer_loss=True)
+        h2d_bytes = batches[0][3].numel() * 4
+        e2e_api = ('graphembed.engine.PairTrainer.step_sampled_host (pinned host int32 source ids of the step; '
+                   f'{per_src} targets per source drawn inside the pair kernel from the counter hash of (seed, pair '
+                   'number), hop counts from the HBM-resident BFS level matrix of the landmark sources); loss read back '
+                   'through pinned memory one step late')
     for k in range(2):
-        trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1, next_batch=grouped(batches[(k + 1) % nb]))
+        e2e_step(k)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    host_losses = []
-    for k in range(args.steps):
-        host_losses.append(trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1,
-                                                     next_batch=grouped(batches[(k + 1) % nb]), defer_loss=True))
+    host_losses = [e2e_step(k) for k in range(args.steps)]
     host_losses.append(trainer.flush_loss())  # every step's loss reaches the host, one step late
     e1.record()
     barrier()
     assert all(v is not None and np.isfinite(v) for v in host_losses[1:]), host_losses
     ms_e2e = e0.elapsed_time(e1)
     clock_info = clocks.stop() if rank == 0 else None  # sampled over both timed regions
-    h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
 
     if pg is not None:
         t = torch.tensor([ms, ms_e2e, pair_ms], device=dev, dtype=torch.float64)
@@ -414,11 +687,7 @@ def main():
             torch.distributed.destroy_process_group()
         return
 
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.isfile(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    peak, peak_src = hbm_peak()
     achieved = P * BYTES_PER_PAIR / (pair_ms * 1e-3) / 1e9
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
     tpath = os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json')
@@ -427,11 +696,13 @@ def main():
     total_pairs = P * world * args.steps
     line = {
         'metric': METRIC, 'value': total_pairs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {
             'workload': 'BASELINE config 5: synthetic scale-free graph, SPD 4x4 affine-invariant, sampled pairs '
-                        '(1024 BFS sources x targets) per step, QuotientLoss, RiemannianAdam(lr .01, clip 100, exact)',
+                        f'({N_SOURCES} BFS sources x targets per step' + (' in total, sources split over the GPUs'
+                                                                         if strong else ' per GPU')
+                        + '), QuotientLoss, RiemannianAdam(lr .01, clip 100, exact)',
             'nodes': N, 'pairs_per_step_per_gpu': P, 'parallelism': f'pair-sharded x{world}'
             + (' + ONE fused kernel over NVLink peer memory: pull+sum the owned (N/G,4,4) gradient rows from every '
                'rank, optimizer update, push the new rows to every rank (gm_optim_step_peer, no NCCL on the step path)'
@@ -443,12 +714,10 @@ def main():
                          f'{N * 64 / 1e6:.0f} MB embedding + {N * 64 / 1e6:.0f} MB gradient touched at random',
             'final_loss': final_loss,
             **({'optimizer_call_ms_rank0': upd_ms} if upd_ms is not None else {}),
+            **({'nvlink_rank0': nvlink} if nvlink is not None else {}),
         },
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
-                'd2h_bytes_per_step': 16, 'ms_per_step': ms_e2e / args.steps,
-                'api': 'graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
-                       + ('int32 j, uint8 hops' if args.unpacked else 'int32 j | hops << 24') + '; per rank); next batch '
-                       'uploaded on a second stream, loss read back through pinned memory one step late'},
+                'd2h_bytes_per_step': 16, 'ms_per_step': ms_e2e / args.steps, 'api': e2e_api},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': 'spd_pair_stream_kernel<SpdAI<float,4>,K_FUSED>',
@@ -458,6 +727,12 @@ def main():
     if not args.no_cpu_baseline:
         rate, med, cores, sample = cpu_step_rate(args.cpu_pairs_log2, 3, 1)
         line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+    if world == 1 and not args.no_secondary:
+        del trainer, emb, dev_batches, levels
+        torch.cuda.empty_cache()
+        sec = {'bfs': bfs_secondary(graph, N, dev)}
+        sec['configs'] = [gpu_config_epoch(tag, 4, dev, with_cpu=not args.no_cpu_baseline) for tag in GPU_CONFIGS]
+        line['secondary'] = sec
     print(json.dumps(line))
     if pg is not None:
         torch.distributed.destroy_process_group()

@@ -76,9 +76,18 @@ typedef struct gm_manifold {
 enum gm_pairs_mode {
   GM_PAIRS_ELEMENTWISE = 0, /* pair k = (xa[k], xb[k])                       -- Manifold.dist(x, y)  (base.py:56-57)        */
   GM_PAIRS_LIST = 1,        /* pair k = (xa[idx_i[k]], xb[idx_j[k]])         -- dist(x[I], x[J]) incl. the gather           */
-  GM_PAIRS_TRIU = 2         /* pair k = (k0+k)-th (a<b) of triu_indices(B,B,1), rows
+  GM_PAIRS_TRIU = 2,        /* pair k = (k0+k)-th (a<b) of triu_indices(B,B,1), rows
                                xa[nodes[a]], xb[nodes[b]] (nodes NULL: a, b) -- Manifold.pdist (base.py:59-63) fused with
                                                                                 x[indices] (modules.py:84-88)              */
+  GM_PAIRS_SAMPLED = 3      /* pairs DRAWN ON THE DEVICE (new capability: BASELINE config 5 "sampled pairs"; the reference
+                               only enumerates all pairs of a node batch, train.py:206-213).  Pair k belongs to source
+                               group g = k / per_src:  i = idx_i[g] (int32 node id of the BFS source),
+                               j = the gm_sample_j(seed, k, i, n_nodes)-th node != i (counter-based: the same (seed, k)
+                               always gives the same j, on any grid -- oracle/sampler_oracle.py is the host statement),
+                               hop = levels[slot_g * n_nodes + j] with slot_g = slots ? slots[g] : g.
+                               The kernels see the pair as the packed word (hop << 24) | j, i.e. exactly a LIST pair with
+                               GM_TGT_HOPS_PACKED targets, but nothing per pair is uploaded or read from memory: a step
+                               uploads the G source ids.  Needs n_nodes < 2^24, hop counts < 255 (uint8 levels).      */
 };
 
 typedef struct gm_pairs {
@@ -92,7 +101,18 @@ typedef struct gm_pairs {
   int64_t k0;        /* TRIU: first pair of the triangle covered by this launch (0 for the whole triangle); per-pair
                         vectors (out_d2, gout, VECTOR / HOPS targets) are indexed by the LOCAL pair number 0..P-1.
                         A rank of a pair-sharded job passes its slice [k0, k0+P) */
+  /* GM_PAIRS_SAMPLED only (zero otherwise) */
+  const void* levels; /* uint8 (S, n_nodes) hop counts from gm_bfs_multi_source, resident on the device */
+  const void* slots;  /* int32 (G): row of `levels` that belongs to group g; NULL: row g                */
+  int64_t n_nodes;    /* rows of the point table == columns of `levels`                                 */
+  int64_t per_src;    /* targets drawn per source; G = ceil(P / per_src)                                */
+  uint64_t seed;      /* stream id of this step's draws (the caller mixes its seed with the step number) */
 } gm_pairs_t;
+
+/* The draw of GM_PAIRS_SAMPLED, stated once so that host code can reproduce a step's pairs bit for bit:
+ *   z = seed + (k + 1) * 0x9E3779B97F4A7C15;  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9;
+ *   z = (z ^ (z >> 27)) * 0x94D049BB133111EB;  z ^= z >> 31;          (the splitmix64 output function, mod 2^64)
+ *   r = z >> 32;  j = (r * (n_nodes - 1)) >> 32;  if (j >= i) j += 1;  (uniform over the n_nodes - 1 nodes != i)      */
 
 /* Loss on (graph target g, manifold squared distance m) -- objectives.py:16-45. */
 enum gm_loss_kind { GM_LOSS_QUOTIENT = 0, GM_LOSS_STRESS = 1 };
@@ -115,7 +135,8 @@ enum gm_target_mode {
   GM_TGT_HOPS_U16 = 3,
   GM_TGT_HOPS_PACKED = 4 /* LIST pairs with int32 indices only: the hop count rides in the top 8 bits of idx_j[k]
                             (row = idx_j[k] & 0xFFFFFF, h = idx_j[k] >> 24; needs < 2^24 rows); `data` is ignored.
-                            One 4-byte word per pair instead of 5 bytes to upload and read (gm_pairs_loss_fused only) */
+                            One 4-byte word per pair instead of 5 bytes to upload and read (gm_pairs_loss_fused only).
+                            Also the target mode of GM_PAIRS_SAMPLED pairs, whose packed word is computed on the fly */
 };
 typedef struct gm_targets {
   int32_t mode;

@@ -24,6 +24,10 @@ int validate_pairs(const gm_pairs_t* p) {
       if (p->B < 0 || p->k0 < 0) return GM_EINVAL;
       if (p->k0 + p->P > p->B * (p->B - 1) / 2) return GM_EINVAL;
       return GM_OK;
+    case GM_PAIRS_SAMPLED:
+      if (p->idx64 || p->per_src < 1 || p->n_nodes < 2 || p->n_nodes >= (1LL << 24)) return GM_EINVAL;
+      if (p->P > 0 && (!p->idx_i || !p->levels)) return GM_ENULL;
+      return GM_OK;
     default:
       return GM_EINVAL;
   }
@@ -221,7 +225,8 @@ int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_
   if (pairs->mode == GM_PAIRS_ELEMENTWISE) return GM_EINVAL;
   if (targets->mode < GM_TGT_VECTOR || targets->mode > GM_TGT_HOPS_PACKED) return GM_EINVAL;
   const bool packed = targets->mode == GM_TGT_HOPS_PACKED;
-  if (packed && (pairs->mode != GM_PAIRS_LIST || pairs->idx64)) return GM_EINVAL;
+  if (packed && ((pairs->mode != GM_PAIRS_LIST && pairs->mode != GM_PAIRS_SAMPLED) || pairs->idx64)) return GM_EINVAL;
+  if (pairs->mode == GM_PAIRS_SAMPLED && !packed) return GM_EINVAL;  // drawn pairs bring their hop count with them
   if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
   if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
   if (pairs->P == 0) return GM_OK;

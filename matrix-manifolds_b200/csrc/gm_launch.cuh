@@ -20,6 +20,12 @@ struct PairSpec {
   const void* nodes;
   long long k0;    // TRIU: triangle index of local pair 0
   unsigned jmask;  // LIST + int32: row = idx_j[k] & jmask (0xFFFFFF when hop counts ride in the top byte)
+  // SAMPLED
+  const unsigned char* levels;
+  const int* slots;
+  long long n_nodes, per_src;
+  unsigned long long seed;
+  int per_shift;  // log2(per_src) if it is a power of two, else -1
 };
 struct TargetSpec {
   int mode;
@@ -34,6 +40,15 @@ inline PairSpec make_pairs(const gm_pairs_t* p) {
   s.idx_i = p->idx_i; s.idx_j = p->idx_j; s.nodes = p->nodes;
   s.k0 = (p->mode == GM_PAIRS_TRIU) ? p->k0 : 0;
   s.jmask = 0xffffffffu;
+  s.levels = nullptr; s.slots = nullptr; s.n_nodes = 0; s.per_src = 1; s.seed = 0; s.per_shift = 0;
+  if (p->mode == GM_PAIRS_SAMPLED) {
+    s.levels = (const unsigned char*)p->levels; s.slots = (const int*)p->slots;
+    s.n_nodes = p->n_nodes; s.per_src = p->per_src; s.seed = p->seed;
+    s.jmask = 0x00ffffffu;
+    s.per_shift = -1;
+    for (int b = 0; b < 62; ++b)
+      if (p->per_src == (1LL << b)) s.per_shift = b;
+  }
   return s;
 }
 inline TargetSpec make_targets(const gm_targets_t* t) {
@@ -100,10 +115,32 @@ __device__ __forceinline__ void triu_decode(long long k, long long B, long long&
   b = k - triu_row_start(r, B) + r + 1;
 }
 
+// GM_PAIRS_SAMPLED: source row of pair k and the packed word (hop << 24) | j of its drawn target
+// (include/gm_kernels.h states the draw; oracle/sampler_oracle.py restates it on the host).
+__host__ __device__ __forceinline__ unsigned sample_hash32(unsigned long long seed, unsigned long long k) {
+  unsigned long long z = seed + (k + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned)(z >> 32);
+}
+__device__ __forceinline__ unsigned sampled_word(const PairSpec& ps, long long k, long long& ra) {
+  const long long g = ps.per_shift >= 0 ? (k >> ps.per_shift) : (k / ps.per_src);
+  const unsigned i = (unsigned)((const int*)ps.idx_i)[g];
+  const long long slot = ps.slots ? (long long)ps.slots[g] : g;
+  unsigned j = __umulhi(sample_hash32(ps.seed, (unsigned long long)k), (unsigned)(ps.n_nodes - 1));
+  j += (j >= i) ? 1u : 0u;
+  const unsigned hop = ps.levels[slot * ps.n_nodes + j];
+  ra = (long long)i;
+  return (hop << 24) | j;
+}
+
 // rows of xa / xb touched by pair k (also the rows gradients go to)
 __device__ __forceinline__ void decode_pair(const PairSpec& ps, long long k, long long& ra, long long& rb) {
   if (ps.mode == GM_PAIRS_ELEMENTWISE) {
     ra = k; rb = k;
+  } else if (ps.mode == GM_PAIRS_SAMPLED) {
+    rb = (long long)(sampled_word(ps, k, ra) & 0x00ffffffu);
   } else if (ps.mode == GM_PAIRS_LIST) {
     ra = load_index(ps.idx_i, k, ps.idx64);
     rb = ps.idx64 ? ((const long long*)ps.idx_j)[k] : (long long)(((const unsigned*)ps.idx_j)[k] & ps.jmask);
@@ -124,6 +161,18 @@ __device__ __forceinline__ T fetch_target(const TargetSpec& tg, long long k, lon
         : (tg.mode == GM_TGT_HOPS_U16) ? (T)((const unsigned short*)tg.data)[k]
                                        : (T)(((const unsigned*)tg.data)[k] >> 24);  // HOPS_PACKED: data == idx_j
   return (h * h) / (T)tg.max_sq;  // pow(2) then div_(max): dataset.py:11-12
+}
+
+// fetch_target for kernels that enumerate pairs themselves: SAMPLED pairs carry their hop count in the drawn word
+template <typename T>
+__device__ __forceinline__ T fetch_target_ps(const PairSpec& ps, const TargetSpec& tg, long long k, long long ra,
+                                             long long rb) {
+  if (ps.mode == GM_PAIRS_SAMPLED && tg.mode == GM_TGT_HOPS_PACKED) {
+    long long dummy;
+    T h = (T)(sampled_word(ps, k, dummy) >> 24);
+    return (h * h) / (T)tg.max_sq;
+  }
+  return fetch_target<T>(tg, k, ra, rb);
 }
 
 // m_k = sum_f sp_f * d2_f[k]: sum() of a Python list starts from int 0 and adds left to right (modules.py:84-88)

@@ -224,12 +224,15 @@ struct SpdAI {
     GM_UNROLL for (int i = 0; i < N; ++i)
       GM_UNROLL for (int j = 0; j <= i; ++j) ap[i * (i + 1) / 2 + j] = ic.a[i * N + j];
   }
-  GM_HD T eig_forward(const T (&a)[E], const T (&y)[E], EigState& st) const {
+  // max_sweeps / converged: see jacobi_eigh.  With the default cap `converged` is of no interest.
+  GM_HD T eig_forward(const T (&a)[E], const T (&y)[E], EigState& st, int max_sweeps = JacobiCfg<T>::max_sweeps,
+                      bool* converged = nullptr) const {
     T m[E], w[N];
     congr_lower<T, N>(a, y, m);
     GM_UNROLL for (int i = 0; i < N; ++i)
       GM_UNROLL for (int j = 0; j < N; ++j) st.wm[i * N + j] = (j >= i) ? a[j * N + i] : (T)0;
-    jacobi_eigh<T, N, true, false>(m, st.wm, w);
+    const bool conv = jacobi_eigh<T, N, true, false>(m, st.wm, w, max_sweeps);
+    if (converged) *converged = conv;
     T phi = (T)0;
     // log_pos needs a positive normal finite argument: guaranteed by the clamp for every sane [wmin, wmax]
     // (default [1e-8, 1e8]); a caller-supplied wmin below the smallest normal is raised to it.
@@ -244,11 +247,12 @@ struct SpdAI {
     }
     return clamp_min(phi, wmin);
   }
-  GM_HD T eig_forward_prepped(const T (&ap)[kPrepSize], const T (&y)[E], EigState& st) const {
+  GM_HD T eig_forward_prepped(const T (&ap)[kPrepSize], const T (&y)[E], EigState& st,
+                              int max_sweeps = JacobiCfg<T>::max_sweeps, bool* converged = nullptr) const {
     T a[E];
     GM_UNROLL for (int i = 0; i < N; ++i)
       GM_UNROLL for (int j = 0; j < N; ++j) a[i * N + j] = (j <= i) ? ap[i * (i + 1) / 2 + j] : (T)0;
-    return eig_forward(a, y, st);
+    return eig_forward(a, y, st, max_sweeps, converged);
   }
   GM_HD void eig_backward(const EigState& st, T wgt, T (&gx)[E], T (&gy)[E]) const {
     T cx[N], cy[N];
@@ -327,7 +331,7 @@ struct SpdStein {
   T wmin, wmax;
   struct EigState {};
   GM_HD void prep(const T (&)[E], T (&)[1]) const {}
-  GM_HD T eig_forward_prepped(const T (&)[1], const T (&)[E], EigState&) const { return (T)0; }
+  GM_HD T eig_forward_prepped(const T (&)[1], const T (&)[E], EigState&, int = 0, bool* = nullptr) const { return (T)0; }
   GM_HD void eig_backward(const EigState&, T, T (&)[E], T (&)[E]) const {}
 
   template <bool WANT_INV>
@@ -570,9 +574,23 @@ struct VecMan {
       co.p1 = co.zA * gz; co.p2 = (T)2 * g_x2; co.p3 = g_xy;
       co.q1 = co.zB * gz; co.q2 = (T)2 * g_y2;
       // d(d^2)/dc: through A, B, D and through sqrt|c| (u = sc r and the 2/sc factor)
+      // The explicit part is 2 d * sgn(c) h(u) / sc^3 with u = sc r and h(u) = u phi'(u) - phi(u): for small u both
+      // terms of h are ~u and their difference ~(2/3) u^3, so the closed form loses log10(1/u^2) digits (all of them
+      // in fp32 at the default init, |c| r^2 ~ 1e-6).  There h is summed as its power series, which in w = c r^2 is
+      // sgn(c) h / sc^3 = r^3 sum_{k>=1} 2k/(2k+1) w^(k-1), valid for either sign of c.  fp32 only: in fp64 the closed
+      // form is evaluated exactly as the reference's autograd evaluates it, so that the two agree to 1e-10 (the
+      // reference's own fp64 value carries the cancellation noise, ~1e-9 relative at the default init).
       const T sgn = cc > (T)0 ? (T)1 : (T)-1;
-      co.dc = dA * (y2 - (T)2 * xy) - dB * x2 + dD * ((T)2 * cc * x2 * y2 - (T)2 * xy) +
-              ((T)4 * d * dphi * r - (T)2 * d2) / sc * (sgn * (T)0.5 / sc);
+      const T w = cc * r2;
+      T explicit_c;
+      if (sizeof(T) == 4 && Num<T>::abs(w) < (T)0.1) {
+        T sres = (T)0;
+        GM_UNROLL for (int k = 8; k >= 1; --k) sres = sres * w + (T)(2.0 * k / (2.0 * k + 1.0));
+        explicit_c = (T)2 * d * r * r2 * sres;
+      } else {
+        explicit_c = ((T)4 * d * dphi * r - (T)2 * d2) / sc * (sgn * (T)0.5 / sc);
+      }
+      co.dc = dA * (y2 - (T)2 * xy) - dB * x2 + dD * ((T)2 * cc * x2 * y2 - (T)2 * xy) + explicit_c;
       return clamp_min(d2, eps);
     }
   }

@@ -85,7 +85,7 @@ template <> struct Num<float> {
   //   t = sgn(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2))   (smaller root; a_pq == 0 -> t == 0)
   GM_HD static void rotation(float d, float apq, float& t, float& c, float& s) {
     float two = apq + apq;
-    float h2 = fmaxf(fmaf(two, two, d * d), FLT_MIN);
+    float h2 = fmaf(two, two, fmaf(d, d, FLT_MIN));  // + FLT_MIN: d == a_pq == 0 must give t == 0, not 0 * inf
     float h = h2 * rsqrt_raw(h2);
     float den = fabsf(d) + h;
     t = mul_sign(two, d) * rcp_raw(den);
@@ -336,19 +336,22 @@ struct JacobiFirstCheck { static constexpr int value = N >= 4 ? 3 : (N == 3 ? 2 
 
 // INIT_V: start from v = I (eigenvectors).  With INIT_V == false the caller passes any matrix B in v and gets
 // B * V back -- the pair kernels pass L^-T so that W = L^-T V comes out of the sweeps directly.
+// max_sweeps (<= JacobiCfg<T>::max_sweeps) caps the number of sweeps; the return value says whether the convergence
+// test passed (always evaluated once the cap is reached, so a caller can run a fixed number of sweeps and hand the
+// few matrices that need more to a second pass -- the streaming pair kernel does, see gm_pairs_spd.cu).
 template <typename T, int N, bool WANT_V = true, bool INIT_V = true>
-GM_HD void jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N]) {
+GM_HD bool jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N], int max_sweeps = JacobiCfg<T>::max_sweeps) {
   if (WANT_V && INIT_V) {
     GM_UNROLL for (int i = 0; i < N; ++i)
       GM_UNROLL for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? (T)1 : (T)0;
   }
-  if (N == 1) { w[0] = a[0]; return; }
+  if (N == 1) { w[0] = a[0]; return true; }
   auto rotate = [&](const int p, const int q) {
     T apq = a[p * N + q];
     T t, c, s;
     Num<T>::rotation(a[q * N + q] - a[p * N + p], apq, t, c, s);
-    a[p * N + p] -= t * apq;
-    a[q * N + q] += t * apq;
+    a[p * N + p] = Num<T>::fma(-t, apq, a[p * N + p]);
+    a[q * N + q] = Num<T>::fma(t, apq, a[q * N + q]);
     a[p * N + q] = (T)0;
     a[q * N + p] = (T)0;
     GM_UNROLL for (int r = 0; r < N; ++r) {
@@ -368,15 +371,17 @@ GM_HD void jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N]) {
       }
     }
   };
-  for (int sweep = 0; sweep < JacobiCfg<T>::max_sweeps; ++sweep) {
-    if (sweep >= JacobiFirstCheck<N>::value) {
+  bool converged = false;
+  for (int sweep = 0;; ++sweep) {
+    if (sweep >= JacobiFirstCheck<N>::value || sweep >= max_sweeps) {
       T off = (T)0, dia = (T)0;
       GM_UNROLL for (int i = 0; i < N; ++i) {
         dia += a[i * N + i] * a[i * N + i];
         GM_UNROLL for (int j = i + 1; j < N; ++j) off += a[i * N + j] * a[i * N + j];
       }
       // converged when the off-diagonal mass is below rounding level of the diagonal
-      if (off <= (Num<T>::eps * Num<T>::eps * (T)0.0625) * dia || off < Num<T>::tiny) break;
+      converged = off <= (Num<T>::eps * Num<T>::eps * (T)0.0625) * dia || off < Num<T>::tiny;
+      if (converged || sweep >= max_sweeps) break;
     }
     if constexpr (N == 4) {
       rotate(0, 1); rotate(2, 3);
@@ -388,6 +393,7 @@ GM_HD void jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N]) {
     }
   }
   GM_UNROLL for (int i = 0; i < N; ++i) w[i] = a[i * N + i];
+  return converged;
 }
 
 // ---------------------------------------------------------------------------

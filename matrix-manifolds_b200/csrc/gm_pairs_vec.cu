@@ -47,7 +47,7 @@ vec_pair_kernel(VecMan<T, KIND> op, int n, PairSpec ps, const T* __restrict__ xa
     } else if constexpr (KMODE == K_BWD) {
       w = coef * gout[k];
     } else {
-      T g = fetch_target<T>(tg, k, ra, rb);
+      T g = fetch_target_ps<T>(ps, tg, k, ra, rb);
       T m = scale_sp * d2;
       T dm;
       T lv = loss_term<T>(lc, g, m, dm);
@@ -153,7 +153,7 @@ grassmann_pair_kernel(GrassmannCore<T, P, FAST> op, int n, PairSpec ps, const T*
     } else if constexpr (KMODE == K_BWD) {
       w = coef * gout[k];
     } else {
-      T g = fetch_target<T>(tg, k, ra, rb);
+      T g = fetch_target_ps<T>(ps, tg, k, ra, rb);
       T m = scale_sp * d2;
       T dm;
       T lv = loss_term<T>(lc, g, m, dm);

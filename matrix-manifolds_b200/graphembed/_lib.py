@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get('GM_B200_LIB') or os.path.join(os.path.dirname(_HERE),
 GM_F32, GM_F64 = 0, 1
 GM_SPD_AI, GM_SPD_STEIN, GM_LORENTZ, GM_SPHERE, GM_GRASSMANN, GM_EUCLIDEAN, GM_UNIVERSAL = range(7)
 GM_FAST_EIG, GM_FAST_CHOL, GM_FAST_SVD = 1, 2, 4
-GM_PAIRS_ELEMENTWISE, GM_PAIRS_LIST, GM_PAIRS_TRIU = 0, 1, 2
+GM_PAIRS_ELEMENTWISE, GM_PAIRS_LIST, GM_PAIRS_TRIU, GM_PAIRS_SAMPLED = 0, 1, 2, 3
 GM_LOSS_QUOTIENT, GM_LOSS_STRESS = 0, 1
 GM_TGT_VECTOR, GM_TGT_DENSE, GM_TGT_HOPS_U8, GM_TGT_HOPS_U16, GM_TGT_HOPS_PACKED = 0, 1, 2, 3, 4
 GM_OPT_RSGD, GM_OPT_RADAM = 0, 1
@@ -37,7 +37,10 @@ class Manifold(ctypes.Structure):
 class Pairs(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('idx64', ctypes.c_int32), ('P', ctypes.c_int64),
                 ('idx_i', ctypes.c_void_p), ('idx_j', ctypes.c_void_p), ('B', ctypes.c_int64),
-                ('nodes', ctypes.c_void_p), ('k0', ctypes.c_int64)]
+                ('nodes', ctypes.c_void_p), ('k0', ctypes.c_int64),
+                # GM_PAIRS_SAMPLED (zero otherwise)
+                ('levels', ctypes.c_void_p), ('slots', ctypes.c_void_p), ('n_nodes', ctypes.c_int64),
+                ('per_src', ctypes.c_int64), ('seed', ctypes.c_uint64)]
 
 
 class Loss(ctypes.Structure):

@@ -78,9 +78,28 @@ def _index_tensor(idx, device):
 class PairSet:
     """Which pairs a launch covers (mirrors gm_pairs_t); keeps the index tensors alive."""
 
-    def __init__(self, mode, P, idx_i=None, idx_j=None, B=0, nodes=None, idx64=0, k0=0):
+    def __init__(self, mode, P, idx_i=None, idx_j=None, B=0, nodes=None, idx64=0, k0=0, levels=None, slots=None,
+                 n_nodes=0, per_src=0, seed=0):
         self.mode, self.P, self.idx_i, self.idx_j, self.B, self.nodes, self.idx64 = mode, P, idx_i, idx_j, B, nodes, idx64
         self.k0 = k0
+        self.levels, self.slots, self.n_nodes, self.per_src, self.seed = levels, slots, n_nodes, per_src, seed
+
+    @staticmethod
+    def sampled(sources, levels, per_src, seed, slots=None, P=None):
+        """Pairs drawn on the device (GM_PAIRS_SAMPLED): for every source g, `per_src` targets j != sources[g] from the
+        counter hash of (seed, pair number), hop counts read from row slots[g] (default g) of the resident uint8
+        (S, N) matrix `levels`.  sources / slots: int32 device tensors."""
+        if sources.dtype != torch.int32 or not sources.is_cuda or levels.dtype != torch.uint8 or levels.ndim != 2:
+            raise ValueError('sampled pairs: int32 CUDA sources and a uint8 (S, N) level matrix')
+        if slots is not None and (slots.dtype != torch.int32 or slots.numel() != sources.numel()):
+            raise ValueError('sampled pairs: slots must be int32, one per source')
+        n = levels.shape[1]
+        if n >= (1 << 24):
+            raise ValueError('sampled pairs need fewer than 2^24 nodes')
+        total = sources.numel() * int(per_src)
+        return PairSet(L.GM_PAIRS_SAMPLED, total if P is None else P, idx_i=sources.contiguous(),
+                       levels=levels.contiguous(), slots=None if slots is None else slots.contiguous(), n_nodes=n,
+                       per_src=int(per_src), seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
 
     @staticmethod
     def elementwise(P):
@@ -128,7 +147,10 @@ class PairSet:
         return L.Pairs(mode=self.mode, idx64=self.idx64, P=self.P,
                        idx_i=None if self.idx_i is None else self.idx_i.data_ptr(),
                        idx_j=None if self.idx_j is None else self.idx_j.data_ptr(), B=self.B,
-                       nodes=None if self.nodes is None else self.nodes.data_ptr(), k0=self.k0)
+                       nodes=None if self.nodes is None else self.nodes.data_ptr(), k0=self.k0,
+                       levels=None if self.levels is None else self.levels.data_ptr(),
+                       slots=None if self.slots is None else self.slots.data_ptr(), n_nodes=self.n_nodes,
+                       per_src=self.per_src, seed=self.seed)
 
 
 @_no_function_modes

@@ -17,7 +17,7 @@ import torch
 from torch.nn.functional import softplus
 
 from . import _ops
-from .modules import ManifoldParameter
+from .modules import ManifoldParameter, _softplus_value
 from .parallel import RowShards, allreduce_step_buffers, try_peer_arena
 
 
@@ -60,7 +60,6 @@ class PairTrainer:
         self.grad = torch.zeros_like(self.x, memory_format=torch.contiguous_format)
         self.x.grad = self.grad
         self.acc = torch.zeros(2, dtype=torch.float64, device=self.x.device)
-        self._sp = float(softplus(embedding.scales[0].detach()))
         self._staging = None
         self._copy_stream = None
         self.shards = None
@@ -116,11 +115,48 @@ class PairTrainer:
             targets = _ops.TargetSpec.hops_packed(self.max_hops_sq)
         else:
             targets = _ops.TargetSpec.hops(hops, self.max_hops_sq)
+        return self._step_pairs(pairs, targets, epoch)
+
+    def step_sampled(self, sources, levels, per_src, seed, slots=None, epoch=1):
+        """One training step whose pairs are DRAWN INSIDE the pair kernel (GM_PAIRS_SAMPLED): for every BFS source
+        sources[g] (int32 device tensor) `per_src` targets j != i come from the counter hash of (seed, pair number) and
+        their hop counts from row slots[g] (default g) of the resident uint8 (S, N) matrix `levels`.  Nothing per pair
+        is uploaded, stored or read: the step's input is the list of sources.  The draw is stated in include/gm_kernels.h
+        and can be reproduced on the host bit for bit, so `step(I, pack_hops(J, H), None)` on such lists is the same step."""
+        pairs = _ops.PairSet.sampled(sources, levels, per_src, seed, slots=slots)
+        if levels.shape[1] != self.x.shape[0]:
+            raise ValueError('the level matrix must have one column per embedded point')
+        return self._step_pairs(pairs, _ops.TargetSpec.hops_packed(self.max_hops_sq), epoch)
+
+    def step_sampled_host(self, sources, levels, per_src, seed, slots=None, epoch=1, defer_loss=False):
+        """step_sampled from PINNED host tensors: `sources` (and `slots`) int32 (G,) are the step's whole upload --
+        8 bytes per source instead of 4-9 bytes per pair.  Returns the loss as a Python float (a device->host read), or
+        with defer_loss=True the loss of the previous deferred step (see step_host_grouped)."""
+        G = sources.numel()
+        dev = self.x.device
+        if getattr(self, '_src_staging', None) is None or self._src_staging[0][0].numel() < G:
+            self._src_staging = [(torch.empty(G, dtype=torch.int32, device=dev),
+                                  torch.empty(G, dtype=torch.int32, device=dev)) for _ in range(2)]
+            self._src_slot = 0
+        ds, dl = self._src_staging[self._src_slot]
+        self._src_slot ^= 1  # the other buffer may still be read by the previous step's kernel
+        ds[:G].copy_(sources, non_blocking=True)
+        if slots is not None:
+            dl[:G].copy_(slots, non_blocking=True)
+        loss = self.step_sampled(ds[:G], levels, per_src, seed, slots=None if slots is None else dl[:G], epoch=epoch)
+        if defer_loss:
+            return self._queue_loss_read()
+        return loss.item()
+
+    def _step_pairs(self, pairs, targets, epoch):
         loss_spec = self.obj.loss_spec(epoch=epoch, alpha=self.alpha)
         if not self._grad_is_clean:
             self.grad.zero_()
         self.acc.zero_()
-        _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, self._sp, self.grad, self.acc)
+        # softplus(scale) is re-read every step (cached on the parameter until somebody steps it or loads a snapshot);
+        # the trainer itself does not train the scale: acc[1] (sum l' d2) is there for a caller who does
+        sp = _softplus_value(self.emb.scales[0])
+        _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, sp, self.grad, self.acc)
         if self.peer is not None:
             self.opt.step()  # ONE kernel: cross-GPU barrier, pull+sum gradients, update, push points, sum the loss
             return self.peer.acc_out[0]
@@ -138,7 +174,8 @@ class PairTrainer:
 
     # ---- host-resident inputs (what a data loader hands over) ----------------------------------------------------------
     def _ensure_staging(self, P, hop_dtype, G=0):
-        if self._staging is None or self._staging[0][0].numel() < P or self._staging[0][3].numel() < G:
+        if (self._staging is None or self._staging[0][0].numel() < P or self._staging[0][3].numel() < G
+                or self._staging[0][2].dtype != hop_dtype):
             dev = self.x.device
             self._staging = [(torch.empty(P, dtype=torch.int32, device=dev), torch.empty(P, dtype=torch.int32, device=dev),
                               torch.empty(P, dtype=hop_dtype, device=dev), torch.empty(max(G, 1), dtype=torch.int32, device=dev),
@@ -169,6 +206,9 @@ class PairTrainer:
             nslot = 1 - slot
             ni, nj, nh = self._staging[nslot][:3]
             n = next_batch[0].numel()
+            if n > ni.numel() or next_batch[2].dtype != nh.dtype:
+                raise ValueError('next_batch does not fit the staging buffers (more pairs, or another hop dtype, than '
+                                 'the batch of this step)')
             self._copy_stream.wait_stream(cur)  # the other slot was consumed by the previous step
             with torch.cuda.stream(self._copy_stream):
                 ni[:n].copy_(next_batch[0], non_blocking=True)
@@ -224,6 +264,9 @@ class PairTrainer:
         def upload(slot, batch):
             di, dj, dh, ds, do = self._staging[slot]
             s_, o_, j_, h_ = batch
+            if s_.numel() > ds.numel() or j_.numel() > dj.numel() or (h_ is not None and h_.dtype != dh.dtype):
+                raise ValueError('batch does not fit the staging buffers (more sources / pairs, or another hop dtype, '
+                                 'than the first batch of this call)')
             ds[:s_.numel()].copy_(s_, non_blocking=True)
             do[:o_.numel()].copy_(o_, non_blocking=True)
             dj[:j_.numel()].copy_(j_, non_blocking=True)

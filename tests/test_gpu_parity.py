@@ -197,13 +197,13 @@ def test_pair_list_and_batch_gather_vs_oracle(name, dtype):
     fix = _fix(name)
 
     def oracle_pairs(dt):
-        xo = xs.to(dt).requires_grad_()
+        xo = xs.detach().clone().to(dt).requires_grad_()
         d2o = orc.dist2(xo[I], xo[J])
         (d2o * w.to(dt)).sum().backward()
         return d2o.detach(), xo.grad
 
     def oracle_batch(dt, nodes):
-        xo = xs.to(dt).requires_grad_()
+        xo = xs.detach().clone().to(dt).requires_grad_()
         pdo = orc.pdist2(xo[nodes])
         pdo.sum().backward()
         return pdo.detach(), xo.grad

@@ -132,3 +132,25 @@ def test_softplus_cache_dropped_when_a_riemannian_optimizer_steps_the_scale(monk
     assert s._version == version  # the update really is invisible to torch's version counter
     assert abs(float(s) - 0.3) < 1e-12
     assert abs(_softplus_value(s) - float(torch.nn.functional.softplus(torch.tensor(0.3, dtype=torch.float64)))) < 1e-15
+
+
+def test_sampler_oracle_is_counter_based_and_uniform():
+    """oracle/sampler_oracle.py: the draw depends only on (seed, k, i, N); j != i; roughly uniform; known answers of
+    the splitmix64 output function (Vigna's reference: seed 0 -> first outputs 0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4)."""
+    import sampler_oracle as S
+    z = S.hash32(0, np.arange(2))
+    assert [int(v) for v in z] == [0xE220A8397B1DCDAF >> 32, 0x6E789E6AA1B965F4 >> 32]
+    N, G, per = 1000, 7, 4096
+    rng = np.random.RandomState(0)
+    levels = rng.randint(1, 9, size=(G, N)).astype(np.uint8)
+    src = rng.choice(N, G, replace=False)
+    I, J, H = S.sample_pairs(src, levels, per, seed=1234)
+    assert I.shape == (G * per,) and (I.reshape(G, per) == src[:, None]).all()
+    assert (J != I).all() and J.min() >= 0 and J.max() < N
+    assert (H == levels[np.repeat(np.arange(G), per), J]).all()
+    # a prefix / another grouping of the same stream gives the same pairs
+    I2, J2, H2 = S.sample_pairs(src, levels, per, seed=1234, P=5000)
+    assert (J2 == J[:5000]).all() and (H2 == H[:5000]).all()
+    counts = np.bincount(J, minlength=N)
+    assert counts.max() < 3 * counts.mean() and (counts > 0).mean() > 0.99
+    assert (S.sample_pairs(src, levels, per, seed=1235)[1] != J).mean() > 0.99
