@@ -14,12 +14,15 @@ step     : zero grad -> ONE fused pair kernel (gather + distance + loss + gradie
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs-log2 24] [--nodes 2000000]
 
 `value`  : whole-job pairs/s with the pair batches resident in HBM (CUDA events, max over ranks).
-`e2e`    : same metric through the public API from PINNED HOST buffers.  Default: PairTrainer.step_sampled_host --
-           the step's input is its 1024 BFS source ids (4 KB upload); the 16384 targets per source are DRAWN INSIDE the
+`e2e`    : same metric through the public API from PINNED HOST buffers.  Sampled path: the step's input is its 1024
+           BFS source ids (4 KB upload); the 16384 targets per source are DRAWN INSIDE the
            pair kernel (counter hash of (seed, pair number), GM_PAIRS_SAMPLED) and their hop counts read from the BFS
            level matrix of those sources, which stays resident in HBM (the landmark set is fixed, BFS once); the loss is
-           read back every step.  --e2e-lists: the round-1 path instead (every step uploads its explicit source-grouped
-           (sources, offsets, j | hops << 24) pair list, 4 bytes per pair).
+           read back every step (PairTrainer.step_sampled_host).  The other path, PairTrainer.step_host_grouped, uploads
+           the step's explicit source-grouped (sources, offsets, j | hops << 24) pair list, 4 bytes per pair, overlapped
+           with the previous step.  Measured on B200: lists 1.31 ms/step at 1 GPU but host-memory bound beyond 2 GPUs of
+           one host (3.05 ms at 8); sampled +0.33 ms per step at any GPU count (one random byte per pair costs a DRAM
+           line).  --e2e auto (default) takes lists up to 2 GPUs and sampled beyond; --e2e lists|sampled forces one.
 `secondary`: (N=1) epoch time of BASELINE configs 1-4 through TrainingEngine on the shipped graphs, each with its
            roofline and the CPU reference beside it, and the multi-source BFS kernel with a fresh BFS every step.
 `roofline`: fused pair kernel, algorithmic bytes (268 B/pair) / its CUDA-event duration vs the
@@ -64,8 +67,10 @@ def parse():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='weak: 2^pairs_log2 pairs per GPU per '
                     'step; strong: 2^pairs_log2 pairs per step in total, split over the GPUs (BASELINE config 5 as '
                     'written)')
-    ap.add_argument('--e2e-lists', action='store_true', help='end-to-end leg uploads explicit pair lists (4 B/pair) '
-                    'instead of drawing the pairs on the device from the uploaded source ids')
+    ap.add_argument('--e2e', default='auto', choices=['auto', 'lists', 'sampled'], help='end-to-end leg: `lists` uploads '
+                    'explicit pair lists (4 B/pair, PCIe / host-memory bound beyond 2 GPUs of one host), `sampled` uploads '
+                    'the source ids and draws the pairs inside the pair kernel (one extra random byte read per pair); '
+                    'auto = lists up to 2 GPUs, sampled beyond')
     ap.add_argument('--no-secondary', action='store_true', help='skip the secondary lines (configs 1-4, BFS)')
     ap.add_argument('--workload', default='5', help="'5' (default, the bench line) or one of 1, 2a, 2b, 3a, 3b, 4 (or a "
                     "comma list / 'all'): epoch time of that BASELINE config -- on the GPU through TrainingEngine, or "
@@ -641,7 +646,8 @@ def main():
 
     # ---- end-to-end timing from pinned host buffers ----------------------------------------------------------------
     nb = len(batches)
-    if args.e2e_lists:
+    e2e_mode = args.e2e if args.e2e != 'auto' else ('lists' if world <= 2 else 'sampled')
+    if e2e_mode == 'lists':
         # source-grouped upload (sources, offsets, j, hops): 4-5 B/pair over PCIe; the next batch is uploaded on a
         # second stream while this one computes; every step ends with a device->host read of the loss
         def grouped(b):

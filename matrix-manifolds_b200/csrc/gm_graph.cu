@@ -10,10 +10,24 @@
 // Algorithm: level-synchronous "pull" BFS for all S sources at once.  Every node
 // keeps W = ceil(S/64) 64-bit words of frontier / visited bits (node-major, so the
 // W words of one neighbour are contiguous and the loads of a warp coalesce).
-// Thread t = v*W + w ORs word w of every in-neighbour's frontier, masks the
-// visited bits, and writes level L for each newly reached (source, v).
+// Thread t = v*W + w ORs word w of every in-neighbour's frontier and masks the
+// visited bits.
+//
+// v2 (uint8 levels, the common case): what made v1 slow was not the search but
+// recording it -- one scattered 1-byte store levels[s*N + v] per newly reached
+// (source, node), i.e. S*N partial-sector writes with stride N.  v2
+//   * records levels in a NODE-major byte matrix lt[v*Sp + s] during the search:
+//     the 64 sources of thread (v, w) are 64 contiguous bytes, updated with
+//     16-byte read-blend-write, and transposes it to the (S, N) result once at
+//     the end with a tiled kernel (coalesced both ways);
+//   * skips a (node, word) whose 64 sources have all arrived (saturated), stops
+//     pulling as soon as the remaining unvisited bits are covered, and never
+//     reads the frontier words of a neighbour that is in no frontier at all
+//     (one byte per node, rebuilt every level).
+// Levels wider than one byte (graphs deeper than 254 hops) keep the v1 kernels.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/gm_kernels.h"
 
 namespace gm {
@@ -91,6 +105,431 @@ bfs_level_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
       if (s < S) levels[(size_t)s * N + v] = lv;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v2: uint8 levels
+// ---------------------------------------------------------------------------------------------------------------------
+// The frontier of level l IS the record of level l: plane[l][v*W + w] has bit s set iff source w*64+s reaches node v in
+// exactly l hops.  The planes of the last kPlanes levels are kept (a ring), so the search itself writes 8 bytes per
+// (node, word, level) and no level bytes at all.  Levels are materialised afterwards:
+//   depth <= kPlanes (every graph of the BASELINE configs but the two trees): ONE pass reads the planes and writes the
+//     (S, N) byte matrix through a shared-memory tile -- 16-byte accesses on both sides, every byte written once;
+//   deeper graphs: every kPlanes levels the ring is committed into a node-major byte matrix lt[v*Sp + s] (64 contiguous
+//     bytes per thread, read-blend-write), which is transposed at the end.
+constexpr int kPlanes = 12;
+constexpr int kFlagStride = 32;  // ints between the per-level "found something" flags: one flag per 128-byte line
+constexpr int kHubDegree = 192;  // nodes with more in-neighbours than this get a whole block per level
+
+struct Bfs2Ws {
+  u64* plane[kPlanes + 1];  // plane[0]: the seeds; level l lives in plane[(l - 1) % kPlanes + 1]
+  u64* visited;
+  unsigned char* any_cur;   // any_cur[u] != 0 iff node u is in the frontier of at least one source
+  unsigned char* any_next;
+  unsigned char* lt;        // node-major levels, N x (W*64) bytes (deep graphs only)
+  int* hubs;                // [0]: count, [1..]: ids of the nodes with degree > kHubDegree
+  int* ell;                 // N x 8: the first 8 in-neighbours of every node (-1 padded), one 32-byte sector per node
+  unsigned char* cls;       // 0: degree <= 8 (the ELL row is the whole list), 1: longer, 2: hub
+  int* changed;
+};
+static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
+static size_t ws2_bytes(int N, int S) {
+  size_t W = ((size_t)S + 63) / 64;
+  return (kPlanes + 2) * align256(W * (size_t)N * sizeof(u64)) + 2 * align256((size_t)N) +
+         align256((size_t)N * W * 64) + align256(((size_t)N + 1) * sizeof(int)) + align256((size_t)N * 32) +
+         align256((size_t)N) + (size_t)(kMaxLevels + 1) * sizeof(int) + 256;
+}
+static Bfs2Ws carve2(void* ws, int N, int S) {
+  size_t W = ((size_t)S + 63) / 64;
+  Bfs2Ws b;
+  char* p = (char*)ws;
+  const size_t words = align256(W * (size_t)N * sizeof(u64));
+  for (int i = 0; i <= kPlanes; ++i) { b.plane[i] = (u64*)p; p += words; }
+  b.visited = (u64*)p; p += words;
+  b.any_cur = (unsigned char*)p; p += align256((size_t)N);
+  b.any_next = (unsigned char*)p; p += align256((size_t)N);
+  b.lt = (unsigned char*)p; p += align256((size_t)N * W * 64);
+  b.hubs = (int*)p; p += align256(((size_t)N + 1) * sizeof(int));
+  b.ell = (int*)p; p += align256((size_t)N * 32);
+  b.cls = (unsigned char*)p; p += align256((size_t)N);
+  b.changed = (int*)p;
+  return b;
+}
+static inline int plane_of(int level) { return level == 0 ? 0 : (level - 1) % kPlanes + 1; }
+
+// sources: seed bit in plane 0 and in visited, "in a frontier" byte; padding bits of the last word count as visited
+__global__ void bfs2_seed_kernel(const int* __restrict__ sources, int S, int N, int W, u64* __restrict__ frontier,
+                                 u64* __restrict__ visited, unsigned char* __restrict__ any_cur) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) {
+    int v = sources[i];
+    u64 bit = 1ull << (i & 63);
+    atomicOr(&frontier[(size_t)v * W + (i >> 6)], bit);
+    atomicOr(&visited[(size_t)v * W + (i >> 6)], bit);
+    any_cur[v] = 1;
+  }
+  if ((S & 63) != 0 && i < N) atomicOr(&visited[(size_t)i * W + (W - 1)], ~0ull << (S & 63));
+}
+
+// Thread (v, w).  The kernel is latency bound -- a handful of dependent round trips per thread with the memory system
+// nearly idle -- so everything that does not depend on another load is fetched in the FIRST round trip: the "search
+// still running" flag, the visited word, the node's class and its ELL row (first 8 neighbours, one sector).  Second
+// round trip: the 8 frontier words.  Only nodes with more than 8 neighbours go on to walk the CSR list (8 per trip,
+// filtered by the "in any frontier" byte); hubs are left to bfs2_hub_kernel.
+__global__ void __launch_bounds__(256)
+bfs2_level_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, int N, int W, int level,
+                  const u64* __restrict__ frontier, u64* __restrict__ next, u64* __restrict__ visited,
+                  const unsigned char* __restrict__ any_cur, unsigned char* __restrict__ any_next,
+                  int* __restrict__ changed, const int* __restrict__ ell, const unsigned char* __restrict__ cls,
+                  int hubs_apart) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = t < (size_t)N * W;
+  const size_t tc = in_range ? t : 0;
+  const int v = (int)(tc / W);
+  const int w = (int)(tc - (size_t)v * W);
+  const int alive = changed[(level - 1) * kFlagStride];
+  const u64 vis = visited[tc];
+  const int kind = cls[v];
+  const int4 n0 = reinterpret_cast<const int4*>(ell)[2 * (size_t)v];
+  const int4 n1 = reinterpret_cast<const int4*>(ell)[2 * (size_t)v + 1];
+  if (!alive) return;  // the search finished at an earlier level (block-uniform)
+  const bool mine = in_range && !(hubs_apart && kind == 2);
+  u64 fresh = 0;
+  if (mine && vis != ~0ull) {  // saturated words have nothing left to learn
+    u64 acc = 0;
+    const int u8[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (u8[i] >= 0) acc |= frontier[(size_t)u8[i] * W + w];
+    if (kind != 0 && (acc | vis) != ~0ull) {
+      const int e1 = rowptr[v + 1];
+      for (int e = rowptr[v] + 8; e < e1; e += 8) {
+        int u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = (e + i < e1) ? colidx[e + i] : -1;
+        unsigned char in[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) in[i] = (u[i] >= 0) ? any_cur[u[i]] : (unsigned char)0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (in[i]) acc |= frontier[(size_t)u[i] * W + w];
+        if ((acc | vis) == ~0ull) break;  // every missing source has arrived
+      }
+    }
+    fresh = acc & ~vis;
+  }
+  if (mine) {
+    next[t] = fresh;
+    if (fresh) {
+      visited[t] = vis | fresh;
+      any_next[v] = 1;
+    }
+  }
+  // ONE store per block: millions of stores to the same word serialise in its L2 slice -- and the loads of the
+  // neighbouring flag at the top of this kernel queue behind them (that was most of v1's and v2.0's level time)
+  if (__syncthreads_or(fresh != 0) && threadIdx.x == 0) changed[level * kFlagStride] = 1;
+}
+
+// ids of the nodes whose neighbour list is long enough to be the tail of every level
+// ... and the per-node adjacency digest the level kernel starts from (ELL row + class)
+__global__ void bfs2_find_hubs_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, int N,
+                                      int* __restrict__ hubs, int* __restrict__ ell, unsigned char* __restrict__ cls,
+                                      int want_hubs) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  const int e0 = rowptr[v], deg = rowptr[v + 1] - e0;
+  int row[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) row[i] = (i < deg) ? colidx[e0 + i] : -1;
+  reinterpret_cast<int4*>(ell)[2 * (size_t)v] = make_int4(row[0], row[1], row[2], row[3]);
+  reinterpret_cast<int4*>(ell)[2 * (size_t)v + 1] = make_int4(row[4], row[5], row[6], row[7]);
+  const bool hub = want_hubs && deg > kHubDegree;
+  cls[v] = hub ? 2 : (deg > 8 ? 1 : 0);
+  if (hub) hubs[1 + atomicAdd(hubs, 1)] = v;
+}
+
+// One block per hub node: the 256 threads split into `parts` edge slices x Wc words (Wc = min(W, 32) rounded up to a
+// power of two); words beyond 32 are looped.  Slice results are OR-ed through shared memory.
+__global__ void __launch_bounds__(256)
+bfs2_hub_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, int W, int level,
+                const u64* __restrict__ frontier, u64* __restrict__ next, u64* __restrict__ visited,
+                const unsigned char* __restrict__ any_cur, unsigned char* __restrict__ any_next,
+                int* __restrict__ changed, const int* __restrict__ hubs, int Wc) {
+  extern __shared__ u64 red[];  // [parts][W]
+  if (changed[(level - 1) * kFlagStride] == 0) return;
+  const int v = hubs[1 + blockIdx.x];
+  const int parts = 256 / Wc;
+  const int part = threadIdx.x / Wc, lane_w = threadIdx.x % Wc;
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  for (int w = lane_w; w < W; w += Wc) {
+    const u64 vis = visited[(size_t)v * W + w];
+    u64 acc = 0;
+    if (vis != ~0ull) {
+      for (int e = e0 + part * 4; e < e1; e += parts * 4) {
+        int u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = (e + i < e1) ? colidx[e + i] : -1;
+        unsigned char in[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) in[i] = (u[i] >= 0) ? any_cur[u[i]] : (unsigned char)0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (in[i]) acc |= frontier[(size_t)u[i] * W + w];
+        if ((acc | vis) == ~0ull) break;
+      }
+    }
+    red[part * W + w] = acc;
+  }
+  __syncthreads();
+  bool any_fresh = false;
+  for (int w = threadIdx.x; w < W; w += 256) {
+    u64 acc = 0;
+    for (int p = 0; p < parts; ++p) acc |= red[p * W + w];
+    const size_t t = (size_t)v * W + w;
+    const u64 vis = visited[t];
+    const u64 fresh = acc & ~vis;
+    next[t] = fresh;
+    if (fresh) { visited[t] = vis | fresh; any_fresh = true; }
+  }
+  if (any_fresh) any_next[v] = 1;
+  if (__syncthreads_or(any_fresh) && threadIdx.x == 0) changed[level * kFlagStride] = 1;
+}
+
+// 4 bits -> 4 byte masks (0xFF where the bit is set)
+__device__ __forceinline__ unsigned spread4(unsigned bits) {
+  return (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+}
+// bytes of 16 sources (bits 16c .. 16c+15 of `fresh`) <- level where their bit is set
+__device__ __forceinline__ void blend16(uint4& o, u64 fresh, int c, unsigned level) {
+  const unsigned bits = (unsigned)(fresh >> (16 * c)) & 0xFFFFu;
+  if (!bits) return;
+  const unsigned lv4 = level * 0x01010101u;
+  unsigned m;
+  m = spread4(bits);       o.x = (o.x & ~m) | (lv4 & m);
+  m = spread4(bits >> 4);  o.y = (o.y & ~m) | (lv4 & m);
+  m = spread4(bits >> 8);  o.z = (o.z & ~m) | (lv4 & m);
+  m = spread4(bits >> 12); o.w = (o.w & ~m) | (lv4 & m);
+}
+
+struct PlaneSet {
+  const u64* p[kPlanes + 1];
+  int level[kPlanes + 1];
+  int count;
+};
+
+// shallow graphs: levels[s*N + v] straight from the planes.  A block owns 32 nodes x 16 words (1024 sources): it stages
+// those words of every plane in shared memory with coalesced loads (32 rows of 128 contiguous bytes per plane), then
+// emits one 32-node x 64-source byte tile per word, transposed through a double-buffered shared-memory tile: every
+// source row receives one full 32-byte sector.
+constexpr int kFinWords = 16;
+constexpr int kFinNodes = 32;
+__device__ __forceinline__ void blend8(uint2& o, u64 fresh, int c, unsigned level) {  // sources 8c .. 8c+7
+  const unsigned bits = (unsigned)(fresh >> (8 * c)) & 0xFFu;
+  if (!bits) return;
+  const unsigned lv4 = level * 0x01010101u;
+  unsigned m;
+  m = spread4(bits);      o.x = (o.x & ~m) | (lv4 & m);
+  m = spread4(bits >> 4); o.y = (o.y & ~m) | (lv4 & m);
+}
+__global__ void __launch_bounds__(256)
+bfs2_finalize_kernel(PlaneSet ps, int N, int W, int S, unsigned char* __restrict__ levels) {
+  extern __shared__ __align__(16) unsigned char fin_smem[];
+  u64* stage = reinterpret_cast<u64*>(fin_smem);  // [count][kFinNodes][kFinWords]
+  typedef unsigned char TileRow[64 + 8];
+  TileRow* tile = reinterpret_cast<TileRow*>(fin_smem + (size_t)ps.count * kFinNodes * kFinWords * 8);  // [2][32] rows
+  const int v0 = blockIdx.x * kFinNodes, w0 = blockIdx.y * kFinWords;
+  const int nw = (W - w0 < kFinWords) ? (W - w0) : kFinWords;
+  for (int i = 0; i < ps.count; ++i) {
+    for (int q = threadIdx.x; q < kFinNodes * kFinWords; q += 256) {
+      const int rr = q / kFinWords, ww = q % kFinWords;
+      u64 val = 0;
+      if (v0 + rr < N && ww < nw) val = ps.p[i][(size_t)(v0 + rr) * W + w0 + ww];
+      stage[((size_t)i * kFinNodes + rr) * kFinWords + ww] = val;
+    }
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 3, c = threadIdx.x & 7;    // blend: node r, sources 8c .. 8c+7 of the word
+  const int q = threadIdx.x >> 2, c2 = threadIdx.x & 3;   // emit: source q of the word, nodes 8*c2 .. 8*c2+7
+  for (int ww = 0; ww < nw; ++ww) {
+    TileRow* tl = tile + (ww & 1) * kFinNodes;
+    uint2 val = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);  // unreached
+    for (int i = 0; i < ps.count; ++i)
+      blend8(val, stage[((size_t)i * kFinNodes + r) * kFinWords + ww], c, (unsigned)ps.level[i]);
+    *reinterpret_cast<uint2*>(&tl[r][8 * c]) = val;
+    __syncthreads();  // (the other buffer is free: its readers passed this barrier one iteration ago)
+    const int s = (w0 + ww) * 64 + q;
+    if (s < S) {
+      unsigned char out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] = tl[8 * c2 + j][q];
+      unsigned char* dst = levels + (size_t)s * N + v0 + 8 * c2;
+      if (v0 + 8 * c2 + 7 < N && (reinterpret_cast<size_t>(dst) & 7) == 0) {
+        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(out);
+      } else {
+        for (int j = 0; j < 8; ++j)
+          if (v0 + 8 * c2 + j < N) dst[j] = out[j];
+      }
+    }
+  }
+}
+
+// deep graphs: fold the planes of the ring into the node-major byte matrix (64 contiguous bytes per thread)
+__global__ void __launch_bounds__(256)
+bfs2_commit_kernel(PlaneSet ps, size_t words, unsigned char* __restrict__ lt) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= words) return;
+  u64 f[kPlanes + 1];
+  u64 any = 0;
+  for (int i = 0; i < ps.count; ++i) { f[i] = ps.p[i][t]; any |= f[i]; }
+  if (!any) return;
+  uint4* row = reinterpret_cast<uint4*>(lt + t * 64);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (((any >> (16 * c)) & 0xFFFFu) == 0) continue;
+    uint4 o = row[c];
+    for (int i = 0; i < ps.count; ++i) blend16(o, f[i], c, (unsigned)ps.level[i]);
+    row[c] = o;
+  }
+}
+
+// levels[s*N + v] = lt[v*Sp + s]: 64 x 64 byte tiles through shared memory, 16-byte accesses on both sides
+__global__ void __launch_bounds__(256)
+bfs2_transpose_kernel(const unsigned char* __restrict__ lt, int N, int Sp, int S, unsigned char* __restrict__ levels) {
+  __shared__ __align__(16) unsigned char tile[64][64 + 16];
+  const int v0 = blockIdx.x * 64, s0 = blockIdx.y * 64;
+  const int r = threadIdx.x >> 2, c = threadIdx.x & 3;
+  {
+    uint4 val = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    if (v0 + r < N) val = *reinterpret_cast<const uint4*>(lt + (size_t)(v0 + r) * Sp + s0 + 16 * c);
+    *reinterpret_cast<uint4*>(&tile[r][16 * c]) = val;
+  }
+  __syncthreads();
+  const int s = s0 + r;
+  if (s >= S) return;
+  unsigned char out[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = tile[16 * c + j][r];
+  unsigned char* dst = levels + (size_t)s * N + v0 + 16 * c;
+  if (v0 + 16 * c + 15 < N && (reinterpret_cast<size_t>(dst) & 15) == 0) {
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+  } else {
+    for (int j = 0; j < 16; ++j)
+      if (v0 + 16 * c + j < N) dst[j] = out[j];
+  }
+}
+
+static int bfs2_run(const int* rowptr, const int* colidx, int N, const int* sources, int S, unsigned char* levels,
+                    void* ws, cudaStream_t st) {
+  const int W = (S + 63) / 64;
+  Bfs2Ws b = carve2(ws, N, S);
+  const size_t words = (size_t)W * N;
+  // plane 0, visited and the two "in a frontier" byte arrays start at zero; the other planes are fully overwritten
+  cudaMemsetAsync(b.plane[0], 0, words * sizeof(u64), st);
+  cudaMemsetAsync(b.visited, 0, words * sizeof(u64), st);
+  cudaMemsetAsync(b.any_cur, 0, 2 * align256((size_t)N), st);
+  cudaMemsetAsync(b.changed, 0, (size_t)256 * kFlagStride * sizeof(int), st);  // fits: kMaxLevels + 1 ints reserved
+  int one = 1;
+  cudaMemcpyAsync(b.changed, &one, sizeof(int), cudaMemcpyHostToDevice, st);
+  const int seed_n = S > N ? S : N;
+  bfs2_seed_kernel<<<(seed_n + 127) / 128, 128, 0, st>>>(sources, S, N, W, b.plane[0], b.visited, b.any_cur);
+  note_launch();
+  const int chunk = 4;
+  size_t blocks = (words + 255) / 256;
+  if (blocks > 0x7fffffffULL) return GM_EINVAL;
+  // hub nodes (one host read per BFS): without this every level ends with the few threads that walk the longest lists
+  int n_hubs = 0, Wc = 1;
+  while (Wc < W && Wc < 32) Wc <<= 1;
+  const size_t hub_smem = (size_t)(256 / Wc) * W * sizeof(u64);
+  const bool want_hubs = hub_smem <= 96 * 1024;
+  cudaMemsetAsync(b.hubs, 0, sizeof(int), st);
+  bfs2_find_hubs_kernel<<<(N + 255) / 256, 256, 0, st>>>(rowptr, colidx, N, b.hubs, b.ell, b.cls, want_hubs ? 1 : 0);
+  note_launch();
+  if (want_hubs) {
+    cudaMemcpyAsync(&n_hubs, b.hubs, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return (int)e;
+    if (hub_smem > 48 * 1024)
+      cudaFuncSetAttribute(bfs2_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hub_smem);
+  }
+  cudaStream_t hub_st = nullptr;  // the hub kernel of a level runs beside its level kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (n_hubs > 0) {
+    cudaStreamCreateWithFlags(&hub_st, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+  }
+  auto release = [&]() {
+    if (hub_st) { cudaStreamDestroy(hub_st); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); hub_st = nullptr; }
+  };
+  bool deep = false;      // the ring has wrapped: levels go through lt
+  int committed = -1;     // deep: levels <= committed are in lt
+  auto commit = [&](int lo, int hi) {  // fold levels lo..hi (all still in the ring) into lt
+    PlaneSet ps;
+    ps.count = 0;
+    for (int l = lo; l <= hi; ++l) { ps.p[ps.count] = b.plane[plane_of(l)]; ps.level[ps.count] = l; ++ps.count; }
+    bfs2_commit_kernel<<<(unsigned)blocks, 256, 0, st>>>(ps, words, b.lt);
+    note_launch();
+  };
+  int level = 1;
+  int last_level = 0;  // deepest level that reached a node (known after the host sync)
+  while (true) {
+    for (int i = 0; i < chunk; ++i, ++level) {
+      if (level > 254) { release(); return GM_EUNSUPPORTED; }  // needs a wider level type (the v1 kernels)
+      if (level > kPlanes && (level - 1) % kPlanes == 0) {  // about to overwrite level (level - kPlanes)
+        if (!deep) {
+          deep = true;
+          cudaMemsetAsync(b.lt, 0xFF, (size_t)N * W * 64, st);
+          commit(0, level - 1);
+        } else {
+          commit(committed + 1, level - 1);
+        }
+        committed = level - 1;
+      }
+      cudaMemsetAsync(b.any_next, 0, (size_t)N, st);
+      if (n_hubs > 0) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(hub_st, ev_fork, 0); }
+      bfs2_level_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, colidx, N, W, level, b.plane[plane_of(level - 1)],
+                                                        b.plane[plane_of(level)], b.visited, b.any_cur, b.any_next,
+                                                        b.changed, b.ell, b.cls, n_hubs > 0);
+      note_launch();
+      if (n_hubs > 0) {
+        bfs2_hub_kernel<<<n_hubs, 256, hub_smem, hub_st>>>(rowptr, colidx, W, level, b.plane[plane_of(level - 1)],
+                                                           b.plane[plane_of(level)], b.visited, b.any_cur, b.any_next,
+                                                           b.changed, b.hubs, Wc);
+        note_launch();
+        cudaEventRecord(ev_join, hub_st);
+        cudaStreamWaitEvent(st, ev_join, 0);
+      }
+      unsigned char* ta = b.any_cur; b.any_cur = b.any_next; b.any_next = ta;
+    }
+    int flags[chunk * kFlagStride];
+    cudaMemcpyAsync(flags, b.changed + (size_t)(level - chunk) * kFlagStride, sizeof(flags), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { release(); return (int)e; }
+    bool done = false;
+    for (int i = 0; i < chunk; ++i) {
+      if (flags[i * kFlagStride]) last_level = level - chunk + i;
+      else { done = true; break; }
+    }
+    if (done) break;
+  }
+  // levels beyond last_level found nothing; their kernels returned immediately and left their planes untouched
+  if (!deep) {
+    PlaneSet ps;
+    ps.count = 0;
+    for (int l = 0; l <= last_level; ++l) { ps.p[ps.count] = b.plane[plane_of(l)]; ps.level[ps.count] = l; ++ps.count; }
+    dim3 grid((unsigned)((N + kFinNodes - 1) / kFinNodes), (unsigned)((W + kFinWords - 1) / kFinWords));
+    const size_t fin_smem = (size_t)ps.count * kFinNodes * kFinWords * 8 + 2 * kFinNodes * (64 + 8);
+    cudaFuncSetAttribute(bfs2_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
+    bfs2_finalize_kernel<<<grid, 256, fin_smem, st>>>(ps, N, W, S, levels);
+    note_launch();
+  } else {
+    if (last_level > committed) commit(committed + 1, last_level);
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)W);
+    bfs2_transpose_kernel<<<grid, 256, 0, st>>>(b.lt, N, W * 64, S, levels);
+    note_launch();
+  }
+  release();
+  return check_launch();
 }
 
 template <typename L>
@@ -195,6 +634,12 @@ __global__ void gather_levels_kernel(const L* __restrict__ levels, int N, const 
 
 using namespace gm;
 
+// GM_BFS_V1=1 keeps the round-1 kernels for uint8 levels too (A/B measurements)
+static bool bfs_force_v1() {
+  static const bool v = [] { const char* e = getenv("GM_BFS_V1"); return e && e[0] == '1'; }();
+  return v;
+}
+
 #define GM_LEVEL_SWITCH(bytes, STMT)                                      \
   switch (bytes) {                                                        \
     case 1: { typedef unsigned char L; STMT; } break;                     \
@@ -206,7 +651,11 @@ using namespace gm;
 extern "C" {
 #pragma GCC visibility push(default)
 
-size_t gm_bfs_workspace_bytes(int32_t N, int32_t S) { return (N > 0 && S > 0) ? ws_bytes(N, S) : 0; }
+size_t gm_bfs_workspace_bytes(int32_t N, int32_t S) {
+  if (N <= 0 || S <= 0) return 0;
+  const size_t a = ws_bytes(N, S), b = ws2_bytes(N, S);
+  return a > b ? a : b;
+}
 
 int gm_bfs_multi_source(const int32_t* rowptr, const int32_t* colidx, int32_t N, const int32_t* sources, int32_t S,
                         int32_t level_bytes, void* levels, void* workspace, size_t workspace_bytes,
@@ -214,8 +663,10 @@ int gm_bfs_multi_source(const int32_t* rowptr, const int32_t* colidx, int32_t N,
   if (N < 0 || S < 0) return GM_EINVAL;
   if (N == 0 || S == 0) return GM_OK;
   if (!rowptr || !colidx || !sources || !levels || !workspace) return GM_ENULL;
-  if (workspace_bytes < ws_bytes(N, S)) return GM_EINVAL;
+  if (workspace_bytes < gm_bfs_workspace_bytes(N, S)) return GM_EINVAL;
   int rc = GM_OK;
+  if (level_bytes == 1 && !bfs_force_v1())
+    return bfs2_run(rowptr, colidx, N, sources, S, (unsigned char*)levels, workspace, (cudaStream_t)stream);
   GM_LEVEL_SWITCH(level_bytes, rc = bfs_run<L>(rowptr, colidx, N, sources, S, (L*)levels, workspace, (cudaStream_t)stream));
   return rc;
 }

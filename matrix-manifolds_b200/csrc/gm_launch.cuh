@@ -124,15 +124,40 @@ __host__ __device__ __forceinline__ unsigned sample_hash32(unsigned long long se
   z ^= z >> 31;
   return (unsigned)(z >> 32);
 }
-__device__ __forceinline__ unsigned sampled_word(const PairSpec& ps, long long k, long long& ra) {
+// the drawn target j of pair k, its source row `ra`, and WHERE its hop count lives (so that a pipelined caller can
+// issue that load long before it needs the value)
+__device__ __forceinline__ unsigned sampled_j(const PairSpec& ps, long long k, long long& ra,
+                                              const unsigned char*& hop_ptr) {
   const long long g = ps.per_shift >= 0 ? (k >> ps.per_shift) : (k / ps.per_src);
   const unsigned i = (unsigned)((const int*)ps.idx_i)[g];
   const long long slot = ps.slots ? (long long)ps.slots[g] : g;
   unsigned j = __umulhi(sample_hash32(ps.seed, (unsigned long long)k), (unsigned)(ps.n_nodes - 1));
   j += (j >= i) ? 1u : 0u;
-  const unsigned hop = ps.levels[slot * ps.n_nodes + j];
+  hop_ptr = ps.levels + slot * ps.n_nodes + j;
   ra = (long long)i;
-  return (hop << 24) | j;
+  return j;
+}
+// One random byte out of a multi-GB table per pair: streaming (evict-first) so that it does not push the gradient and
+// point tables out of L2.
+#ifndef GM_HOP_LOAD
+#define GM_HOP_LOAD 0
+#endif
+__device__ __forceinline__ unsigned load_hop(const unsigned char* p) {
+#if GM_HOP_LOAD == 0
+  return (unsigned)__ldcs(p);
+#elif GM_HOP_LOAD == 1
+  return (unsigned)__ldg(p);
+#elif GM_HOP_LOAD == 2
+  return (unsigned)*p;
+#else  // aligned 32-bit load of the word that holds the byte
+  const unsigned w = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<size_t>(p) & ~(size_t)3));
+  return (w >> (8 * (unsigned)(reinterpret_cast<size_t>(p) & 3))) & 0xFFu;
+#endif
+}
+__device__ __forceinline__ unsigned sampled_word(const PairSpec& ps, long long k, long long& ra) {
+  const unsigned char* hp;
+  const unsigned j = sampled_j(ps, k, ra, hp);
+  return (load_hop(hp) << 24) | j;
 }
 
 // rows of xa / xb touched by pair k (also the rows gradients go to)

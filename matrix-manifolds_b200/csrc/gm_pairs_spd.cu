@@ -133,13 +133,14 @@ struct RowStage {
 // TRIU position of one lane's look-ahead pair: walks k, k+32, k+64, ... (LIST pairs need no state beyond k)
 struct PairCursor {
   long long a, pos;  // TRIU: row a, position inside the row
+  int slot;          // SAMPLED: level row of the cached group
   __device__ __forceinline__ void init(const PairSpec& ps, long long k0) {
     if (ps.mode == GM_PAIRS_TRIU && k0 < ps.P) {
       long long b;
       triu_decode(k0 + ps.k0, ps.B, a, b);
       pos = b - a - 1;
     } else {
-      a = 0; pos = 0;
+      a = -1; pos = 0; slot = 0;  // SAMPLED: no group cached yet
     }
   }
   __device__ __forceinline__ void rows(const PairSpec& ps, long long k, long long& ra, long long& rb) const {
@@ -147,12 +148,32 @@ struct PairCursor {
       ra = load_index(ps.idx_i, k, ps.idx64);
       rb = load_index(ps.idx_j, k, ps.idx64);  // raw word: HOPS_PACKED callers split off the top byte
     } else if (ps.mode == GM_PAIRS_SAMPLED) {
-      rb = (long long)sampled_word(ps, k, ra);  // raw word (hop << 24) | j, drawn here: nothing is read per pair
+      const unsigned char* hp;  // callers that want the hop count use rows_sampled()
+      rb = (long long)sampled_j(ps, k, ra, hp);
     } else {
       long long b = a + 1 + pos;
       if (ps.nodes) { ra = load_index(ps.nodes, a, ps.idx64); rb = load_index(ps.nodes, b, ps.idx64); }
       else { ra = a; rb = b; }
     }
+  }
+  // SAMPLED: the drawn pair, plus its hop count as a load issued NOW and (by a pipelined caller) consumed an
+  // iteration later -- nothing is read per pair except that one byte
+  // The source id and level row of the lane's current group are cached (a group is thousands of consecutive pairs):
+  // the draw itself then depends on no load at all, and the hop load can be issued straight away.
+  __device__ __forceinline__ void rows_sampled(const PairSpec& ps, long long k, long long& ra, long long& rb,
+                                               unsigned& hop) {
+    const int g = (int)(ps.per_shift >= 0 ? (k >> ps.per_shift) : (k / ps.per_src));
+    if (g != a) {  // (a, pos) are free in SAMPLED mode: a = cached group, pos = its source id; row in `slot`
+      a = g;
+      pos = ((const int*)ps.idx_i)[g];
+      slot = ps.slots ? ps.slots[g] : g;
+    }
+    const unsigned i = (unsigned)pos;
+    unsigned j = __umulhi(sample_hash32(ps.seed, (unsigned long long)k), (unsigned)(ps.n_nodes - 1));
+    j += (j >= i) ? 1u : 0u;
+    hop = load_hop(ps.levels + (long long)slot * ps.n_nodes + j);
+    ra = (long long)i;
+    rb = (long long)j;
   }
   __device__ __forceinline__ void advance(const PairSpec& ps) {
     if (ps.mode == GM_PAIRS_TRIU) {
@@ -218,6 +239,8 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   PairCursor ahead;                  // TRIU position of the furthest pair whose indices have been loaded
   row_t ra0 = kNoRow, rb0 = kNoRow;  // rows of pair kc
   row_t ra1 = kNoRow, rb1 = kNoRow;  // rows of pair kc + 32 (indices loaded, rows not yet issued)
+  unsigned hop1 = 0;                 // SAMPLED: hop count of pair kc + 32 (load in flight since the previous iteration)
+  const bool sampled = ps.mode == GM_PAIRS_SAMPLED;
   raw_t tg0 = 0;                     // target (K_FUSED) or upstream gradient (K_BWD) of pair kc, raw
   int stage = 0;
 
@@ -225,7 +248,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     if constexpr (KMODE == K_BWD) {
       return Raw::pack(gout[k]);
     } else {
-      if (hopsP) return (raw_t)(((unsigned)rb) >> 24);
+      if (hopsP) return (raw_t)(((unsigned)rb) >> 24);  // (SAMPLED pairs: see the callers)
       if (hops8) return (raw_t)((const unsigned char*)tg.data)[k];
       if (hops16) return (raw_t)((const unsigned short*)tg.data)[k];
       return Raw::pack(fetch_target<T>(tg, k, (long long)ra, (long long)rb));
@@ -240,17 +263,19 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
       return Raw::unpack(r);
     }
   };
-  auto load_rows = [&](long long k, row_t& ra, row_t& rb) {
+  auto load_rows = [&](long long k, row_t& ra, row_t& rb, unsigned& hop) {
     long long a, b;
-    ahead.rows(ps, k, a, b);
+    if (sampled) ahead.rows_sampled(ps, k, a, b, hop);
+    else ahead.rows(ps, k, a, b);
     ra = (row_t)a; rb = (row_t)b;
   };
 
   ahead.init(ps, kc);
   bool v0 = kc < kend;
   if (v0) {
-    load_rows(kc, ra0, rb0);
-    tg0 = fetch_scalar(kc, ra0, rb0);
+    unsigned hop0 = 0;
+    load_rows(kc, ra0, rb0, hop0);
+    tg0 = (sampled && hopsP) ? (raw_t)hop0 : fetch_scalar(kc, ra0, rb0);
     if (rawj) rb0 &= (row_t)0x00ffffffu;
     Stage::issue(stage_mem, 0, 0, tid, xa + (size_t)ra0 * E);
     Stage::issue(stage_mem, 0, 1, tid, xb + (size_t)rb0 * E);
@@ -258,7 +283,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   cp_async_commit();
   ahead.advance(ps);
   bool v1 = kc + 32 < kend;
-  if (v1) load_rows(kc + 32, ra1, rb1);
+  if (v1) load_rows(kc + 32, ra1, rb1, hop1);
 
   // ---- per-lane running state -------------------------------------------------------------------------------------
   double loss_v = 0.0, gd2_v = 0.0;
@@ -296,7 +321,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     // (2) stage the next pair: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
     raw_t tgn = 0;
     if (v1) {
-      tgn = fetch_scalar(kc + 32, ra1, rb1);
+      tgn = (sampled && hopsP) ? (raw_t)hop1 : fetch_scalar(kc + 32, ra1, rb1);
       if (rawj) rb1 &= (row_t)0x00ffffffu;
       Stage::issue(stage_mem, stage ^ 1, 0, tid, xa + (size_t)ra1 * E);
       Stage::issue(stage_mem, stage ^ 1, 1, tid, xb + (size_t)rb1 * E);
@@ -305,7 +330,8 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     ahead.advance(ps);
     bool v2 = kc + 64 < kend;
     row_t ra2 = kNoRow, rb2 = kNoRow;
-    if (v2) load_rows(kc + 64, ra2, rb2);
+    unsigned hop2 = 0;
+    if (v2) load_rows(kc + 64, ra2, rb2, hop2);
 
     // (4) the math
     T gx[E], gy[E];
@@ -357,7 +383,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     // (6) rotate the pipeline
     kc += 32;
     ra0 = ra1; rb0 = rb1; tg0 = tgn; v0 = v1;
-    ra1 = ra2; rb1 = rb2; v1 = v2;
+    ra1 = ra2; rb1 = rb2; hop1 = hop2; v1 = v2;
     stage ^= 1;
   }
   flush();
