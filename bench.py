@@ -199,15 +199,19 @@ class NvlinkCounter:
             self.h = None
 
     def _read(self):
-        try:
-            vals = self.nv.nvmlDeviceGetFieldValues(self.h, [(f, 0xFFFFFFFF) for f in self.fields])  # scope: all links
-            return [int(v.value.ullVal) for v in vals]
-        except Exception:  # noqa: BLE001
+        """[tx KiB, rx KiB] summed over the links (scope id = link number; a few drivers also take UINT_MAX = all)."""
+        tot = [0, 0]
+        got = False
+        for link in range(18):
             try:
-                vals = self.nv.nvmlDeviceGetFieldValues(self.h, self.fields)
-                return [int(v.value.ullVal) for v in vals]
+                vals = self.nv.nvmlDeviceGetFieldValues(self.h, [(f, link) for f in self.fields])
             except Exception:  # noqa: BLE001
-                return None
+                break
+            for k, v in enumerate(vals):
+                if getattr(v, 'nvmlReturn', 0) == 0:
+                    tot[k] += int(v.value.ullVal)
+                    got = True
+        return tot if got else None
 
     def start(self):
         self.t0 = self._read() if self.h is not None else None
@@ -218,13 +222,18 @@ class NvlinkCounter:
             return {'available': False}
         tx, rx = (t1[0] - self.t0[0]) * 1024, (t1[1] - self.t0[1]) * 1024
         return {'available': True, 'tx_bytes_per_step': tx / steps, 'rx_bytes_per_step': rx / steps,
-                'source': 'NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX over the device-timed region'}
+                'source': 'NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX, summed over the links, across 5 extra steps'}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port): same step on a bounded sample of the workload
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_step_rate(log2_pairs, steps, warmup, seed=0):
+def cpu_step_rate(log2_pairs, steps, warmup, seed=0, device='cpu'):
+    """The reference's implementation of the step (oracle port: the same torch / LAPACK calls) on a bounded sample.
+    device='cpu': the host cores (the reference arm).  device='cuda': the same torch-op path on the same B200 -- the
+    "second comparator" of SURVEY 8(d): what the reference's own PyTorch code does when its tensors live on the GPU
+    (run.py:33-35), except that torch.linalg.eigh stays on the device instead of round-tripping through the host as
+    linalg/torch_batch.py:94-135 does (cpu_offload=True), which only flatters the comparator."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import manifolds_oracle as O
     cores = os.cpu_count() or 1
@@ -233,19 +242,23 @@ def cpu_step_rate(log2_pairs, steps, warmup, seed=0):
     n = max(64, P // 8)  # same pairs-per-node ratio as the full workload (2^24 pairs / 2M nodes)
     gen = torch.Generator().manual_seed(seed)
     orc = O.SpdOracle(4)
-    x = orc.rand(n, ir=0.1, dtype=torch.float32, generator=gen)
-    I = torch.randint(n, (P,), generator=gen)
-    J = (I + 1 + torch.randint(n - 1, (P,), generator=gen)) % n
-    t = torch.randint(1, 9, (P,), generator=gen).float().pow(2) / 64.0
-    sp = torch.nn.functional.softplus(torch.tensor(0.5))
+    x = orc.rand(n, ir=0.1, dtype=torch.float32, generator=gen).to(device)
+    I = torch.randint(n, (P,), generator=gen).to(device)
+    J = ((I.cpu() + 1 + torch.randint(n - 1, (P,), generator=gen)) % n).to(device)
+    t = (torch.randint(1, 9, (P,), generator=gen).float().pow(2) / 64.0).to(device)
+    sp = torch.nn.functional.softplus(torch.tensor(0.5)).to(device)
     state = {}
     times = []
     for k in range(warmup + steps):
+        if device != 'cpu':
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         xr = x.clone().requires_grad_()
         loss = O.quotient_loss(t, sp * orc.dist2(xr[I], xr[J]), 1.0, 1)
         loss.backward()
         x = O.radam_step(orc, x, xr.grad, state, lr=0.01, max_grad_norm=100, exact=True).detach()
+        if device != 'cpu':
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if k >= warmup:
             times.append(dt)
@@ -626,8 +639,6 @@ def main():
     if rank == 0:
         clocks.start()
     launches0 = _lib.launch_count()
-    if nvl:
-        nvl.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     loss = None
@@ -635,7 +646,13 @@ def main():
         loss = trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
     t1.record()
     barrier()
-    nvlink = nvl.stop(args.steps) if nvl else None
+    nvlink = None
+    if nvl:  # NVLink payload bytes per step, from the driver's counters, over a few extra (untimed) steps
+        nvl.start()
+        for k in range(5):
+            trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
+        barrier()
+        nvlink = nvl.stop(5)
     launches = _lib.launch_count() - launches0
     _ops.pairs_loss_fused = orig
     trainer.opt.step = opt_step
@@ -733,6 +750,15 @@ def main():
     if not args.no_cpu_baseline:
         rate, med, cores, sample = cpu_step_rate(args.cpu_pairs_log2, 3, 1)
         line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+        if world == 1:
+            try:  # SURVEY 8(d) second comparator: the same torch-op path with its tensors on this B200
+                rate_g, med_g, _, sample_g = cpu_step_rate(args.cpu_pairs_log2, 3, 1, device='cuda')
+                line['cpu_baseline']['torch_ops_on_this_gpu'] = {
+                    'value': rate_g, 'unit': UNIT, 'sample': sample_g,
+                    'what': "the reference's PyTorch-op implementation (oracle port: batched torch.linalg.cholesky / "
+                            'eigh, autograd, index_put_ scatter) with every tensor on the B200'}
+            except Exception as e:  # noqa: BLE001 -- a comparator must not take the bench line down
+                line['cpu_baseline']['torch_ops_on_this_gpu'] = {'unavailable': repr(e)[:200]}
     if world == 1 and not args.no_secondary:
         del trainer, emb, dev_batches, levels
         torch.cuda.empty_cache()

@@ -16,7 +16,9 @@ import os
 import torch
 from torch.nn.functional import softplus
 
+from . import _lib as L
 from . import _ops
+from . import _torch_ops
 from .modules import ManifoldParameter, _softplus_value
 from .parallel import RowShards, allreduce_step_buffers, try_peer_arena
 
@@ -156,7 +158,15 @@ class PairTrainer:
         # softplus(scale) is re-read every step (cached on the parameter until somebody steps it or loads a snapshot);
         # the trainer itself does not train the scale: acc[1] (sum l' d2) is there for a caller who does
         sp = _softplus_value(self.emb.scales[0])
-        _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, sp, self.grad, self.acc)
+        if (pairs.mode == L.GM_PAIRS_LIST and self.man.spec.kind != L.GM_UNIVERSAL
+                and targets.mode in (L.GM_TGT_HOPS_PACKED, L.GM_TGT_HOPS_U8, L.GM_TGT_HOPS_U16)):
+            # explicit pair lists: through the registered custom op (torch.ops.graphembed_b200.pairs_loss_fused)
+            torch.ops.graphembed_b200.pairs_loss_fused(
+                self.x.detach(), pairs.idx_i, pairs.idx_j, targets.data, *_torch_ops.manifold_args(self.man.spec),
+                loss_spec.kind, bool(loss_spec.inc_l1), bool(loss_spec.inc_l2), float(loss_spec.alpha),
+                float(loss_spec.eps), float(targets.max_sq), float(sp), self.grad, self.acc)
+        else:
+            _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, sp, self.grad, self.acc)
         if self.peer is not None:
             self.opt.step()  # ONE kernel: cross-GPU barrier, pull+sum gradients, update, push points, sum the loss
             return self.peer.acc_out[0]
@@ -295,3 +305,55 @@ class PairTrainer:
         if defer_loss:  # read this step's loss back asynchronously, hand out the previous step's
             return self._queue_loss_read()
         return loss.item()
+
+
+class ProductPairTrainer:
+    """(I, J, hops) pair batches through a PRODUCT-manifold embedding -- BASELINE config 3 ("product SPD 3x3 x Lorentz 5,
+    sampled pairs").  The distance of a pair is sum_f softplus(scale_f) * d_f^2 (modules.py:84-88); one step is
+
+        F x gm_pairs_dist2  ->  gm_product_loss (loss term, dL/dm per pair, sum l' d2_f per factor)
+        ->  F x gm_pairs_grad (scatter-add of softplus(scale_f) * dL/dm * d(d2_f)/dx)  ->  the optimizer kernels
+
+    with the reference's semantics of `loss.backward(); optimizer.step()`.  `scale_optimizer` (optional: any optimizer
+    over embedding.scales, e.g. the second RiemannianAdam group of experiments/run_grid.py:25-28) receives
+    d loss / d scale_f = sigmoid(scale_f) * sum_k l'_k d2_f,k and is stepped after the points.  With a process group
+    the pair batch is sharded over the ranks and gradients, loss and scale gradients are all-reduced (replicated
+    update)."""
+
+    def __init__(self, embedding, optimizer, objective, max_hops_sq, alpha=1.0, scale_optimizer=None,
+                 process_group=None):
+        self.emb, self.opt, self.obj = embedding, optimizer, objective
+        self.max_hops_sq, self.alpha, self.pg = float(max_hops_sq), alpha, process_group
+        self.scale_opt = scale_optimizer
+        self.xs = list(embedding.xs)
+        self.mans = list(embedding.manifolds)
+        self.scales = list(getattr(embedding, 'scales', ()))
+        if any(hasattr(m, 'get_c') for m in self.mans):
+            raise ValueError('Universal factors carry a curvature gradient: train them through BatchedObjective')
+        self.grads = [torch.zeros_like(x, memory_format=torch.contiguous_format) for x in self.xs]
+        for x, g in zip(self.xs, self.grads):
+            x.grad = g
+
+    def step(self, idx_i, idx_j, hops, epoch=1):
+        """One training step on device tensors (int32/int64 indices, uint8/int16 hop counts); returns the (device,
+        float64) loss of the batch."""
+        dev = self.xs[0].device
+        pairs = _ops.PairSet.from_lists(idx_i, idx_j, dev)
+        targets = _ops.TargetSpec.hops(hops, self.max_hops_sq)
+        loss_spec = self.obj.loss_spec(epoch=epoch, alpha=self.alpha)
+        sps = [_softplus_value(s) for s in self.scales] if self.scales else [1.0] * len(self.xs)
+        d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs) for m, x in zip(self.mans, self.xs)]
+        acc, g = _ops.product_loss(d2s, sps, targets, loss_spec)
+        for m, x, gx, sp in zip(self.mans, self.xs, self.grads, sps):
+            gx.zero_()
+            _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, gx, gx, coef=sp)
+        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
+            for gx in self.grads:
+                torch.distributed.all_reduce(gx, group=self.pg)
+            torch.distributed.all_reduce(acc, group=self.pg)
+        self.opt.step()
+        if self.scale_opt is not None:
+            for f, s in enumerate(self.scales):
+                s.grad = (acc[1 + f] * torch.sigmoid(s.detach().double())).to(s.dtype).reshape(s.shape)
+            self.scale_opt.step()
+        return acc[0]

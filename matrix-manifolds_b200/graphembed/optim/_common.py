@@ -4,6 +4,7 @@ import torch
 
 from .. import _lib as L
 from .. import _ops
+from .. import _torch_ops
 
 
 def spec_of(param):
@@ -28,8 +29,10 @@ def fused_step(param, grad, cfg, buf1=None, buf2=None):
         if arena is not None:  # multi-GPU owner update over NVLink peer memory (graphembed.parallel.PeerArena):
             # `param` aliases the owned rows of arena.x; the gradient is the sum of every rank's arena.grad rows
             _ops.optim_step_peer(spec, cfg, arena, param.shape[0], buf1, buf2)
-        else:
-            _ops.optim_step(spec, cfg, param.data, grad, buf1, buf2)
+        elif spec.kind == L.GM_UNIVERSAL or grad.dtype != param.dtype or not grad.is_contiguous():
+            _ops.optim_step(spec, cfg, param.data, grad, buf1, buf2)  # needs the curvature tensor / a gradient copy
+        else:  # the registered custom op torch.ops.graphembed_b200.optim_step
+            _torch_ops.optim_step(spec, cfg, param.data, grad, buf1, buf2)
     # The kernel wrote through the raw pointer: neither tensor._version nor data_ptr() changed, so anything cached
     # against them (modules._softplus_value: the host copy of softplus(scale)) must be dropped explicitly.
     if getattr(param, '_gm_softplus', None) is not None:

@@ -1,7 +1,7 @@
 """Round-2 fixtures, all produced by the REAL reference (dalab/matrix-manifolds `graphembed`, imported from
 /root/reference through oracle/ref_import.py) on CPU.  Run in the build container only:
 
-    python tests/golden/make_golden_r2.py [graphs] [truth] [config1] [steps]
+    python tests/golden/make_golden_r2.py [graphs] [truth] [config1] [steps] [precision]
 
   graphs  : tests/golden/graphs/<name>.npz -- the integer-labelled edge lists of the graphs BASELINE.json's configs
             1-4 name (tree1000, power, facebook, condmat), exactly as the reference's loader numbers the nodes
@@ -15,6 +15,10 @@
             data/tree1000.edges.gz -> SPD 3x3, fp64, all 499 500 pairs per step, QuotientLoss, RiemannianSGD(lr .01,
             exact, clip 20) (experiments/run_grid.py:30-33), 5 epochs, validation every epoch; and the same with the
             scale ("curvature") parameter in a second RiemannianSGD group as run_grid.py:30-33 builds it.
+  precision: precision_f1.npz -- per-layer F1 statistics of the REFERENCE's own native FastPrecision
+            (graphembed/pyx/impl/precision.cpp compiled unmodified into oracle/_ref/, see oracle/Makefile) on the four
+            random graphs of precision_map.npz with random fp32 / fp64 distances: LayerMeanF1Scores (all degrees and a
+            degree window), LayerMeanAverageF1Scores, MeanAveragePrecision, NodesPerLayer.
   steps   : config<k>_step_<dtype>.npz -- one teacher-forced training step (512-node batch = 130 816 pairs, the
             reference's canonical batch, run_grid.py:131) of configs 2a / 2b / 3a / 3b / 4 on the shipped graphs:
             loss, gradient rows, points / optimizer state after one RiemannianAdam step (run_grid.py:25-28), in the
@@ -333,8 +337,36 @@ def make_step(tag, hops):
     return out
 
 
+def make_precision_f1():
+    sys.path.insert(0, os.path.join(HERE, '..'))
+    import precision_ref as R
+    from helpers_precision import TAGS, csr_of, load_precision_golden
+    assert R.available(), 'run `make -C oracle` first (builds oracle/_ref/libprecision_ref.so from the reference)'
+    g = load_precision_golden()
+    out = {}
+    rng = np.random.RandomState(11)
+    for tag in TAGS:
+        n = int(g[f'{tag}_n'])
+        ref = R.FastPrecisionRef(*csr_of(n, g[f'{tag}_edges']))
+        pd32 = g[f'{tag}_pdists'].astype(np.float32)
+        pd64 = rng.rand(n * (n - 1) // 2)
+        out[f'{tag}_pd64'] = pd64
+        out[f'{tag}_npl'] = ref.nodes_per_layer()
+        for name, pd in (('f32', pd32), ('f64', pd64)):
+            m, s_ = ref.layer_mean_f1_scores(pd)
+            out[f'{tag}_{name}_f1_mean'], out[f'{tag}_{name}_f1_std'] = m, s_
+            m, s_ = ref.layer_mean_f1_scores(pd, 3, 8)
+            out[f'{tag}_{name}_f1w_mean'], out[f'{tag}_{name}_f1w_std'] = m, s_
+            m, s_ = ref.layer_mean_average_f1_scores(pd.astype(np.float64))
+            out[f'{tag}_{name}_af_mean'], out[f'{tag}_{name}_af_std'] = m, s_
+            out[f'{tag}_{name}_map'] = np.array(ref.mean_average_precision(pd))
+    return out
+
+
 def main():
-    what = set(sys.argv[1:]) or {'graphs', 'truth', 'config1', 'steps'}
+    what = set(sys.argv[1:]) or {'graphs', 'truth', 'config1', 'steps', 'precision'}
+    if 'precision' in what:
+        np.savez_compressed(os.path.join(HERE, 'precision_f1.npz'), **make_precision_f1())
     os.makedirs(os.path.join(HERE, 'graphs'), exist_ok=True)
     hops = {}
 

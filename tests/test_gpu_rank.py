@@ -99,3 +99,25 @@ def test_embedding_distances_on_a_larger_graph():
     rc = L.lib().gm_rank_metrics(L.GM_F64, L.ptr(z), L.ptr(zi), 20000, 0, 1, 1, 9, 5, L.ptr(z), L.ptr(z), L.ptr(zi),
                                  L.ptr(z), L.ptr(z), L.ptr(zi), L.ptr(z), None)
     assert rc == -2  # 20000 fp64 keys do not fit one SM's shared memory
+
+
+@pytest.mark.parametrize('name', ['f32', 'f64'])
+@pytest.mark.parametrize('tag', TAGS)
+def test_f1_vs_reference_native_fixture(tag, name):
+    """gm_rank_metrics against the outputs of the reference's own native FastPrecision on random distances
+    (tests/golden/precision_f1.npz, from graphembed/pyx/impl/precision.cpp compiled unmodified -- oracle/Makefile)."""
+    import os
+    from helpers import GOLDEN
+    from graphembed.pyx import FastPrecision
+    g = load_precision_golden()
+    with np.load(os.path.join(GOLDEN, 'precision_f1.npz')) as z:
+        f = {k: z[k] for k in z.files}
+    n = int(g[f'{tag}_n'])
+    fp = FastPrecision(nx_graph(n, g[f'{tag}_edges']))
+    pd = g[f'{tag}_pdists'].astype(np.float32) if name == 'f32' else f[f'{tag}_pd64']
+    assert np.array_equal(fp.nodes_per_layer(), f[f'{tag}_npl'])
+    assert abs(fp.mean_average_precision(pd) - float(f[f'{tag}_{name}_map'])) < 1e-12
+    for got, key in ((fp.layer_mean_f1_scores(pd), 'f1'), (fp.layer_mean_f1_scores(pd, min_degree=3, max_degree=8), 'f1w'),
+                     (fp.layer_mean_average_f1_scores(pd), 'af')):
+        assert np.allclose(got[0], f[f'{tag}_{name}_{key}_mean'], rtol=1e-11, atol=0, equal_nan=True)
+        assert np.allclose(got[1], f[f'{tag}_{name}_{key}_std'], atol=1e-11, equal_nan=True)

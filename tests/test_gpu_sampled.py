@@ -135,3 +135,82 @@ def test_full_size_draw_config5():
     assert torch.equal(outs[0][1], outs[1][1])
     assert rel_err(outs[0][0], outs[1][0]) < 1e-12
     assert rel_err(outs[0][2], outs[1][2]) < 1e-5 and torch.isfinite(outs[0][2]).all()
+
+
+def test_registered_custom_ops_match_the_python_api():
+    """torch.ops.graphembed_b200.* (the torch custom-op layer over the C-ABI) against the manifold API / _ops."""
+    from graphembed import _ops, _torch_ops, _lib as L
+    from graphembed.data import bfs_levels, edges_to_csr
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    ns = torch.ops.graphembed_b200
+    man = SymmetricPositiveDefinite(4)
+    torch.manual_seed(0)
+    x = man.rand(500, out=torch.empty(0, device=DEV, dtype=torch.float32), ir=0.7).contiguous()
+    g = torch.Generator().manual_seed(0)
+    I = torch.randint(500, (4000,), generator=g, dtype=torch.int32).to(DEV)
+    J = ((I.cpu() + 1 + torch.randint(499, (4000,), generator=g, dtype=torch.int32)) % 500).to(DEV)
+    H = torch.randint(1, 9, (4000,), generator=g, dtype=torch.uint8).to(DEV)
+    margs = _torch_ops.manifold_args(man.spec)
+    assert torch.equal(ns.pair_dist2(x, I, J, *margs), man.pair_dist2(x, I, J))
+    grad_a, acc_a = torch.zeros_like(x), torch.zeros(2, dtype=torch.float64, device=DEV)
+    ns.pairs_loss_fused(x, I, J, H, *margs, L.GM_LOSS_QUOTIENT, True, True, 1.0, 0.5, 64.0, 0.9, grad_a, acc_a)
+    grad_b = torch.zeros_like(x)
+    acc_b, _ = _ops.pairs_loss_fused(man.spec, x, _ops.PairSet.from_lists(I, J, DEV), _ops.TargetSpec.hops(H, 64.0),
+                                     _ops.LossSpec(L.GM_LOSS_QUOTIENT, True, True, alpha=1.0, eps=0.5), 0.9, grad_b)
+    assert rel_err(acc_a, acc_b) < 1e-12 and rel_err(grad_a, grad_b) < 1e-5
+    rowptr, colidx = edges_to_csr(50, np.stack([np.arange(1, 50), np.arange(49) // 2], 1))
+    rp, ci = torch.as_tensor(rowptr, device=DEV), torch.as_tensor(colidx, device=DEV)
+    src = torch.arange(7, dtype=torch.int32, device=DEV)
+    assert torch.equal(ns.bfs_levels(rp, ci, src), bfs_levels(rp, ci, sources=src, device=DEV))
+    with pytest.raises(NotImplementedError):  # no CPU kernel behind the ops
+        ns.pair_dist2(x.cpu(), I.cpu(), J.cpu(), *margs)
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_product_pair_trainer_vs_oracle(dtype):
+    """BASELINE config 3's "product SPD 3x3 x Lorentz 5, sampled pairs": three steps of ProductPairTrainer (points by
+    RiemannianAdam, the two scales by a second RiemannianAdam as run_grid.py:25-28 groups them) against the oracle's
+    autograd + optimizer restatement on the same explicit pair lists."""
+    import manifolds_oracle as O
+    from graphembed.engine import ProductPairTrainer
+    from graphembed.manifolds import Lorentz, SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+    N, P = 400, 6000
+    torch.manual_seed(3)
+    emb = ManifoldEmbedding(N, [SymmetricPositiveDefinite(3), Lorentz(5)], device=DEV, dtype=dtype)
+    with torch.no_grad():  # spread the default init (points within 1e-2 of each other are fp32-cancellation limited)
+        emb.xs[0].copy_(emb.manifolds[0].rand(N, out=torch.empty(0, device=DEV, dtype=dtype), ir=0.8))
+        emb.xs[1].copy_(emb.manifolds[1].rand(N, out=torch.empty(0, device=DEV, dtype=dtype), ir=0.8))
+    x0 = [x.detach().cpu().clone() for x in emb.xs]
+    opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
+    sopt = RiemannianAdam(list(emb.scales), lr=0.01)
+    tr = ProductPairTrainer(emb, opt, QuotientLoss(), max_hops_sq=64.0, scale_optimizer=sopt)
+    g = torch.Generator().manual_seed(1)
+    oracles = [O.SpdOracle(3), O.LorentzOracle(5)]
+    xs = [t.clone() for t in x0]
+    scales = [torch.tensor(0.5, dtype=dtype) for _ in range(2)]
+    states, sstates = [{}, {}], [{}, {}]
+    eu = O.EuclideanOracle(1)
+    for step in range(3):
+        I = torch.randint(N, (P,), generator=g, dtype=torch.int32)
+        J = ((I + 1 + torch.randint(N - 1, (P,), generator=g, dtype=torch.int32)) % N).int()
+        H = torch.randint(1, 9, (P,), generator=g, dtype=torch.uint8)
+        loss = tr.step(I.to(DEV), J.to(DEV), H.to(DEV), epoch=step + 1).item()
+        leaves = [x.clone().requires_grad_() for x in xs]
+        sl = [s.clone().requires_grad_() for s in scales]
+        m = O.product_dist2(oracles, leaves, sl, lambda o, x: o.dist2(x[I.long()], x[J.long()]))
+        lo = O.quotient_loss(H.to(dtype).pow(2) / 64.0, m, 1.0, step + 1)
+        lo.backward()
+        t = 1e-10 if dtype == torch.float64 else 2e-5
+        assert abs(loss - lo.item()) <= t * abs(lo.item()), (step, loss, lo.item())
+        xs = [O.radam_step(o, x, leaf.grad, st, lr=0.01, max_grad_norm=100, exact=True).detach()
+              for o, x, leaf, st in zip(oracles, xs, leaves, states)]
+        scales = [O.radam_step(eu, s.reshape(1), sg.grad.reshape(1), st, lr=0.01).reshape(()).detach()
+                  for s, sg, st in zip(scales, sl, sstates)]
+    t = 1e-10 if dtype == torch.float64 else 2e-5
+    for f in range(2):
+        assert rel_err(emb.xs[f].detach(), xs[f]) < t
+        assert abs(float(emb.scales[f].detach()) - float(scales[f])) <= t * abs(float(scales[f]))
+    assert abs(float(emb.scales[0].detach()) - 0.5) > 1e-3  # the scales moved, and the kernels followed them

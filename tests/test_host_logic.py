@@ -122,6 +122,8 @@ def test_softplus_cache_dropped_when_a_riemannian_optimizer_steps_the_scale(monk
         assert x.data_ptr() == ptr_before
 
     monkeypatch.setattr(_ops, 'optim_step', fake_optim_step)
+    from graphembed import _torch_ops
+    monkeypatch.setattr(_torch_ops, 'optim_step', fake_optim_step)  # (the registered op has no CPU kernel)
     s = torch.nn.Parameter(torch.tensor(0.5, dtype=torch.float64))
     v0 = _softplus_value(s)
     assert _softplus_value(s) == v0 and s._gm_softplus is not None
@@ -154,3 +156,20 @@ def test_sampler_oracle_is_counter_based_and_uniform():
     counts = np.bincount(J, minlength=N)
     assert counts.max() < 3 * counts.mean() and (counts > 0).mean() > 0.99
     assert (S.sample_pairs(src, levels, per, seed=1235)[1] != J).mean() > 0.99
+
+
+def test_custom_ops_are_registered_and_have_no_cpu_kernel():
+    """torch.ops.graphembed_b200.*: schema-checked custom ops over the C-ABI, CUDA only (no CPU fallback)."""
+    import graphembed  # noqa: F401
+    from graphembed import _torch_ops  # noqa: F401
+    ns = torch.ops.graphembed_b200
+    for name in ('pair_dist2', 'pairs_loss_fused', 'optim_step', 'bfs_levels'):
+        assert hasattr(ns, name)
+    schema = str(ns.pairs_loss_fused.default._schema)
+    assert 'Tensor(a!) grad' in schema and 'Tensor(b!) acc' in schema
+    with pytest.raises(NotImplementedError):
+        ns.pair_dist2(torch.zeros(3, 2, 2), torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64), 0, 2,
+                      0, 0, 1e-8, 1e8)
+    with pytest.raises(NotImplementedError):
+        ns.bfs_levels(torch.zeros(3, dtype=torch.int32), torch.zeros(2, dtype=torch.int32),
+                      torch.zeros(1, dtype=torch.int32))
