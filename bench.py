@@ -71,6 +71,9 @@ def parse():
                     'explicit pair lists (4 B/pair, PCIe / host-memory bound beyond 2 GPUs of one host), `sampled` uploads '
                     'the source ids and draws the pairs inside the pair kernel (one extra random byte read per pair); '
                     'auto = lists up to 2 GPUs, sampled beyond')
+    ap.add_argument('--lists3', action='store_true', help='--e2e lists: upload 3-byte pair words (pack_hops3) instead of '
+                    '4-byte ones; measured on one B200 it is NOT faster (1.339 vs 1.31 ms per step: the step is not PCIe '
+                    'bound at 4 B/pair and the extra expansion kernel costs 0.03 ms)')
     ap.add_argument('--no-secondary', action='store_true', help='skip the secondary lines (configs 1-4, BFS)')
     ap.add_argument('--workload', default='5', help="'5' (default, the bench line) or one of 1, 2a, 2b, 3a, 3b, 4 (or a "
                     "comma list / 'all'): epoch time of that BASELINE config -- on the GPU through TrainingEngine, or "
@@ -107,7 +110,7 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, 
     hop^2; hop targets come from the multi-source BFS kernel.  (sources, offsets) is the source-grouped form of I, the
     last entry the packed 4-byte-per-pair form of (J, hops)."""
     from graphembed.data import bfs_levels, edges_to_csr
-    from graphembed.engine import pack_hops
+    from graphembed.engine import pack_hops, pack_hops3
     from graphembed import _lib as L
     P = 1 << log2_pairs
     per_src = max(1, P // N_SOURCES)
@@ -136,8 +139,10 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, 
         assert int(hops.min().item()) >= 1 and int(hops.max().item()) < 255
         offsets = (torch.arange(n_src + 1, dtype=torch.int64) * per_src)
         hops_h = hops.cpu()
+        three = n_nodes <= (1 << 21) and int(hops_h.max()) <= 8  # (j, hops - 1) fit 21 + 3 bits: 3 bytes per pair
         batches.append((I.pin_memory(), J.pin_memory(), hops_h.pin_memory(), src.contiguous().pin_memory(),
-                        offsets.pin_memory(), pack_hops(J, hops_h).pin_memory()))
+                        offsets.pin_memory(), pack_hops(J, hops_h).pin_memory(),
+                        pack_hops3(J, hops_h).pin_memory() if three else None))
         if keep_levels:
             kept.append(levels)  # (n_src, N) uint8, resident: the hop counts of this batch's landmark sources
         del levels
@@ -249,14 +254,18 @@ def cpu_step_rate(log2_pairs, steps, warmup, seed=0, device='cpu'):
     sp = torch.nn.functional.softplus(torch.tensor(0.5)).to(device)
     state = {}
     times = []
+    import contextlib
+    # tensors the port creates itself (identities for the triangular solves ...) must land on the same device
+    factory_device = torch.device(device) if device != 'cpu' else contextlib.nullcontext()
     for k in range(warmup + steps):
         if device != 'cpu':
             torch.cuda.synchronize()
         t0 = time.perf_counter()
-        xr = x.clone().requires_grad_()
-        loss = O.quotient_loss(t, sp * orc.dist2(xr[I], xr[J]), 1.0, 1)
-        loss.backward()
-        x = O.radam_step(orc, x, xr.grad, state, lr=0.01, max_grad_norm=100, exact=True).detach()
+        with factory_device:
+            xr = x.clone().requires_grad_()
+            loss = O.quotient_loss(t, sp * orc.dist2(xr[I], xr[J]), 1.0, 1)
+            loss.backward()
+            x = O.radam_step(orc, x, xr.grad, state, lr=0.01, max_grad_norm=100, exact=True).detach()
         if device != 'cpu':
             torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -667,7 +676,11 @@ def main():
     if e2e_mode == 'lists':
         # source-grouped upload (sources, offsets, j, hops): 4-5 B/pair over PCIe; the next batch is uploaded on a
         # second stream while this one computes; every step ends with a device->host read of the loss
+        use3 = args.lists3 and not args.unpacked and all(b[6] is not None for b in batches)
+
         def grouped(b):
+            if use3:
+                return (b[3], b[4], b[6], None)
             return (b[3], b[4], b[1], b[2]) if args.unpacked else (b[3], b[4], b[5], None)
 
         def e2e_step(k):
@@ -675,7 +688,9 @@ def main():
                                              next_batch=grouped(batches[(k + 1) % nb]), defer_loss=True)
         h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
         e2e_api = ('graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
-                   + ('int32 j, uint8 hops' if args.unpacked else 'int32 j | hops << 24') + '; per rank); next batch '
+                   + ('int32 j, uint8 hops' if args.unpacked else
+                      '3-byte words j | (hops - 1) << 21, expanded on the device' if use3 else 'int32 j | hops << 24')
+                   + '; per rank); next batch '
                    'uploaded on a second stream, loss read back through pinned memory one step late')
     else:
         # the step's input is its list of BFS sources: 4 KB from pinned host memory per step; targets are drawn inside

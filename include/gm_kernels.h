@@ -272,7 +272,7 @@ int gm_train_epoch_product(int32_t F, const gm_manifold_t* mans, const gm_optim_
  * gm_peer_open (CUDA IPC, one process per GPU on one NVLink domain).  Each rank's flag block is
  * GM_PEER_FLAG_BYTES of zero-initialised arena memory. */
 #define GM_MAX_PEERS 8
-#define GM_PEER_FLAG_BYTES ((2 * GM_MAX_PEERS + 1) * 8)
+#define GM_PEER_FLAG_BYTES ((2 * GM_MAX_PEERS + 2) * 8)
 #define GM_PEER_HANDLE_BYTES 64
 typedef struct gm_peers {
   int32_t world, rank;
@@ -284,6 +284,12 @@ typedef struct gm_peers {
   const void* acc[GM_MAX_PEERS];  /* rank r's double[n_acc] step accumulator (loss, scale grads) or NULL    */
   void* acc_out;                  /* local double[n_acc]: sum over ranks of acc                             */
   int32_t n_acc, reserved;
+  void* gsum;                     /* optional LOCAL workspace of N_owned rows (dtype of the points).  Non-NULL selects the
+                                     pipelined exchange: the owned rows are cut into chunks; a light kernel pulls and
+                                     sums chunk c+1 of every rank's gradient table into gsum over NVLink while a second
+                                     kernel, on a second stream, updates chunk c from gsum and pushes the new rows to
+                                     every rank -- inbound and outbound NVLink traffic overlap instead of alternating
+                                     inside one kernel.  NULL: the single fused kernel                         */
 } gm_peers_t;
 int gm_peer_alloc(size_t bytes, void** ptr);            /* zero-filled device memory on the current device  */
 int gm_peer_free(void* ptr);
@@ -342,6 +348,13 @@ int gm_gather_levels(int32_t level_bytes, const void* levels, int32_t N, const i
  * than the (i, j) lists base.py:62-63 builds with triu_indices. */
 int gm_expand_groups(const int32_t* group_row, const int64_t* offsets, int32_t G, int32_t* out_i, int64_t P,
                      gm_stream_t stream);
+
+/* Upload format of sampled pair batches, 3 bytes per pair: little-endian 24-bit words, bits 0-20 = second-endpoint row
+ * (N <= 2^21), bits 21-23 = hop count - 1 (1 <= hops <= 8).  Expands them on the device to the 4-byte words of
+ * GM_TGT_HOPS_PACKED, out[k] = (hops << 24) | j -- the end-to-end step is PCIe bound at 4 bytes per pair on one GPU
+ * (67 MB per 2^24-pair step), this is 25 % less over the bus for a 20 us kernel.  src3: 4-byte aligned, 3*P bytes
+ * (readable up to the next multiple of 4); out: 16-byte aligned, P words. */
+int gm_unpack_pairs3(const void* src3, int64_t P, int32_t* out, gm_stream_t stream);
 
 /* ---- ranking metrics (evaluation) ------------------------------------------------------------------------------
  * FastPrecision on the GPU (graphembed/pyx/impl/precision.cpp:249-291 mean average precision, :321-446 per-layer F1

@@ -1,7 +1,9 @@
 // C-ABI entry points of libgm_b200.so (declared in include/gm_kernels.h):
 // argument validation and dispatch to the templated kernel launchers.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "gm_point_kernels.cuh"
 
@@ -10,6 +12,23 @@ namespace gm {
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int check_launch() { return (int)cudaGetLastError(); }
+
+// one side stream + event set per device for the pipelined exchange (created on first use, kept for the process)
+PeerPipe& peer_pipe() {
+  static std::mutex mu;
+  static PeerPipe pipes[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  PeerPipe& p = pipes[dev & 63];
+  if (!p.side) {
+    if (cudaStreamCreateWithFlags(&p.side, cudaStreamNonBlocking) != cudaSuccess) { p.side = nullptr; return p; }
+    for (auto& e : p.pulled) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p.joined, cudaEventDisableTiming);
+  }
+  return p;
+}
+
 
 int validate_pairs(const gm_pairs_t* p) {
   if (!p) return GM_ENULL;
@@ -450,6 +469,13 @@ int gm_optim_step_peer(const gm_manifold_t* man, const gm_optim_t* opt, const gm
   }
   if (peers->n_acc > 0 && !peers->acc_out) return GM_ENULL;
   pt.acc_out = (double*)peers->acc_out; pt.n_acc = peers->n_acc;
+  pt.gsum = peers->gsum;
+  {
+    static const long long timeout_s = [] { const char* e = getenv("GM_PEER_TIMEOUT_S"); return e ? atoll(e) : 300LL; }();
+    static const int chunks = [] { const char* e = getenv("GM_PEER_CHUNKS"); return e ? atoi(e) : 4; }();
+    pt.timeout_ns = timeout_s > 0 ? (unsigned long long)timeout_s * 1000000000ull : 0ull;
+    pt.chunks = chunks;
+  }
   PointArgs a{};
   a.kind = man->kind; a.dtype = man->dtype; a.n = man->n; a.p = man->p; a.flags = man->flags;
   a.wmin = man->wmin; a.wmax = man->wmax; a.c_dev = man->c_dev;

@@ -622,6 +622,24 @@ __global__ void expand_groups_kernel(const int* __restrict__ row, const long lon
   }
 }
 
+// 3-byte pair words -> the 4-byte packed form of GM_TGT_HOPS_PACKED: 4 pairs (12 bytes in, 16 bytes out) per thread
+__global__ void unpack_pairs3_kernel(const unsigned* __restrict__ src, long long P, int* __restrict__ out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pairs
+  const long long k = 4 * q;
+  if (k >= P) return;
+  auto expand = [](unsigned w24) -> int { return (int)((w24 & 0x1FFFFFu) | (((w24 >> 21) + 1u) << 24)); };
+  if (k + 3 < P) {
+    const unsigned a = src[3 * q], b = src[3 * q + 1], c = src[3 * q + 2];
+    const int4 v = make_int4(expand(a & 0xFFFFFFu), expand((a >> 24) | ((b & 0xFFFFu) << 8)),
+                             expand((b >> 16) | ((c & 0xFFu) << 16)), expand(c >> 8));
+    *reinterpret_cast<int4*>(out + k) = v;
+  } else {
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(src);
+    for (long long e = k; e < P; ++e)
+      out[e] = expand((unsigned)bytes[3 * e] | ((unsigned)bytes[3 * e + 1] << 8) | ((unsigned)bytes[3 * e + 2] << 16));
+  }
+}
+
 template <typename L>
 __global__ void gather_levels_kernel(const L* __restrict__ levels, int N, const int* __restrict__ slot,
                                      const int* __restrict__ col, long long P, L* __restrict__ out) {
@@ -720,6 +738,18 @@ int gm_gather_levels(int32_t level_bytes, const void* levels, int32_t N, const i
   if (blocks > 0x7fffffffLL) return GM_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   GM_LEVEL_SWITCH(level_bytes, (gather_levels_kernel<L><<<(unsigned)blocks, 256, 0, st>>>((const L*)levels, N, src_slot, col, P, (L*)out)));
+  note_launch();
+  return check_launch();
+}
+
+int gm_unpack_pairs3(const void* src3, int64_t P, int32_t* out, gm_stream_t stream) {
+  if (P < 0) return GM_EINVAL;
+  if (P == 0) return GM_OK;
+  if (!src3 || !out) return GM_ENULL;
+  if ((reinterpret_cast<size_t>(src3) & 3) || (reinterpret_cast<size_t>(out) & 15)) return GM_EINVAL;
+  long long blocks = ((P + 3) / 4 + 255) / 256;
+  if (blocks > 0x7fffffffLL) return GM_EINVAL;
+  unpack_pairs3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned*)src3, P, out);
   note_launch();
   return check_launch();
 }

@@ -23,6 +23,9 @@ struct PeerTable {
   const double* acc[kMaxPeers];  // every rank's [loss, scale-grad, ...] accumulator (may be null)
   double* acc_out;               // local: sum over ranks of acc[r][0..n_acc)
   int n_acc;
+  void* gsum;                    // local workspace (N_owned rows): non-null selects the pipelined exchange
+  unsigned long long timeout_ns; // flag_wait gives up (traps) after this long; 0 = never
+  int chunks;                    // pipelined exchange: number of row chunks (1..8)
 };
 
 struct PointArgs {
@@ -101,16 +104,19 @@ __device__ __forceinline__ unsigned long long flag_load_acquire(const unsigned l
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// Spin until *p >= epoch.  A peer that never arrives (crashed rank) must not hang the GPU: trap after ~10 s.
-__device__ __forceinline__ void flag_wait(const unsigned long long* p, unsigned long long epoch) {
+// Spin until *p >= epoch.  A peer that never arrives (crashed rank) must not hang the GPU for ever: trap after
+// timeout_ns (PeerTable::timeout_ns: GM_PEER_TIMEOUT_S seconds, default 300 -- rank skew of minutes is legitimate: a
+// rank writing a checkpoint, a slow data loader, a debugger; 0 waits for ever).
+__device__ __forceinline__ void flag_wait(const unsigned long long* p, unsigned long long epoch,
+                                          unsigned long long timeout_ns) {
   unsigned long long t0 = 0;
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
   unsigned spins = 0;
   while (flag_load_acquire(p) < epoch) {
-    if ((++spins & 0x3ff) == 0) {
+    if ((++spins & 0x3ff) == 0 && timeout_ns) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
-      if (t1 - t0 > 10000000000ull) __trap();
+      if (t1 - t0 > timeout_ns) __trap();
     }
     __nanosleep(64);
   }
@@ -186,7 +192,7 @@ peer_optim_kernel(Man man, OptimCfg oc, PeerTable pt, T* __restrict__ buf1, T* _
   const int tid = threadIdx.x;
   unsigned long long* my_flags = pt.flags[pt.rank];
   if (blockIdx.x == 0 && tid < pt.world) flag_store_release(pt.flags[tid] + pt.rank, pt.epoch);
-  if (tid < pt.world) flag_wait(my_flags + tid, pt.epoch);
+  if (tid < pt.world) flag_wait(my_flags + tid, pt.epoch, pt.timeout_ns);
   __syncthreads();
 
   const int cnt = man.count();
@@ -281,9 +287,166 @@ peer_optim_kernel(Man man, OptimCfg oc, PeerTable pt, T* __restrict__ buf1, T* _
     if (tid == 0) my_flags[2 * kMaxPeers] = 0;
     if (tid < pt.world) {
       flag_store_release(pt.flags[tid] + kMaxPeers + pt.rank, pt.epoch);
-      flag_wait(my_flags + kMaxPeers + tid, pt.epoch);
+      flag_wait(my_flags + kMaxPeers + tid, pt.epoch, pt.timeout_ns);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pipelined exchange (PeerTable::gsum != nullptr).  The fused kernel above alternates, inside every block, between
+// pulling (inbound NVLink), computing and pushing (outbound NVLink), so neither direction of the links is ever busy
+// for long.  Here the owned rows are cut into chunks and two kernels run side by side on two streams:
+//   peer_pull_kernel        chunk c+1: gsum[rows] = sum over ranks of their partial gradient rows -- nothing but 16-byte
+//                           peer loads, all ranks' loads of a vector in flight before the first add, few registers, so
+//                           thousands of threads keep the inbound links full
+//   peer_update_push_kernel chunk c: optimizer update from gsum (local), new rows stored into every rank's point table
+// The cross-GPU handshakes stay where the data dependencies are: the FIRST pull kernel of a step publishes "my partial
+// gradients are final" and waits for everyone's; the LAST update kernel publishes "I have read your gradients and
+// written your points" and waits for everyone's (and sums the per-step scalars).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+peer_pull_kernel(PeerTable pt, size_t byte_off, size_t gsum_off, long long nvec, int handshake) {
+  const int tid = threadIdx.x;
+  if (handshake) {
+    unsigned long long* my_flags = pt.flags[pt.rank];
+    if (blockIdx.x == 0 && tid < pt.world) flag_store_release(pt.flags[tid] + pt.rank, pt.epoch);
+    if (tid < pt.world) flag_wait(my_flags + tid, pt.epoch, pt.timeout_ns);
+    __syncthreads();
+  }
+  float4* out = reinterpret_cast<float4*>((char*)pt.gsum + gsum_off);
+  constexpr int U = 2;
+  const long long stride = (long long)gridDim.x * 256 * U;
+  for (long long c0 = (long long)blockIdx.x * 256 * U + tid; c0 < nvec; c0 += stride) {
+    float4 v[kMaxPeers][U];
+    GM_UNROLL for (int r = 0; r < kMaxPeers; ++r) {
+      if (r < pt.world) {
+        const float4* src = reinterpret_cast<const float4*>((const char*)pt.g[r] + byte_off);
+        GM_UNROLL for (int u = 0; u < U; ++u) {
+          const long long c = c0 + (long long)u * 256;
+          v[r][u] = (c < nvec) ? src[c] : float4{};
+        }
+      }
+    }
+    GM_UNROLL for (int u = 0; u < U; ++u) {
+      float4 acc = v[0][u];
+      GM_UNROLL for (int r = 1; r < kMaxPeers; ++r) {
+        if (r < pt.world) {
+          acc = vec_add<T, float4>(acc, v[r][u]);
+        }
+      }
+      const long long c = c0 + (long long)u * 256;
+      if (c < nvec) out[c] = acc;
+    }
+  }
+}
+
+template <class Man, typename T>
+__global__ void __launch_bounds__(128)
+peer_update_push_kernel(Man man, OptimCfg oc, PeerTable pt, T* __restrict__ buf1, T* __restrict__ buf2,
+                        long long row0_chunk, long long rows_chunk, int last) {
+  constexpr int CAP = Man::CAP;
+  extern __shared__ __align__(16) char tile_mem[];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  const int cnt = man.count();
+  const long long row0 = row0_chunk + (long long)blockIdx.x * 128;  // first owned row of this tile
+  const long long k = row0 + tid;
+  const long long end = row0_chunk + rows_chunk;
+  const int rows_here = (int)((end - row0 < 128) ? (end - row0) : 128);
+  T* tile = reinterpret_cast<T*>(tile_mem);
+  if (k < end) {
+    const long long row = pt.row_lo + k;
+    T xs[CAP], gs[CAP], b1[CAP], b2[CAP];
+    static_assert(Man::kStatic, "the pipelined exchange is built for fixed-size points");
+    load_row<T, CAP>((const T*)pt.gsum, k, gs);
+    load_row<T, CAP>((const T*)pt.x[pt.rank], row, xs);
+    if (buf1) load_row<T, CAP>(buf1, k, b1);
+    if (buf2) load_row<T, CAP>(buf2, k, b2);
+    if (!buf1) { GM_UNROLL for (int e = 0; e < CAP; ++e) b1[e] = (T)0; }
+    if (!buf2) { GM_UNROLL for (int e = 0; e < CAP; ++e) b2[e] = (T)0; }
+    optim_update<Man, T>(man, oc, xs, gs, b1, b2);
+    GM_UNROLL for (int e = 0; e < CAP; ++e) tile[tid * CAP + e] = xs[e];
+    if (buf1) store_row<T, CAP>(buf1, k, b1);
+    if (buf2) store_row<T, CAP>(buf2, k, b2);
+  }
+  __syncthreads();
+  const size_t tile_off = (size_t)(pt.row_lo + row0) * cnt * sizeof(T);
+  peer_push<float4>(pt, tile_off, rows_here * cnt * (int)sizeof(T) / 16, reinterpret_cast<const float4*>(tile_mem), tid);
+  if (!last) return;
+  unsigned long long* my_flags = pt.flags[pt.rank];
+  if (blockIdx.x == 0 && tid >= 32 && tid < 32 + pt.n_acc) {
+    double s = 0.0;
+    for (int r = 0; r < pt.world; ++r) s += pt.acc[r][tid - 32];
+    pt.acc_out[tid - 32] = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long prev = atomicAdd(my_flags + 2 * kMaxPeers, 1ull);
+    is_last = (prev == (unsigned long long)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (tid == 0) my_flags[2 * kMaxPeers] = 0;
+    if (tid < pt.world) {
+      flag_store_release(pt.flags[tid] + kMaxPeers + pt.rank, pt.epoch);
+      flag_wait(my_flags + kMaxPeers + tid, pt.epoch, pt.timeout_ns);
+    }
+  }
+}
+
+// side stream + events of the pipelined exchange, one set per device, created on first use
+struct PeerPipe {
+  cudaStream_t side = nullptr;
+  cudaEvent_t pulled[8] = {};
+  cudaEvent_t joined = nullptr;
+};
+PeerPipe& peer_pipe();  // gm_api.cu
+
+template <class Man, typename T>
+static int launch_peer_pipelined(const Man& man, const PointArgs& a) {
+  const PeerTable& pt = *a.peer;
+  const int cnt = man.count();
+  const size_t row_bytes = (size_t)cnt * sizeof(T);
+  PeerPipe& pp = peer_pipe();
+  if (!pp.side) return GM_EINVAL;
+  // chunks of whole 128-row tiles, at most 4 (and at least ~8k rows each: below that the launches cost more than the
+  // overlap buys)
+  const long long tiles = (a.N + 127) / 128;
+  int K = (int)(tiles / 64);
+  const int kmax = pt.chunks >= 1 && pt.chunks <= 8 ? pt.chunks : 4;
+  K = K < 1 ? 1 : (K > kmax ? kmax : K);
+  const long long tiles_per = (tiles + K - 1) / K;
+  int launched = 0;
+  for (int c = 0; c < K; ++c) {
+    const long long r0 = (long long)c * tiles_per * 128;
+    if (r0 >= a.N) { K = c; break; }
+    const long long rows = (a.N - r0 < tiles_per * 128) ? (a.N - r0) : tiles_per * 128;
+    const size_t off = (size_t)(pt.row_lo + r0) * row_bytes;
+    const long long nvec = (long long)(rows * row_bytes / 16);
+    // two blocks per SM keep megabytes of 16-byte peer loads in flight and leave the rest of every SM to the
+    // update+push kernel of the previous chunk, which runs beside this one
+    long long pb = (nvec + 256 * 2 - 1) / (256 * 2);
+    if (pb > 148 * 2) pb = 148 * 2;
+    peer_pull_kernel<T><<<(unsigned)pb, 256, 0, a.stream>>>(pt, off, (size_t)r0 * row_bytes, nvec, c == 0 ? 1 : 0);
+    note_launch();
+    cudaEventRecord(pp.pulled[c], a.stream);
+    ++launched;
+  }
+  for (int c = 0; c < K; ++c) {
+    const long long r0 = (long long)c * tiles_per * 128;
+    const long long rows = (a.N - r0 < tiles_per * 128) ? (a.N - r0) : tiles_per * 128;
+    cudaStreamWaitEvent(pp.side, pp.pulled[c], 0);
+    const long long ub = (rows + 127) / 128;
+    peer_update_push_kernel<Man, T><<<(unsigned)ub, 128, 128 * row_bytes, pp.side>>>(
+        man, a.oc, pt, (T*)a.buf1, (T*)a.buf2, r0, rows, c == K - 1 ? 1 : 0);
+    note_launch();
+  }
+  cudaEventRecord(pp.joined, pp.side);
+  cudaStreamWaitEvent(a.stream, pp.joined, 0);
+  (void)launched;
+  return check_launch();
 }
 
 template <class Man, typename T>
@@ -343,6 +506,9 @@ static int launch_point(const Man& man, const PointArgs& a) {
   if (a.op < 0 && a.peer) {
     const size_t tile_bytes = (size_t)threads * man.count() * sizeof(T);
     const int use_tile = tile_bytes <= (size_t)kPeerTileBytes;
+    if constexpr (Man::kStatic) {
+      if (a.peer->gsum && use_tile && (man.count() * sizeof(T)) % 16 == 0) return launch_peer_pipelined<Man, T>(man, a);
+    }
     peer_optim_kernel<Man, T><<<(unsigned)blocks, threads, use_tile ? tile_bytes : 0, a.stream>>>(
         man, a.oc, *a.peer, (T*)a.buf1, (T*)a.buf2, a.N, use_tile);
   } else if (a.op < 0)

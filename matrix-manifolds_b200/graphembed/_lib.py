@@ -62,7 +62,7 @@ class Optim(ctypes.Structure):
 
 
 GM_MAX_PEERS, GM_PEER_HANDLE_BYTES = 8, 64
-GM_PEER_FLAG_BYTES = (2 * GM_MAX_PEERS + 1) * 8
+GM_PEER_FLAG_BYTES = (2 * GM_MAX_PEERS + 2) * 8
 
 
 class Peers(ctypes.Structure):
@@ -70,7 +70,7 @@ class Peers(ctypes.Structure):
                 ('epoch', ctypes.c_uint64), ('x', ctypes.c_void_p * GM_MAX_PEERS),
                 ('grad', ctypes.c_void_p * GM_MAX_PEERS), ('flags', ctypes.c_void_p * GM_MAX_PEERS),
                 ('acc', ctypes.c_void_p * GM_MAX_PEERS), ('acc_out', ctypes.c_void_p), ('n_acc', ctypes.c_int32),
-                ('reserved', ctypes.c_int32)]
+                ('reserved', ctypes.c_int32), ('gsum', ctypes.c_void_p)]
 
 
 _vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
@@ -114,6 +114,7 @@ _PROTOTYPES = {
     'gm_levels_to_dense_targets': (ctypes.c_int, [_i32, _vp, _i32, _dbl, _i32, _vp, _vp]),
     'gm_gather_levels': (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     'gm_expand_groups': (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _vp]),
+    'gm_unpack_pairs3': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     'gm_rank_metrics': (ctypes.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),
 }

@@ -433,6 +433,16 @@ def dist2_indexed(spec, x, pairs, c=None, wmin=None):
     return _Dist2Indexed.apply(x, spec, pairs, c, wmin)
 
 
+def unpack_pairs3(src3, P, out):
+    """3-byte pair words (engine.pack_hops3) -> out[k] = (hops << 24) | j, the GM_TGT_HOPS_PACKED form (all CUDA)."""
+    L.require_cuda(src3, out)
+    if src3.dtype != torch.uint8 or out.dtype != torch.int32 or src3.numel() < 3 * P or out.numel() < P:
+        raise ValueError('unpack_pairs3: uint8 source of 3*P bytes, int32 output of P words')
+    rc = L.lib().gm_unpack_pairs3(L.ptr(src3), P, L.ptr(out), L.stream_ptr(out.device))
+    L.check(rc, 'gm_unpack_pairs3')
+    return out
+
+
 def expand_groups(group_rows, offsets, out):
     """out[k] = group_rows[g] for offsets[g] <= k < offsets[g+1] (int32 rows, int64 offsets, int32 out; all CUDA)."""
     L.require_cuda(group_rows, offsets, out)

@@ -161,6 +161,16 @@ class PeerArena:
         self.table.world, self.table.rank, self.table.row_lo = self.world, self.rank, self.lo
         self.table.n_acc = self.n_acc
         self.table.acc_out = self.base + self.off_out
+        # local workspace of the pipelined exchange (sum of every rank's gradient rows this rank owns); GM_PEER_PIPELINE=0
+        # keeps the single fused kernel
+        # Measured on B200 (bench.py, 2 M points): 2 GPUs 1.361 ms per step pipelined vs 1.452 fused; 4 GPUs 1.44-1.52
+        # (2-8 chunks) vs 1.420 fused; 8 GPUs 1.62 vs 1.43 -- with more peers the fused kernel's thousands of blocks
+        # already overlap pulls and pushes, and the extra launches cost more than they buy.  Default: pipelined for 2 ranks.
+        self.gsum = None
+        mode = os.environ.get('GM_PEER_PIPELINE', 'auto')
+        if mode == '1' or (mode == 'auto' and self.world == 2):
+            self.gsum = torch.empty_like(self.x[self.lo:self.hi])
+            self.table.gsum = self.gsum.data_ptr()
         for r, b in enumerate(self.peer_base):
             self.table.x[r] = b + self.off_x
             self.table.grad[r] = b + self.off_g

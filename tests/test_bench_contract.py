@@ -47,3 +47,16 @@ def test_reference_arm_secondary_workloads():
 def test_b200_arm_refuses_to_run_without_cuda():
     out = _run('--steps', '1', '--warmup', '1')
     assert out.returncode != 0 and 'no CPU fallback' in (out.stderr + out.stdout)
+
+
+def test_shipped_graphs_and_config_table_are_consistent():
+    """bench.py --workload 1..4 runs on the shipped edge lists (tests/golden/graphs/*.npz): they are present, have the
+    sizes the config table names, and every GPU config has a CPU twin for the baseline beside it."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert set(bench.GPU_CONFIGS) == set(bench.CPU_CONFIGS) == {'1', '2a', '2b', '3a', '3b', '4'}
+    for tag, (gname, factors, dtype, opt, batch, E, flops) in bench.GPU_CONFIGS.items():
+        n, edges, src = bench.load_graph(gname)
+        assert n == bench.GRAPH_SIZES[gname] and src == f'data/{gname}.edges.gz'
+        assert edges.ndim == 2 and edges.shape[1] == 2 and edges.max() == n - 1
+        assert bench.CPU_CONFIGS[tag][3] == n and len(E) == len(factors)

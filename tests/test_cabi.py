@@ -69,7 +69,7 @@ def test_peer_update_argument_validation_without_gpu():
     assert call() == -1  # epochs start at 1
     t.epoch = 1
     assert call(0) == -1  # every rank must own rows
-    assert ctypes.sizeof(L.Peers) == 8 + 8 + 8 + 4 * 8 * L.GM_MAX_PEERS + 8 + 8
+    assert ctypes.sizeof(L.Peers) == 8 + 8 + 8 + 4 * 8 * L.GM_MAX_PEERS + 8 + 8 + 8  # ... + gsum (pipelined exchange)
     assert lib.gm_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) == -1
     assert lib.gm_peer_export(None, None) == -3
 

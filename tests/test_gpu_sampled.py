@@ -214,3 +214,48 @@ def test_product_pair_trainer_vs_oracle(dtype):
         assert rel_err(emb.xs[f].detach(), xs[f]) < t
         assert abs(float(emb.scales[f].detach()) - float(scales[f])) <= t * abs(float(scales[f]))
     assert abs(float(emb.scales[0].detach()) - 0.5) > 1e-3  # the scales moved, and the kernels followed them
+
+
+def test_three_byte_pair_upload_format():
+    """pack_hops3 (j | (hops - 1) << 21 in 3 bytes) expands on the device to exactly pack_hops' 4-byte words, for any
+    length (the 4-pair vector path and the ragged tail), and step_host_grouped on it is the same step."""
+    from graphembed import _ops
+    from graphembed.engine import PairTrainer, pack_hops, pack_hops3
+    from graphembed.manifolds import SymmetricPositiveDefinite
+    from graphembed.modules import ManifoldEmbedding
+    from graphembed.objectives import QuotientLoss
+    from graphembed.optim import RiemannianAdam
+    g = torch.Generator().manual_seed(0)
+    for P in (1, 3, 4, 5, 1023, 40000):
+        J = torch.randint(1 << 21, (P,), generator=g, dtype=torch.int32)
+        H = torch.randint(1, 9, (P,), generator=g, dtype=torch.uint8)
+        b3 = pack_hops3(J, H)
+        assert b3.dtype == torch.uint8 and b3.numel() == (3 * P + 3) // 4 * 4
+        out = torch.empty(P, dtype=torch.int32, device=DEV)
+        _ops.unpack_pairs3(b3.to(DEV), P, out)
+        assert torch.equal(out.cpu(), pack_hops(J, H))
+    with pytest.raises(ValueError):
+        pack_hops3(torch.tensor([1 << 21], dtype=torch.int32), torch.tensor([1], dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        pack_hops3(torch.tensor([5], dtype=torch.int32), torch.tensor([9], dtype=torch.uint8))
+    n, G, per = 300, 37, 129
+    res = []
+    for three in (False, True):
+        torch.manual_seed(3)
+        emb = ManifoldEmbedding(n, [SymmetricPositiveDefinite(4)], device=DEV, dtype=torch.float32)
+        opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
+        tr = PairTrainer(emb, opt, QuotientLoss(), max_hops_sq=64.0)
+        gg = torch.Generator().manual_seed(5)
+        losses = []
+        for step in range(3):
+            src = torch.randperm(n, generator=gg)[:G].int()
+            offsets = torch.arange(G + 1, dtype=torch.int64) * per
+            I = src.repeat_interleave(per)
+            J = torch.randint(n - 1, (G * per,), generator=gg, dtype=torch.int32)
+            J = torch.where(J >= I, J + 1, J).contiguous()
+            H = torch.randint(1, 9, (G * per,), generator=gg, dtype=torch.uint8)
+            words = (pack_hops3 if three else pack_hops)(J, H)
+            losses.append(tr.step_host_grouped(src.pin_memory(), offsets.pin_memory(), words.pin_memory(), None, epoch=1))
+        res.append((losses, emb.xs[0].detach().cpu().clone()))
+    assert max(abs(a - b) / abs(b) for a, b in zip(res[0][0], res[1][0])) < 1e-6
+    assert rel_err(res[0][1], res[1][1]) < 1e-5
