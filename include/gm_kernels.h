@@ -181,6 +181,19 @@ int gm_product_loss(int32_t dtype, int32_t F, const void* const* d2_ptrs_host, c
                     const gm_pairs_t* pairs, const gm_targets_t* targets, const gm_loss_t* loss, int64_t P, double* acc,
                     void* out_g, gm_stream_t stream);
 
+/* Fused pair kernel of a PRODUCT manifold (modules.py:84-105 with F factors + objectives.py:16-45 + loss.backward()):
+ * ONE launch evaluates every factor's d2 of a pair, m_k = sum_f sp[f] * d2_f[k] (left to right, as Python's sum() over the
+ * factor list), the loss of m_k against the pair's target, and adds every factor's gradient into grad[f]:
+ *   acc[0] += sum_k l(g_k, m_k);   acc[1+f] += sum_k l'_k * d2_f[k];   grad[f][i_k], grad[f][j_k] += l'_k sp[f] d(d2_f)/d(x, y).
+ * Host arrays of length F: mans, x, grad, sp.  Pairs / targets as gm_pairs_loss_fused (LIST / TRIU / SAMPLED; every
+ * target mode).  Supported products: at most one SPD factor (either divergence) and up to three of Lorentz / Sphere /
+ * Euclidean, 2 <= F <= 4, one dtype; anything else returns GM_EUNSUPPORTED and the caller keeps the unfused sequence
+ * gm_pairs_dist2 x F -> gm_product_loss -> gm_pairs_grad x F.  gm_train_epoch_product uses it when it can
+ * (GM_PRODUCT_FUSED=0 in the environment forces the unfused sequence). */
+int gm_pairs_product_fused(int32_t F, const gm_manifold_t* mans, void* const* x, const gm_pairs_t* pairs,
+                           const gm_targets_t* targets, const gm_loss_t* loss, const double* sp, double* acc,
+                           void* const* grad, gm_stream_t stream);
+
 /* Validation metrics over a pair set, streamed (TrainingEngine._validate, train.py:230-265; metrics.average_distortion
  * and metrics.pearsonr, metrics.py:13-17,46-56) without materialising the N(N-1)/2 distance vectors:
  *   squared_inputs != 0:  m_k = sqrt(sum_f sp[f]*d2[f][k]),  g_k = sqrt(target_k)   (train.py:231-232)
@@ -247,7 +260,8 @@ int gm_train_epoch(const gm_manifold_t* man, const gm_optim_t* opt, void* x, voi
                    int64_t max_steps, int64_t* n_steps, gm_stream_t stream);
 
 /* gm_train_epoch for a PRODUCT of F manifolds (modules.py:84-88: m = sum_f sp[f] * d2_f): per slice
- * zero(grad_f) x F -> gm_pairs_dist2 x F -> gm_product_loss -> gm_pairs_grad x F -> gm_optim_step x F, all enqueued from
+ * zero(grad_f) x F -> gm_pairs_dist2 x F -> gm_product_loss -> gm_pairs_grad x F -> gm_optim_step x F (or, for the
+ * products gm_pairs_product_fused takes: zero x F -> gm_pairs_product_fused -> gm_optim_step x F), all enqueued from
  * this one call.  Host arrays of length F: mans, opts (opts[f].step / first_step as in gm_train_epoch), x, grad, buf1,
  * buf2, sp, d2_ws (device workspaces of >= batch_nodes*(batch_nodes-1)/2 elements of the dtype each); g_ws is one more
  * such workspace.  acc: [max_steps][1 + F] doubles, zeroed by the caller (slice k: loss, then sum l' d2_f per factor).

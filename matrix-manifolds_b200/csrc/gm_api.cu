@@ -368,6 +368,70 @@ int gm_train_epoch(const gm_manifold_t* man, const gm_optim_t* opt, void* x, voi
   return GM_OK;
 }
 
+// Can the fused product kernel (gm_product.cuh) take this factor list?  At most one SPD factor, the rest Lorentz /
+// Sphere / Euclidean, one dtype.
+static bool product_fusable(int F, const gm_manifold_t* mans) {
+  if (F < 2 || F > 1 + kMaxVecExtra) return false;
+  int n_spd = 0, n_vec = 0;
+  for (int f = 0; f < F; ++f) {
+    const int k = mans[f].kind;
+    if (mans[f].dtype != mans[0].dtype) return false;
+    if (k == GM_SPD_AI || k == GM_SPD_STEIN) ++n_spd;
+    else if (k == GM_LORENTZ || k == GM_SPHERE || k == GM_EUCLIDEAN) ++n_vec;
+    else return false;
+  }
+  return n_spd <= 1 && n_vec <= kMaxVecExtra;
+}
+
+int gm_pairs_product_fused(int32_t F, const gm_manifold_t* mans, void* const* x, const gm_pairs_t* pairs,
+                           const gm_targets_t* targets, const gm_loss_t* loss, const double* sp, double* acc,
+                           void* const* grad, gm_stream_t stream) {
+  if (!mans || !x || !grad || !sp || !targets || !loss) return GM_ENULL;
+  if (F < 1 || F > 8) return GM_EINVAL;
+  for (int f = 0; f < F; ++f) {
+    int rc = manifold_ok(&mans[f]);
+    if (rc) return rc;
+  }
+  if (!product_fusable(F, mans)) return GM_EUNSUPPORTED;
+  int rc = validate_pairs(pairs);
+  if (rc) return rc;
+  if (pairs->mode == GM_PAIRS_ELEMENTWISE) return GM_EINVAL;
+  if (targets->mode < GM_TGT_VECTOR || targets->mode > GM_TGT_HOPS_PACKED) return GM_EINVAL;
+  const bool packed = targets->mode == GM_TGT_HOPS_PACKED;
+  if (packed && ((pairs->mode != GM_PAIRS_LIST && pairs->mode != GM_PAIRS_SAMPLED) || pairs->idx64)) return GM_EINVAL;
+  if (pairs->mode == GM_PAIRS_SAMPLED && !packed) return GM_EINVAL;
+  if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
+  if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
+  if (pairs->P == 0) return GM_OK;
+  if (!acc || (!packed && !targets->data)) return GM_ENULL;
+  ProductExtra px{};
+  px.F = F; px.lead_slot = -1; px.nvec = 0;
+  for (int f = 0; f < F; ++f) {
+    if (!x[f] || !grad[f]) return GM_ENULL;
+    if (mans[f].kind == GM_SPD_AI || mans[f].kind == GM_SPD_STEIN) { px.lead_slot = f; continue; }
+    VecExtra& v = px.v[px.nvec++];
+    v.kind = mans[f].kind; v.n = mans[f].n; v.slot = f; v.x = x[f]; v.g = grad[f]; v.sp = sp[f];
+  }
+  PairArgs a{};
+  if (px.lead_slot >= 0) {
+    fill_manifold(a, &mans[px.lead_slot]);
+    a.xa = a.xb = x[px.lead_slot];
+    a.ga = a.gb = grad[px.lead_slot];
+    a.scale_sp = sp[px.lead_slot];
+  } else {
+    fill_manifold(a, &mans[0]);  // dtype; the factors themselves travel in px
+  }
+  a.kmode = K_FUSED;
+  a.ps = make_pairs(pairs);
+  a.tg = make_targets(targets);
+  if (packed) { a.tg.data = pairs->idx_j; a.ps.jmask = 0x00ffffffu; }
+  a.lc = make_loss(loss);
+  a.acc = acc;
+  a.stream = (cudaStream_t)stream;
+  a.px = &px;
+  return pair_dispatch(a);
+}
+
 int gm_train_epoch_product(int32_t F, const gm_manifold_t* mans, const gm_optim_t* opts, void* const* x,
                            void* const* grad, void* const* buf1, void* const* buf2, int64_t N, const void* perm,
                            int32_t perm_is_int64, int64_t n_perm, int64_t batch_nodes, int64_t drop_last_n,
@@ -392,6 +456,8 @@ int gm_train_epoch_product(int32_t F, const gm_manifold_t* mans, const gm_optim_
   cudaStream_t st = (cudaStream_t)stream;
   gm_optim_t o[8];
   for (int f = 0; f < F; ++f) o[f] = opts[f];
+  const char* fuse_env = getenv("GM_PRODUCT_FUSED");  // "0": keep the unfused 2 F + 1 pair launches per step (A/B, tests)
+  const bool fused = !(fuse_env && fuse_env[0] == '0') && product_fusable(F, mans);
   int64_t k = 0;
   for (int64_t i = 0; i < n_perm; i += batch_nodes, ++k) {
     const int64_t b = (n_perm - i < batch_nodes) ? (n_perm - i) : batch_nodes;
@@ -403,15 +469,19 @@ int gm_train_epoch_product(int32_t F, const gm_manifold_t* mans, const gm_optim_
     for (int f = 0; f < F; ++f) {
       cudaError_t e = cudaMemsetAsync(grad[f], 0, (size_t)N * point_elems(&mans[f]) * s_bytes, st);
       if (e != cudaSuccess) return (int)e;
+      if (fused) continue;
       int rc = gm_pairs_dist2(&mans[f], x[f], x[f], &pr, d2_ws[f], stream);
       if (rc) return rc;
     }
-    int rc = gm_product_loss(mans[0].dtype, F, (const void* const*)d2_ws, sp, &pr, targets, loss, pr.P,
-                             acc + (1 + F) * k, g_ws, stream);
+    int rc = fused ? gm_pairs_product_fused(F, mans, x, &pr, targets, loss, sp, acc + (1 + F) * k, grad, stream)
+                   : gm_product_loss(mans[0].dtype, F, (const void* const*)d2_ws, sp, &pr, targets, loss, pr.P,
+                                     acc + (1 + F) * k, g_ws, stream);
     if (rc) return rc;
     for (int f = 0; f < F; ++f) {
-      rc = gm_pairs_grad(&mans[f], x[f], x[f], &pr, g_ws, sp[f], grad[f], grad[f], stream);
-      if (rc) return rc;
+      if (!fused) {
+        rc = gm_pairs_grad(&mans[f], x[f], x[f], &pr, g_ws, sp[f], grad[f], grad[f], stream);
+        if (rc) return rc;
+      }
       rc = gm_optim_step(&mans[f], &o[f], x[f], grad[f], buf1[f], buf2[f], N, stream);
       if (rc) return rc;
       o[f].step += 1;

@@ -69,6 +69,19 @@ struct FactorPtrs {
   double sp[8];
 };
 
+// ---- fused product-manifold launch: the vector factors evaluated next to the lead factor (gm_product.cuh) ----
+constexpr int kMaxVecExtra = 3;
+struct VecExtra {
+  int kind, n, slot;  // slot: position of the factor in the product's factor list
+  const void* x;
+  void* g;
+  double sp;          // softplus(scale) of the factor
+};
+struct ProductExtra {
+  int F, lead_slot, nvec;  // lead_slot: slot of the SPD factor, -1 when the product has none
+  VecExtra v[kMaxVecExtra];
+};
+
 // ---- one pair-kernel launch request (filled by gm_api.cu) --------------------
 enum { K_FWD = 0, K_BWD = 1, K_FUSED = 2 };
 struct PairArgs {
@@ -91,6 +104,7 @@ struct PairArgs {
   double scale_sp;
   double* acc;
   cudaStream_t stream;
+  const ProductExtra* px;  // K_FUSED only: non-null = product-manifold launch (acc has 1 + F slots)
 };
 
 // ---- pair enumeration --------------------------------------------------------

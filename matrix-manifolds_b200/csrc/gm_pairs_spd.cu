@@ -7,7 +7,7 @@
 // their autograd backward (manifolds/spd.py:171-194,246-295), fused with the
 // gather x[m[0]], x[m[1]] (base.py:62-63), the loss (objectives.py:16-45) and
 // the index_put_ scatter-add of the gradients.
-#include "gm_launch.cuh"
+#include "gm_product.cuh"
 
 #ifndef GM_N
 #error "compile with -DGM_N=<matrix size>"
@@ -97,14 +97,16 @@ __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
 
-template <typename T, int E>
+template <typename T, int E, int STAGES = 2>
 struct RowStage {
   static constexpr int ROWB = E * (int)sizeof(T);
   static constexpr int CPB = (ROWB % 16 == 0) ? 16 : ((ROWB % 8 == 0) ? 8 : 4);
   static constexpr int NCH = ROWB / CPB;
   static constexpr int THREADS = 128;
-  static constexpr int BYTES = 2 /*stages*/ * 2 /*rows*/ * ROWB * THREADS;
+  static constexpr int BYTES = STAGES * 2 /*rows*/ * ROWB * THREADS;
   // slot of chunk c of row r (0: a side, 1: b side) of stage s for thread t
   __device__ __forceinline__ static char* slot(char* base, int s, int r, int c, int t) {
     return base + ((((s * 2 + r) * NCH + c) * THREADS + t) * CPB);
@@ -203,7 +205,7 @@ template <> struct RawScalar<double> {
   __device__ __forceinline__ static double unpack(unsigned long long r) { return __longlong_as_double((long long)r); }
 };
 
-template <class Op, typename T, int KMODE, int MINB>
+template <class Op, typename T, int KMODE, int MINB, int DEPTH>
 __global__ void __launch_bounds__(128, MINB)
 spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __restrict__ xb,
                        const T* __restrict__ gout, T coef, T* __restrict__ ga, T* __restrict__ gb,
@@ -212,7 +214,8 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   constexpr int E = Op::E;
   constexpr int N = GM_N;
   constexpr int EU = N * (N + 1) / 2;  // gradients are symmetric: the run-length accumulator keeps the upper triangle
-  using Stage = RowStage<T, E>;
+  constexpr int D = DEPTH;  // a pair's rows are in flight for D iterations of the loop (D + 1 staging slots per thread)
+  using Stage = RowStage<T, E, D + 1>;
   using Raw = RawScalar<T>;
   using raw_t = typename Raw::type;
   extern __shared__ __align__(16) char stage_mem[];
@@ -235,13 +238,17 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   // ---- pipeline registers -------------------------------------------------------------------------------------
   using row_t = typename RowId<E * (int)sizeof(T)>::type;
   const row_t kNoRow = (row_t)-1;
-  long long kc = k0 + lane;          // pair computed in this iteration (rows staged in `stage`)
-  PairCursor ahead;                  // TRIU position of the furthest pair whose indices have been loaded
-  row_t ra0 = kNoRow, rb0 = kNoRow;  // rows of pair kc
-  row_t ra1 = kNoRow, rb1 = kNoRow;  // rows of pair kc + 32 (indices loaded, rows not yet issued)
-  unsigned hop1 = 0;                 // SAMPLED: hop count of pair kc + 32 (load in flight since the previous iteration)
+  long long kc = k0 + lane;  // pair computed in this iteration (rows staged in `stage`)
+  PairCursor ahead;          // TRIU position of the furthest pair whose indices have been loaded
+  // queue of pairs kc + 32 q: q = 0 is computed now, q = 1..D-1 have their rows in flight, q = D has its indices (rows
+  // are issued this iteration), q = D + 1 is the pair whose indices are being loaded
+  row_t ra[D + 2], rb[D + 2];
+  raw_t tgq[D + 1];    // target (K_FUSED) or upstream gradient (K_BWD) of the pair, raw
+  bool v[D + 2];
+  unsigned hopn = 0;   // SAMPLED: hop count of pair q = D (load in flight since the previous iteration)
+  GM_UNROLL for (int q = 0; q < D + 2; ++q) { ra[q] = kNoRow; rb[q] = kNoRow; v[q] = false; }
+  GM_UNROLL for (int q = 0; q < D + 1; ++q) tgq[q] = 0;
   const bool sampled = ps.mode == GM_PAIRS_SAMPLED;
-  raw_t tg0 = 0;                     // target (K_FUSED) or upstream gradient (K_BWD) of pair kc, raw
   int stage = 0;
 
   auto fetch_scalar = [&](long long k, row_t ra, row_t rb) -> raw_t {
@@ -271,19 +278,21 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   };
 
   ahead.init(ps, kc);
-  bool v0 = kc < kend;
-  if (v0) {
-    unsigned hop0 = 0;
-    load_rows(kc, ra0, rb0, hop0);
-    tg0 = (sampled && hopsP) ? (raw_t)hop0 : fetch_scalar(kc, ra0, rb0);
-    if (rawj) rb0 &= (row_t)0x00ffffffu;
-    Stage::issue(stage_mem, 0, 0, tid, xa + (size_t)ra0 * E);
-    Stage::issue(stage_mem, 0, 1, tid, xb + (size_t)rb0 * E);
+  GM_UNROLL for (int q = 0; q < D; ++q) {
+    v[q] = kc + 32 * q < kend;
+    if (v[q]) {
+      unsigned hop = 0;
+      load_rows(kc + 32 * q, ra[q], rb[q], hop);
+      tgq[q] = (sampled && hopsP) ? (raw_t)hop : fetch_scalar(kc + 32 * q, ra[q], rb[q]);
+      if (rawj) rb[q] &= (row_t)0x00ffffffu;
+      Stage::issue(stage_mem, q, 0, tid, xa + (size_t)ra[q] * E);
+      Stage::issue(stage_mem, q, 1, tid, xb + (size_t)rb[q] * E);
+    }
+    cp_async_commit();
+    ahead.advance(ps);
   }
-  cp_async_commit();
-  ahead.advance(ps);
-  bool v1 = kc + 32 < kend;
-  if (v1) load_rows(kc + 32, ra1, rb1, hop1);
+  v[D] = kc + 32 * D < kend;
+  if (v[D]) load_rows(kc + 32 * D, ra[D], rb[D], hopn);
 
   // ---- per-lane running state -------------------------------------------------------------------------------------
   double loss_v = 0.0, gd2_v = 0.0;
@@ -310,28 +319,33 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     }
   };
 
-  while (__any_sync(full, v0)) {
-    // (1) rows of the current pair have landed in my slots
-    cp_async_wait_all();
+  while (__any_sync(full, v[0])) {
+    // (1) rows of the current pair have landed in my slots (the D - 1 younger groups may still be in flight)
+    cp_async_wait_group<D - 1>();
+    const bool v0 = v[0];
+    const row_t ra0 = ra[0], rb0 = rb[0];
+    const raw_t tg0 = tgq[0];
     T x[E], y[E];
     if (v0) {
       Stage::read(stage_mem, stage, 1, tid, y);
       if (!Op::kCanPrep || ra0 != prep_row) Stage::read(stage_mem, stage, 0, tid, x);
     }
-    // (2) stage the next pair: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
-    raw_t tgn = 0;
-    if (v1) {
-      tgn = (sampled && hopsP) ? (raw_t)hop1 : fetch_scalar(kc + 32, ra1, rb1);
-      if (rawj) rb1 &= (row_t)0x00ffffffu;
-      Stage::issue(stage_mem, stage ^ 1, 0, tid, xa + (size_t)ra1 * E);
-      Stage::issue(stage_mem, stage ^ 1, 1, tid, xb + (size_t)rb1 * E);
+    // (2) issue the rows of pair q = D: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
+    tgq[D] = 0;
+    if (v[D]) {
+      tgq[D] = (sampled && hopsP) ? (raw_t)hopn : fetch_scalar(kc + 32 * D, ra[D], rb[D]);
+      if (rawj) rb[D] &= (row_t)0x00ffffffu;
+      int sn = stage + D;
+      if (sn > D) sn -= D + 1;
+      Stage::issue(stage_mem, sn, 0, tid, xa + (size_t)ra[D] * E);
+      Stage::issue(stage_mem, sn, 1, tid, xb + (size_t)rb[D] * E);
     }
     cp_async_commit();
     ahead.advance(ps);
-    bool v2 = kc + 64 < kend;
-    row_t ra2 = kNoRow, rb2 = kNoRow;
-    unsigned hop2 = 0;
-    if (v2) load_rows(kc + 64, ra2, rb2, hop2);
+    v[D + 1] = kc + 32 * (D + 1) < kend;
+    ra[D + 1] = kNoRow; rb[D + 1] = kNoRow;
+    unsigned hop_next = 0;
+    if (v[D + 1]) load_rows(kc + 32 * (D + 1), ra[D + 1], rb[D + 1], hop_next);
 
     // (4) the math
     T gx[E], gy[E];
@@ -382,9 +396,10 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     }
     // (6) rotate the pipeline
     kc += 32;
-    ra0 = ra1; rb0 = rb1; tg0 = tgn; v0 = v1;
-    ra1 = ra2; rb1 = rb2; hop1 = hop2; v1 = v2;
-    stage ^= 1;
+    GM_UNROLL for (int q = 0; q < D + 1; ++q) { ra[q] = ra[q + 1]; rb[q] = rb[q + 1]; v[q] = v[q + 1]; }
+    GM_UNROLL for (int q = 0; q < D; ++q) tgq[q] = tgq[q + 1];
+    hopn = hop_next;
+    stage = (stage == D) ? 0 : stage + 1;
   }
   flush();
   if constexpr (KMODE == K_FUSED) {
@@ -396,18 +411,24 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
 template <class Op, typename T>
 static int launch_op(const Op& op, const PairArgs& a) {
   if (a.ps.P <= 0) return 0;
+  if (a.px) return launch_product<SpdLead<Op>, T>(SpdLead<Op>{op}, a);
   const int threads = 128;
   long long blocks = (a.ps.P + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return GM_EINVAL;
   dim3 grid((unsigned)blocks), block(threads);
   const T* xa = (const T*)a.xa;
   const T* xb = (const T*)a.xb;
-  using Stage = RowStage<T, Op::E>;
-  if (a.kmode != K_FWD && a.ps.mode != GM_PAIRS_ELEMENTWISE && Stage::BYTES <= 64 * 1024) {
 #ifndef GM_MINB_F32
 #define GM_MINB_F32 4
 #endif
-    constexpr int MINB = sizeof(T) == 4 ? GM_MINB_F32 : 2;
+#ifndef GM_PF_DEPTH
+#define GM_PF_DEPTH 2
+#endif
+  constexpr int MINB = sizeof(T) == 4 ? GM_MINB_F32 : 2;
+  // rows stay in flight for two iterations when MINB CTAs of three staging slots still fit one SM's shared memory
+  constexpr int DEPTH = (RowStage<T, Op::E, GM_PF_DEPTH + 1>::BYTES + 3 * 1024) * MINB <= 224 * 1024 ? GM_PF_DEPTH : 1;
+  using Stage = RowStage<T, Op::E, DEPTH + 1>;
+  if (a.kmode != K_FWD && a.ps.mode != GM_PAIRS_ELEMENTWISE && RowStage<T, Op::E, 2>::BYTES <= 64 * 1024) {
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -426,9 +447,9 @@ static int launch_op(const Op& op, const PairArgs& a) {
       return check_launch();
     };
     if (a.kmode == K_BWD)
-      return launch_stream(spd_pair_stream_kernel<Op, T, K_BWD, MINB>, (const T*)a.gout, (T)a.coef, nullptr, (T)0,
+      return launch_stream(spd_pair_stream_kernel<Op, T, K_BWD, MINB, DEPTH>, (const T*)a.gout, (T)a.coef, nullptr, (T)0,
                            nullptr);
-    return launch_stream(spd_pair_stream_kernel<Op, T, K_FUSED, MINB>, nullptr, (T)0, (T*)a.out_d2, (T)a.scale_sp,
+    return launch_stream(spd_pair_stream_kernel<Op, T, K_FUSED, MINB, DEPTH>, nullptr, (T)0, (T*)a.out_d2, (T)a.scale_sp,
                          a.acc);
   }
   switch (a.kmode) {

@@ -7,20 +7,9 @@
 // base.py:56-57, Universal.dist (manifolds/universal.py:76-81 + impl/math.py:567-572),
 // Grassmann.dist (manifolds/grassmann.py:91-96), each fused with the pair gather
 // (base.py:59-63), the loss and the gradient scatter-add.
-#include "gm_launch.cuh"
+#include "gm_product.cuh"
 
 namespace gm {
-
-// accumulate one scalar of row `row` (all 32 lanes call; uniform => one atomic)
-template <typename T>
-__device__ __forceinline__ void warp_accumulate_elem(T* p, T v, bool uniform, bool active) {
-  if (uniform) {
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) atomicAdd(p, v);
-  } else if (active) {
-    atomicAdd(p, v);
-  }
-}
 
 template <typename T, int KIND, int KMODE>
 __global__ void __launch_bounds__(128)
@@ -68,46 +57,7 @@ vec_pair_kernel(VecMan<T, KIND> op, int n, PairSpec ps, const T* __restrict__ xa
         }
       }
     } else {
-      const unsigned full = 0xffffffffu;
-      long long ra0 = __shfl_sync(full, ra, 0);
-      bool uni_a = __all_sync(full, ra == ra0) && ra0 >= 0;
-      bool vectorised = false;
-      if constexpr (sizeof(T) == 4) {
-        // 16-byte rows (n % 4 == 0, tables 16-byte aligned): one 128-bit reduction per four elements
-        // (REDG.E.ADD.F32x4, as the SPD kernels issue) instead of four scalar ones
-        if ((n & 3) == 0 && (((size_t)ga | (size_t)gb) & 15) == 0) {
-          vectorised = true;
-          for (int e = 0; e < n; e += 4) {
-            float gx4[4], gy4[4];
-            GM_UNROLL for (int j = 0; j < 4; ++j) {
-              float gxe = 0.f, gye = 0.f;
-              if (active) {
-                op.grad_elem(e + j, px[e + j], py[e + j], c, gxe, gye);
-                gxe *= w; gye *= w;
-              }
-              gx4[j] = gxe; gy4[j] = gye;
-            }
-            if (uni_a) {
-              GM_UNROLL for (int j = 0; j < 4; ++j) gx4[j] = warp_sum(gx4[j]);
-              if ((threadIdx.x & 31) == 0)
-                atomicAdd(reinterpret_cast<float4*>(ga + ra0 * n + e), make_float4(gx4[0], gx4[1], gx4[2], gx4[3]));
-            } else if (active) {
-              atomicAdd(reinterpret_cast<float4*>(ga + ra * n + e), make_float4(gx4[0], gx4[1], gx4[2], gx4[3]));
-            }
-            if (active)
-              atomicAdd(reinterpret_cast<float4*>(gb + rb * n + e), make_float4(gy4[0], gy4[1], gy4[2], gy4[3]));
-          }
-        }
-      }
-      for (int e = 0; e < n && !vectorised; ++e) {
-        T gxe = (T)0, gye = (T)0;
-        if (active) {
-          op.grad_elem(e, px[e], py[e], c, gxe, gye);
-          gxe *= w; gye *= w;
-        }
-        warp_accumulate_elem<T>(ga + (uni_a ? ra0 : ra) * n + e, gxe, uni_a, active);
-        if (active) atomicAdd(gb + rb * n + e, gye);
-      }
+      vec_scatter<T>(op, n, px, py, c, w, ga, gb, ra, rb, active);
     }
   }
   if constexpr (KMODE == K_FUSED) {
@@ -278,6 +228,11 @@ static int vec_launch_typed(const PairArgs& a) {
 }
 
 int vec_launch(const PairArgs& a) {
+  if (a.px) {  // product of vector manifolds only: every factor travels in a.px
+    if (a.dtype == GM_F32) return launch_product<NoLead<float>, float>(NoLead<float>{}, a);
+    if (a.dtype == GM_F64) return launch_product<NoLead<double>, double>(NoLead<double>{}, a);
+    return GM_EINVAL;
+  }
   if (a.dtype == GM_F32) return vec_launch_typed<float>(a);
   if (a.dtype == GM_F64) return vec_launch_typed<double>(a);
   return GM_EINVAL;

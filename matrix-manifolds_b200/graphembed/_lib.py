@@ -83,6 +83,9 @@ _PROTOTYPES = {
                                      _vp]),
     'gm_pairs_loss_fused': (ctypes.c_int, [ctypes.POINTER(Manifold), _vp, ctypes.POINTER(Pairs),
                                            ctypes.POINTER(Targets), ctypes.POINTER(Loss), _dbl, _vp, _vp, _vp, _vp]),
+    'gm_pairs_product_fused': (ctypes.c_int, [_i32, ctypes.POINTER(Manifold), ctypes.POINTER(_vp), ctypes.POINTER(Pairs),
+                                              ctypes.POINTER(Targets), ctypes.POINTER(Loss), ctypes.POINTER(_dbl), _vp,
+                                              ctypes.POINTER(_vp), _vp]),
     'gm_product_loss': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl), ctypes.POINTER(Pairs),
                                        ctypes.POINTER(Targets), ctypes.POINTER(Loss), _i64, _vp, _vp, _vp]),
     'gm_pairs_metrics': (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_dbl), ctypes.POINTER(Pairs),

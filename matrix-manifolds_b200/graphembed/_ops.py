@@ -243,6 +243,41 @@ def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, wa
     return acc, d2
 
 
+FUSABLE_VECTOR_KINDS = (L.GM_LORENTZ, L.GM_SPHERE, L.GM_EUCLIDEAN)
+MAX_FUSED_VECTOR_FACTORS = 3
+
+
+def product_fusable(specs, dtypes):
+    """Does gm_pairs_product_fused take this factor list?  (At most one SPD factor, up to three of Lorentz / Sphere /
+    Euclidean, 2 <= F <= 4, one dtype -- include/gm_kernels.h.)"""
+    kinds = [sp.kind for sp in specs]
+    n_spd = sum(k in (L.GM_SPD_AI, L.GM_SPD_STEIN) for k in kinds)
+    n_vec = sum(k in FUSABLE_VECTOR_KINDS for k in kinds)
+    return (2 <= len(kinds) <= 1 + MAX_FUSED_VECTOR_FACTORS and n_spd + n_vec == len(kinds) and n_spd <= 1
+            and n_vec <= MAX_FUSED_VECTOR_FACTORS and len(set(dtypes)) == 1)
+
+
+@_no_function_modes
+def pairs_product_fused(specs, xs, pairs, targets, loss, sp_list, grads, acc=None):
+    """One kernel for a product manifold: every factor's d2, the loss of m = sum_f sp_f d2_f and every factor's gradient
+    (accumulated into grads[f]).  Returns acc (float64, 1 + F: [sum loss, sum l' d2_f ...], accumulated into)."""
+    F = len(specs)
+    xs = [_prep(x) for x in xs]
+    dtype, device = xs[0].dtype, xs[0].device
+    if acc is None:
+        acc = torch.zeros(1 + F, dtype=torch.float64, device=device)
+    mans = (L.Manifold * F)(*[sp.c_struct(dtype, device) for sp in specs])
+    xp = (ctypes.c_void_p * F)(*[x.data_ptr() for x in xs])
+    gp = (ctypes.c_void_p * F)(*[g.data_ptr() for g in grads])
+    sps = (ctypes.c_double * F)(*[float(s) for s in sp_list])
+    p, t, l = pairs.c_struct(), targets.c_struct(), loss.c_struct()
+    with torch.cuda.device(device):
+        rc = L.lib().gm_pairs_product_fused(F, mans, xp, ctypes.byref(p), ctypes.byref(t), ctypes.byref(l), sps,
+                                            L.ptr(acc), gp, L.stream_ptr(device))
+    L.check(rc, 'gm_pairs_product_fused')
+    return acc
+
+
 @_no_function_modes
 def product_loss(d2_list, sp_list, targets, loss, want_g=True, pairs=None):
     """Loss over the product distance m = sum_f sp_f * d2_f.  Returns (acc[1+F] float64, dL/dm per pair).  DENSE

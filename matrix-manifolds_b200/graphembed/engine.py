@@ -340,6 +340,11 @@ class ProductPairTrainer:
     """(I, J, hops) pair batches through a PRODUCT-manifold embedding -- BASELINE config 3 ("product SPD 3x3 x Lorentz 5,
     sampled pairs").  The distance of a pair is sum_f softplus(scale_f) * d_f^2 (modules.py:84-88); one step is
 
+        gm_pairs_product_fused (ONE launch: every factor's d2, the loss, sum l' d2_f per factor, every factor's
+        gradient scatter-add)  ->  the optimizer kernels
+
+    for products of at most one SPD factor with up to three of Lorentz / Sphere / Euclidean, and otherwise
+
         F x gm_pairs_dist2  ->  gm_product_loss (loss term, dL/dm per pair, sum l' d2_f per factor)
         ->  F x gm_pairs_grad (scatter-add of softplus(scale_f) * dL/dm * d(d2_f)/dx)  ->  the optimizer kernels
 
@@ -350,7 +355,7 @@ class ProductPairTrainer:
     update)."""
 
     def __init__(self, embedding, optimizer, objective, max_hops_sq, alpha=1.0, scale_optimizer=None,
-                 process_group=None):
+                 process_group=None, fused=None):
         self.emb, self.opt, self.obj = embedding, optimizer, objective
         self.max_hops_sq, self.alpha, self.pg = float(max_hops_sq), alpha, process_group
         self.scale_opt = scale_optimizer
@@ -362,6 +367,10 @@ class ProductPairTrainer:
         self.grads = [torch.zeros_like(x, memory_format=torch.contiguous_format) for x in self.xs]
         for x, g in zip(self.xs, self.grads):
             x.grad = g
+        # one launch for all factors where the fused product kernel takes the factor list (fused=False: the F + 1 + F
+        # launches above, kept for the other products and as the A/B of the fused kernel)
+        can_fuse = _ops.product_fusable([m.spec for m in self.mans], [x.dtype for x in self.xs])
+        self.fused = can_fuse if fused is None else (bool(fused) and can_fuse)
 
     def step(self, idx_i, idx_j, hops, epoch=1):
         """One training step on device tensors (int32/int64 indices, uint8/int16 hop counts); returns the (device,
@@ -371,11 +380,17 @@ class ProductPairTrainer:
         targets = _ops.TargetSpec.hops(hops, self.max_hops_sq)
         loss_spec = self.obj.loss_spec(epoch=epoch, alpha=self.alpha)
         sps = [_softplus_value(s) for s in self.scales] if self.scales else [1.0] * len(self.xs)
-        d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs) for m, x in zip(self.mans, self.xs)]
-        acc, g = _ops.product_loss(d2s, sps, targets, loss_spec)
-        for m, x, gx, sp in zip(self.mans, self.xs, self.grads, sps):
-            gx.zero_()
-            _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, gx, gx, coef=sp)
+        if self.fused:
+            for gx in self.grads:
+                gx.zero_()
+            acc = _ops.pairs_product_fused([m.spec for m in self.mans], [x.detach() for x in self.xs], pairs, targets,
+                                           loss_spec, sps, self.grads)
+        else:
+            d2s = [_ops.pairs_dist2(m.spec, x.detach(), x.detach(), pairs) for m, x in zip(self.mans, self.xs)]
+            acc, g = _ops.product_loss(d2s, sps, targets, loss_spec)
+            for m, x, gx, sp in zip(self.mans, self.xs, self.grads, sps):
+                gx.zero_()
+                _ops.pairs_grad(m.spec, x.detach(), x.detach(), pairs, g, gx, gx, coef=sp)
         if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
             for gx in self.grads:
                 torch.distributed.all_reduce(gx, group=self.pg)

@@ -166,8 +166,9 @@ def test_registered_custom_ops_match_the_python_api():
         ns.pair_dist2(x.cpu(), I.cpu(), J.cpu(), *margs)
 
 
+@pytest.mark.parametrize('fused', [True, False])
 @pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
-def test_product_pair_trainer_vs_oracle(dtype):
+def test_product_pair_trainer_vs_oracle(dtype, fused):
     """BASELINE config 3's "product SPD 3x3 x Lorentz 5, sampled pairs": three steps of ProductPairTrainer (points by
     RiemannianAdam, the two scales by a second RiemannianAdam as run_grid.py:25-28 groups them) against the oracle's
     autograd + optimizer restatement on the same explicit pair lists."""
@@ -186,7 +187,8 @@ def test_product_pair_trainer_vs_oracle(dtype):
     x0 = [x.detach().cpu().clone() for x in emb.xs]
     opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
     sopt = RiemannianAdam(list(emb.scales), lr=0.01)
-    tr = ProductPairTrainer(emb, opt, QuotientLoss(), max_hops_sq=64.0, scale_optimizer=sopt)
+    tr = ProductPairTrainer(emb, opt, QuotientLoss(), max_hops_sq=64.0, scale_optimizer=sopt, fused=fused)
+    assert tr.fused == fused  # SPD x Lorentz is a product the one-launch kernel takes
     g = torch.Generator().manual_seed(1)
     oracles = [O.SpdOracle(3), O.LorentzOracle(5)]
     xs = [t.clone() for t in x0]
@@ -214,6 +216,84 @@ def test_product_pair_trainer_vs_oracle(dtype):
         assert rel_err(emb.xs[f].detach(), xs[f]) < t
         assert abs(float(emb.scales[f].detach()) - float(scales[f])) <= t * abs(float(scales[f]))
     assert abs(float(emb.scales[0].detach()) - 0.5) > 1e-3  # the scales moved, and the kernels followed them
+
+
+PRODUCTS = {
+    'spd3xlorentz5': [('spd', 3, False), ('lorentz', 5)],
+    'lorentz4xspd4stein': [('lorentz', 4), ('spd', 4, True)],
+    'lorentz3xlorentz6': [('lorentz', 3), ('lorentz', 6)],
+    'sphere4xspd2xeuclidean3xlorentz8': [('sphere', 4), ('spd', 2, False), ('euclidean', 3), ('lorentz', 8)],
+    'euclidean5xsphere3xlorentz4': [('euclidean', 5), ('sphere', 3), ('lorentz', 4)],
+}
+
+
+def _make_factor(desc):
+    from graphembed import manifolds as M
+    if desc[0] == 'spd':
+        return M.SymmetricPositiveDefinite(desc[1], use_stein_div=desc[2])
+    return {'lorentz': M.Lorentz, 'sphere': M.Sphere, 'euclidean': M.Euclidean}[desc[0]](desc[1])
+
+
+@pytest.mark.parametrize('mode', ['list_hops', 'triu_dense'])
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('name', sorted(PRODUCTS))
+def test_fused_product_kernel_vs_unfused_sequence(name, dtype, mode):
+    """gm_pairs_product_fused (one launch) against gm_pairs_dist2 x F -> gm_product_loss -> gm_pairs_grad x F (which the
+    oracle tests pin): loss and per-factor scale sums to rounding, every factor's gradient table to the dtype's
+    tolerance; factor order (the left-to-right sum of modules.py:84-88) with the SPD factor in any slot."""
+    from graphembed import _lib as L, _ops
+    mans = [_make_factor(d) for d in PRODUCTS[name]]
+    N = 300
+    torch.manual_seed(11)
+    xs = [m.rand(N, out=torch.empty(0, device=DEV, dtype=dtype), ir=0.7).contiguous() for m in mans]
+    sps = [0.6 + 0.25 * f for f in range(len(mans))]
+    g = torch.Generator().manual_seed(2)
+    if mode == 'list_hops':
+        P = 5000 + 77
+        I = torch.randint(N, (P,), generator=g, dtype=torch.int32).sort().values
+        J = ((I + 1 + torch.randint(N - 1, (P,), generator=g, dtype=torch.int32)) % N).int()
+        H = torch.randint(1, 9, (P,), generator=g, dtype=torch.uint8)
+        pairs = _ops.PairSet.from_lists(I.to(DEV), J.to(DEV), DEV)
+        targets = _ops.TargetSpec.hops(H.to(DEV), 64.0)
+    else:
+        B = 97
+        nodes = torch.randperm(N, generator=g)[:B].to(DEV)
+        dense = (torch.rand(N, N, generator=g, dtype=torch.float64) + 0.05).to(dtype).to(DEV)
+        dense = (dense + dense.T).contiguous()
+        pairs = _ops.PairSet.triu(B, nodes=nodes)
+        targets = _ops.TargetSpec.dense(dense)
+    for kind in (L.GM_LOSS_QUOTIENT, L.GM_LOSS_STRESS):
+        spec = _ops.LossSpec(kind, True, True, alpha=0.7, eps=0.5)
+        d2s = [_ops.pairs_dist2(m.spec, x, x, pairs) for m, x in zip(mans, xs)]
+        acc_u, gw = _ops.product_loss(d2s, sps, targets, spec, pairs=pairs if mode == 'triu_dense' else None)
+        grads_u = [torch.zeros_like(x) for x in xs]
+        for m, x, gx, sp in zip(mans, xs, grads_u, sps):
+            _ops.pairs_grad(m.spec, x, x, pairs, gw, gx, gx, coef=sp)
+        grads_f = [torch.zeros_like(x) for x in xs]
+        acc_f = _ops.pairs_product_fused([m.spec for m in mans], xs, pairs, targets, spec, sps, grads_f)
+        t, ta = (1e-11, 1e-12) if dtype == torch.float64 else (2e-5, 1e-6)
+        assert rel_err(acc_f, acc_u) < ta, (acc_f, acc_u)
+        for gf, gu in zip(grads_f, grads_u):
+            assert torch.isfinite(gf).all() and rel_err(gf, gu) < t, rel_err(gf, gu)
+
+
+def test_fused_product_kernel_declines_other_products():
+    from graphembed import _lib as L, _ops
+    from graphembed import manifolds as M
+    for mans in ([M.SymmetricPositiveDefinite(2), M.SymmetricPositiveDefinite(3)], [M.Grassmann(5, 2), M.Lorentz(4)],
+                 [M.Lorentz(3)] * 5):
+        assert not _ops.product_fusable([m.spec for m in mans], [torch.float32] * len(mans))
+        xs = [m.rand(20, out=torch.empty(0, device=DEV, dtype=torch.float32)).contiguous() for m in mans]
+        I = torch.arange(10, dtype=torch.int32, device=DEV)
+        pairs = _ops.PairSet.from_lists(I, I + 10, DEV)
+        targets = _ops.TargetSpec.hops(torch.ones(10, dtype=torch.uint8, device=DEV), 64.0)
+        spec = _ops.LossSpec(L.GM_LOSS_QUOTIENT, True, True, alpha=1.0, eps=0.5)
+        with pytest.raises(RuntimeError, match='GM_EUNSUPPORTED'):
+            _ops.pairs_product_fused([m.spec for m in mans], xs, pairs, targets, spec, [1.0] * len(mans),
+                                     [torch.zeros_like(x) for x in xs])
+    assert _ops.product_fusable([M.SymmetricPositiveDefinite(3).spec, M.Lorentz(5).spec], [torch.float32] * 2)
+    assert not _ops.product_fusable([M.SymmetricPositiveDefinite(3).spec, M.Lorentz(5).spec],
+                                    [torch.float32, torch.float64])
 
 
 def test_three_byte_pair_upload_format():
