@@ -74,6 +74,13 @@ def parse():
     ap.add_argument('--lists3', action='store_true', help='--e2e lists: upload 3-byte pair words (pack_hops3) instead of '
                     '4-byte ones; measured on one B200 it is NOT faster (1.339 vs 1.31 ms per step: the step is not PCIe '
                     'bound at 4 B/pair and the extra expansion kernel costs 0.03 ms)')
+    ap.add_argument('--layout', default='replicated', choices=['replicated', 'sharded'], help='N>1: `replicated` = every '
+                    'rank holds the whole point table, partial gradients exchanged by the peer-memory owner update after '
+                    'the pair kernel; `sharded` = ROW-SHARDED embeddings (engine.ShardedPairTrainer): every rank holds '
+                    '1/N of the rows, the pair kernel gathers / reduces remote rows over NVLink, the optimizer is local')
+    ap.add_argument('--windows', type=int, default=0, help='order every batch by (window of the target row, source) '
+                    'and let the pair kernel walk the windows one after another (gm_pairs_t.segments); 0: plain '
+                    'source-grouped batches')
     ap.add_argument('--no-secondary', action='store_true', help='skip the secondary lines (configs 1-4, BFS)')
     ap.add_argument('--workload', default='5', help="'5' (default, the bench line) or one of 1, 2a, 2b, 3a, 3b, 4 (or a "
                     "comma list / 'all'): epoch time of that BASELINE config -- on the GPU through TrainingEngine, or "
@@ -105,12 +112,15 @@ def scale_free_edges(n, m, seed):
     return np.stack([t, target], axis=1)
 
 
-def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, keep_levels=False, graph=None):
+def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, keep_levels=False, graph=None,
+                      windows=0):
     """[(I int32, J int32, hops uint8, sources int32, offsets int64, J|hops<<24 int32)] pinned host tensors + max
     hop^2; hop targets come from the multi-source BFS kernel.  (sources, offsets) is the source-grouped form of I, the
-    last entry the packed 4-byte-per-pair form of (J, hops)."""
+    last entry the packed 4-byte-per-pair form of (J, hops).  windows > 1: every batch is put into (window of the target
+    row, source) order (graphembed.engine.window_order) -- the groups are then the (window, source) runs -- for a launch
+    with gm_pairs_t.segments = windows."""
     from graphembed.data import bfs_levels, edges_to_csr
-    from graphembed.engine import pack_hops, pack_hops3
+    from graphembed.engine import pack_hops, pack_hops3, window_order
     from graphembed import _lib as L
     P = 1 << log2_pairs
     per_src = max(1, P // N_SOURCES)
@@ -139,8 +149,17 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, 
         assert int(hops.min().item()) >= 1 and int(hops.max().item()) < 255
         offsets = (torch.arange(n_src + 1, dtype=torch.int64) * per_src)
         hops_h = hops.cpu()
+        if windows > 1:
+            order = window_order(J, n_nodes, windows)
+            I, J, hops_h = I[order].contiguous(), J[order].contiguous(), hops_h[order].contiguous()
+            key = (J.long() * windows) // n_nodes * n_src + slot.long()[order]
+            counts = torch.bincount(key, minlength=windows * n_src)
+            offsets = torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)])
+            src_groups = src.repeat(windows)
+        else:
+            src_groups = src
         three = n_nodes <= (1 << 21) and int(hops_h.max()) <= 8  # (j, hops - 1) fit 21 + 3 bits: 3 bytes per pair
-        batches.append((I.pin_memory(), J.pin_memory(), hops_h.pin_memory(), src.contiguous().pin_memory(),
+        batches.append((I.pin_memory(), J.pin_memory(), hops_h.pin_memory(), src_groups.contiguous().pin_memory(),
                         offsets.pin_memory(), pack_hops(J, hops_h).pin_memory(),
                         pack_hops3(J, hops_h).pin_memory() if three else None))
         if keep_levels:
@@ -593,13 +612,19 @@ def main():
     opt = RiemannianAdam(emb.xs, lr=0.01, max_grad_norm=100, exact=True)
     # every rank draws its own batches (different seed) on the same graph; embeddings replicated
     batches, max_sq, levels, per_src, graph = make_pair_batches(N, args.pairs_log2, args.batches, dev, seed=1234 + rank,
-                                                                n_src=n_src, keep_levels=True)
+                                                                n_src=n_src, keep_levels=True, windows=args.windows)
     P = n_src * per_src  # pairs per step on this rank
+    seg = args.windows if args.windows > 1 else 0
     if pg is not None:
         m = torch.tensor([max_sq], device=dev)
         torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MAX)
         max_sq = float(m.item())
-    trainer = PairTrainer(emb, opt, QuotientLoss(), max_hops_sq=max_sq, alpha=1.0, process_group=pg)
+    sharded = args.layout == 'sharded' and world > 1
+    if sharded:
+        from graphembed.engine import ShardedPairTrainer
+        trainer = ShardedPairTrainer(emb, opt, QuotientLoss(), max_hops_sq=max_sq, process_group=pg, alpha=1.0)
+    else:
+        trainer = PairTrainer(emb, opt, QuotientLoss(), max_hops_sq=max_sq, alpha=1.0, process_group=pg)
     if args.unpacked:
         dev_batches = [tuple(t.to(dev) for t in b[:3]) for b in batches]
     else:  # (i, j | hops << 24): the hop count rides in the top byte of the second index
@@ -612,11 +637,12 @@ def main():
 
     # ---- device-resident timing (value, roofline) ----------------------------------------------------------------
     for k in range(args.warmup):
-        trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
+        trainer.step(*dev_batches[k % len(dev_batches)], epoch=1, segments=seg)
     # per-kernel events for the dominant (pair) kernel: bracket it inside the step by patching the trainer's call
     from graphembed import _ops
     pair_events = []
-    orig = _ops.pairs_loss_fused
+    pair_fn = 'pairs_loss_fused_sharded' if sharded else 'pairs_loss_fused'
+    orig = getattr(_ops, pair_fn)
 
     def timed_pairs(*a, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -626,7 +652,7 @@ def main():
         pair_events.append((e0, e1))
         return r
 
-    _ops.pairs_loss_fused = timed_pairs
+    setattr(_ops, pair_fn, timed_pairs)
     # N>1: also bracket the optimizer call (the fused peer-memory owner update, or the owner update between the NCCL
     # reduce-scatter and all-gather); it includes the wait for the slowest rank's pair kernel
     upd_events = []
@@ -652,18 +678,18 @@ def main():
     t0.record()
     loss = None
     for k in range(args.steps):
-        loss = trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
+        loss = trainer.step(*dev_batches[k % len(dev_batches)], epoch=1, segments=seg)
     t1.record()
     barrier()
     nvlink = None
     if nvl:  # NVLink payload bytes per step, from the driver's counters, over a few extra (untimed) steps
         nvl.start()
         for k in range(5):
-            trainer.step(*dev_batches[k % len(dev_batches)], epoch=1)
+            trainer.step(*dev_batches[k % len(dev_batches)], epoch=1, segments=seg)
         barrier()
         nvlink = nvl.stop(5)
     launches = _lib.launch_count() - launches0
-    _ops.pairs_loss_fused = orig
+    setattr(_ops, pair_fn, orig)
     trainer.opt.step = opt_step
     upd_ms = float(np.mean([a.elapsed_time(b) for a, b in upd_events])) if upd_events else None
     ms = t0.elapsed_time(t1)
@@ -685,7 +711,8 @@ def main():
 
         def e2e_step(k):
             return trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1,
-                                             next_batch=grouped(batches[(k + 1) % nb]), defer_loss=True)
+                                             next_batch=grouped(batches[(k + 1) % nb]), defer_loss=True,
+                                             segments=seg)
         h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
         e2e_api = ('graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
                    + ('int32 j, uint8 hops' if args.unpacked else
@@ -741,8 +768,13 @@ def main():
                         f'({N_SOURCES} BFS sources x targets per step' + (' in total, sources split over the GPUs'
                                                                          if strong else ' per GPU')
                         + '), QuotientLoss, RiemannianAdam(lr .01, clip 100, exact)',
-            'nodes': N, 'pairs_per_step_per_gpu': P, 'parallelism': f'pair-sharded x{world}'
-            + (' + ONE fused kernel over NVLink peer memory: pull+sum the owned (N/G,4,4) gradient rows from every '
+            'nodes': N, 'pairs_per_step_per_gpu': P, 'layout': 'sharded' if sharded else 'replicated',
+            'parallelism': f'pair-sharded x{world}'
+            + (' + ROW-SHARDED embeddings (row v on rank v % G): the pair kernel gathers remote rows and reduces remote '
+               'gradient rows over NVLink peer memory, two flag barriers, LOCAL optimizer update of the owned N/G rows '
+               '(gm_pairs_loss_fused_sharded + gm_peer_barrier + gm_optim_step, no NCCL on the step path)'
+               if sharded else
+               ' + ONE fused kernel over NVLink peer memory: pull+sum the owned (N/G,4,4) gradient rows from every '
                'rank, optimizer update, push the new rows to every rank (gm_optim_step_peer, no NCCL on the step path)'
                if trainer.peer is not None else
                ' + NCCL reduce-scatter of the (N,4,4) gradient, owner-rank optimizer update, all-gather of the points'

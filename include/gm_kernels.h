@@ -107,6 +107,15 @@ typedef struct gm_pairs {
   int64_t n_nodes;    /* rows of the point table == columns of `levels`                                 */
   int64_t per_src;    /* targets drawn per source; G = ceil(P / per_src)                                */
   uint64_t seed;      /* stream id of this step's draws (the caller mixes its seed with the step number) */
+  /* GM_PAIRS_LIST, optional locality hint (0 or 1: none).  The list is `segments` consecutive parts of
+   * ceil(P / segments) pairs (the last may be shorter) and the training kernels walk the parts one after another with
+   * the whole grid instead of giving every warp one contiguous range of the list.  A sampler that orders a batch by
+   * (window of the target row, source) -- segment s holding the pairs whose target lies in rows
+   * [s N / segments, (s+1) N / segments) -- thereby keeps the gradient rows and point rows the grid is scattering into
+   * and gathering from inside a window that fits the L2 cache; the result is the same sum over the same pairs (only the
+   * order of the floating-point reductions changes, as it does from launch to launch anyway). */
+  int32_t segments;
+  int32_t reserved;
 } gm_pairs_t;
 
 /* The draw of GM_PAIRS_SAMPLED, stated once so that host code can reproduce a step's pairs bit for bit:
@@ -312,6 +321,34 @@ int gm_peer_open(const void* handle, void** ptr);       /* maps a peer's arena; 
 int gm_peer_close(void* ptr);
 int gm_optim_step_peer(const gm_manifold_t* man, const gm_optim_t* opt, const gm_peers_t* peers, void* buf1,
                        void* buf2, int64_t N_owned, gm_stream_t stream);
+
+/* ---- row-sharded embeddings (SURVEY 8(e) second scheme; BASELINE config 5 "embeddings row-sharded over NVLink") ----
+ * The (N, ...) point table and its gradient table are cut over `world` GPUs of one NVLink domain, CYCLICALLY: global
+ * row v is row v / world of the shard of rank v % world (world a power of two, <= GM_MAX_PEERS; a cyclic cut needs no
+ * division in the kernel and spreads correlated node ids -- the hubs of a preferential-attachment graph are its first
+ * ids -- evenly).  x[r] / grad[r] are rank r's shards as mapped into THIS process (CUDA IPC, gm_peer_open; the local
+ * shard for r == rank).  The training kernel gathers a pair's rows from whichever shard holds them (16-byte cp.async
+ * over NVLink for remote rows) and adds its gradient rows into the owning shard with red.global.add (NVLink atomics),
+ * so after a step every rank holds the COMPLETE gradient of the rows it owns, and the optimizer update is local:
+ *     gm_pairs_loss_fused_sharded (every rank, its slice of the pair batch)
+ *     gm_peer_barrier(phase 0)    -- all ranks' reductions into my shard are final; acc_out = sum of the ranks' acc
+ *     gm_optim_step               (local shard, zero_grad folded)
+ *     gm_peer_barrier(phase 1)    -- all shards updated and all gradient shards zero: the next step may start
+ * No point row is ever replicated; no collective library call is on the step path.  The reference has no counterpart
+ * (its only multi-GPU mechanism is nn.DataParallel over node chunks, train.py:107-109,203-204).
+ * SPD manifolds (the streaming pair kernels), GM_PAIRS_LIST / GM_PAIRS_SAMPLED; GM_EUNSUPPORTED otherwise. */
+typedef struct gm_row_shards {
+  int32_t world, reserved;
+  const void* x[GM_MAX_PEERS];
+  void* grad[GM_MAX_PEERS];
+} gm_row_shards_t;
+int gm_pairs_loss_fused_sharded(const gm_manifold_t* man, const gm_row_shards_t* shards, const gm_pairs_t* pairs,
+                                const gm_targets_t* targets, const gm_loss_t* loss, double scale_sp, void* out_d2,
+                                double* acc, gm_stream_t stream);
+/* Lock-step barrier over the flag blocks of gm_peers_t (only world, rank, epoch, flags[], acc[], acc_out, n_acc are
+ * read).  `epoch` must increase by one per step and be the same on every rank; phase 0 and 1 use separate flag words.
+ * Phase 0 additionally sums acc[r][0..n_acc) over the ranks into acc_out. */
+int gm_peer_barrier(const gm_peers_t* peers, int32_t phase, gm_stream_t stream);
 
 /* ---- per-point manifold operations (Manifold API, manifolds/base.py:7-81) ----------------------------------- */
 enum gm_point_op {

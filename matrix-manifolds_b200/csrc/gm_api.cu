@@ -38,6 +38,7 @@ int validate_pairs(const gm_pairs_t* p) {
       return GM_OK;
     case GM_PAIRS_LIST:
       if (p->P > 0 && (!p->idx_i || !p->idx_j)) return GM_ENULL;
+      if (p->segments < 0 || p->segments > 64) return GM_EINVAL;
       return GM_OK;
     case GM_PAIRS_TRIU:
       if (p->B < 0 || p->k0 < 0) return GM_EINVAL;
@@ -74,6 +75,33 @@ static int vec_point(const PointArgs& a) {
     case GM_UNIVERSAL: return vec_point_4(a);
     default: return GM_EINVAL;
   }
+}
+
+// Cross-GPU barrier of the row-sharded step (gm_peer_barrier): tell every peer "I have passed point `phase` of step
+// pt.epoch" and wait until every peer has said the same.  It runs in stream order after the kernel whose effects it
+// publishes (the pair kernel's reductions into the peers' gradient shards for phase 0, the optimizer's writes of the
+// local point shard for phase 1); kernel completion makes those visible at system scope before the release stores
+// here.  Phase 0 also sums the ranks' per-step scalars (loss, sum l' d2) into the local acc_out.
+__global__ void __launch_bounds__(64)
+peer_barrier_kernel(PeerTable pt, int phase) {
+  const int tid = threadIdx.x;
+  unsigned long long* mine = pt.flags[pt.rank] + (phase ? kMaxPeers : 0);
+  __threadfence_system();
+  if (tid < pt.world) {
+    flag_store_release(pt.flags[tid] + (phase ? kMaxPeers : 0) + pt.rank, pt.epoch);
+    flag_wait(mine + tid, pt.epoch, pt.timeout_ns);
+  }
+  __syncthreads();
+  if (tid < pt.n_acc) {
+    double s = 0.0;
+    for (int r = 0; r < pt.world; ++r) s += pt.acc[r][tid];
+    pt.acc_out[tid] = s;
+  }
+}
+static int launch_peer_barrier(const PeerTable& pt, int phase, cudaStream_t stream) {
+  peer_barrier_kernel<<<1, 64, 0, stream>>>(pt, phase);
+  note_launch();
+  return check_launch();
 }
 
 static int point_dispatch(const PointArgs& a) {
@@ -138,6 +166,7 @@ static void fill_manifold(PairArgs& a, const gm_manifold_t* m) {
   a.kind = m->kind; a.dtype = m->dtype; a.n = m->n; a.p = m->p; a.flags = m->flags;
   a.wmin = m->wmin; a.wmax = m->wmax;
   a.c_dev = m->c_dev; a.c_grad = m->c_grad;
+  a.sh = no_shards();
 }
 
 static int pair_dispatch(const PairArgs& a) {
@@ -255,6 +284,48 @@ int gm_pairs_loss_fused(const gm_manifold_t* man, const void* x, const gm_pairs_
   a.kmode = K_FUSED;
   a.ps = make_pairs(pairs);
   a.xa = x; a.xb = x; a.ga = grad; a.gb = grad; a.out_d2 = out_d2;
+  a.tg = make_targets(targets);
+  if (packed) { a.tg.data = pairs->idx_j; a.ps.jmask = 0x00ffffffu; }
+  a.lc = make_loss(loss);
+  a.scale_sp = scale_sp;
+  a.acc = acc;
+  a.stream = (cudaStream_t)stream;
+  return pair_dispatch(a);
+}
+
+int gm_pairs_loss_fused_sharded(const gm_manifold_t* man, const gm_row_shards_t* shards, const gm_pairs_t* pairs,
+                                const gm_targets_t* targets, const gm_loss_t* loss, double scale_sp, void* out_d2,
+                                double* acc, gm_stream_t stream) {
+  int rc = manifold_ok(man);
+  if (rc) return rc;
+  if (!shards) return GM_ENULL;
+  const int W = shards->world;
+  if (W < 1 || W > GM_MAX_PEERS || (W & (W - 1)) != 0) return GM_EINVAL;  // cyclic ownership by the low bits of the row id
+  if (man->kind != GM_SPD_AI && man->kind != GM_SPD_STEIN) return GM_EUNSUPPORTED;
+  rc = validate_pairs(pairs);
+  if (rc) return rc;
+  if (!targets || !loss) return GM_ENULL;
+  if (pairs->mode != GM_PAIRS_LIST && pairs->mode != GM_PAIRS_SAMPLED) return GM_EINVAL;
+  if (targets->mode < GM_TGT_VECTOR || targets->mode > GM_TGT_HOPS_PACKED) return GM_EINVAL;
+  const bool packed = targets->mode == GM_TGT_HOPS_PACKED;
+  if (packed && pairs->idx64) return GM_EINVAL;
+  if (pairs->mode == GM_PAIRS_SAMPLED && !packed) return GM_EINVAL;
+  if (loss->kind != GM_LOSS_QUOTIENT && loss->kind != GM_LOSS_STRESS) return GM_EINVAL;
+  if (loss->kind == GM_LOSS_QUOTIENT && !loss->inc_l1 && !loss->inc_l2) return GM_EINVAL;
+  if (pairs->P == 0) return GM_OK;
+  if (!acc || (!packed && !targets->data)) return GM_ENULL;
+  PairArgs a{};
+  fill_manifold(a, man);
+  a.kmode = K_FUSED;
+  a.ps = make_pairs(pairs);
+  a.sh.log2w = 0;
+  while ((1 << a.sh.log2w) < W) ++a.sh.log2w;
+  a.sh.mask = (unsigned)W - 1u;
+  for (int r = 0; r < W; ++r) {
+    if (!shards->x[r] || !shards->grad[r]) return GM_ENULL;
+    a.sh.x[r] = shards->x[r]; a.sh.g[r] = shards->grad[r];
+  }
+  a.xa = shards->x[0]; a.xb = shards->x[0]; a.ga = shards->grad[0]; a.gb = shards->grad[0]; a.out_d2 = out_d2;
   a.tg = make_targets(targets);
   if (packed) { a.tg.data = pairs->idx_j; a.ps.jmask = 0x00ffffffu; }
   a.lc = make_loss(loss);
@@ -558,6 +629,27 @@ int gm_optim_step_peer(const gm_manifold_t* man, const gm_optim_t* opt, const gm
   a.stream = (cudaStream_t)stream;
   a.peer = &pt;
   return point_dispatch(a);
+}
+
+int gm_peer_barrier(const gm_peers_t* peers, int32_t phase, gm_stream_t stream) {
+  if (!peers) return GM_ENULL;
+  if (peers->world < 1 || peers->world > GM_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return GM_EINVAL;
+  if (phase < 0 || phase > 1 || peers->epoch == 0 || peers->n_acc < 0 || peers->n_acc > 64) return GM_EINVAL;
+  PeerTable pt{};
+  pt.world = peers->world; pt.rank = peers->rank; pt.epoch = peers->epoch;
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->flags[r]) return GM_ENULL;
+    if (phase == 0 && peers->n_acc > 0 && !peers->acc[r]) return GM_ENULL;
+    pt.flags[r] = (unsigned long long*)peers->flags[r];
+    pt.acc[r] = (const double*)peers->acc[r];
+  }
+  if (phase == 0 && peers->n_acc > 0 && !peers->acc_out) return GM_ENULL;
+  pt.acc_out = (double*)peers->acc_out; pt.n_acc = phase == 0 ? peers->n_acc : 0;
+  {
+    static const long long timeout_s = [] { const char* e = getenv("GM_PEER_TIMEOUT_S"); return e ? atoll(e) : 300LL; }();
+    pt.timeout_ns = timeout_s > 0 ? (unsigned long long)timeout_s * 1000000000ull : 0ull;
+  }
+  return launch_peer_barrier(pt, phase, (cudaStream_t)stream);
 }
 
 int gm_point_op(const gm_manifold_t* man, int32_t op, const void* x, const void* u, const void* v, void* out,

@@ -26,7 +26,24 @@ struct PairSpec {
   long long n_nodes, per_src;
   unsigned long long seed;
   int per_shift;  // log2(per_src) if it is a power of two, else -1
+  // LIST: the list is nseg consecutive segments of seg_len pairs (the last one may be shorter); the streaming kernels
+  // walk them one after another with the whole grid (seg_len is filled in by the launcher)
+  int nseg;
+  long long seg_len;
 };
+// Row-sharded point / gradient tables (gm_row_shards_t): global row v is row (v >> log2w) of shard (v & mask).
+// log2w < 0: not sharded (the kernels use their plain base pointers).
+struct ShardTab {
+  int log2w;
+  unsigned mask;
+  const void* x[8];
+  void* g[8];
+};
+inline ShardTab no_shards() {
+  ShardTab t{};
+  t.log2w = -1;
+  return t;
+}
 struct TargetSpec {
   int mode;
   const void* data;
@@ -41,6 +58,8 @@ inline PairSpec make_pairs(const gm_pairs_t* p) {
   s.k0 = (p->mode == GM_PAIRS_TRIU) ? p->k0 : 0;
   s.jmask = 0xffffffffu;
   s.levels = nullptr; s.slots = nullptr; s.n_nodes = 0; s.per_src = 1; s.seed = 0; s.per_shift = 0;
+  s.nseg = (p->mode == GM_PAIRS_LIST && p->segments > 1) ? p->segments : 1;
+  s.seg_len = (p->P + s.nseg - 1) / s.nseg;
   if (p->mode == GM_PAIRS_SAMPLED) {
     s.levels = (const unsigned char*)p->levels; s.slots = (const int*)p->slots;
     s.n_nodes = p->n_nodes; s.per_src = p->per_src; s.seed = p->seed;
@@ -105,6 +124,7 @@ struct PairArgs {
   double* acc;
   cudaStream_t stream;
   const ProductExtra* px;  // K_FUSED only: non-null = product-manifold launch (acc has 1 + F slots)
+  ShardTab sh;             // row-sharded tables (xa / xb / ga / gb ignored) when sh.log2w >= 0
 };
 
 // ---- pair enumeration --------------------------------------------------------

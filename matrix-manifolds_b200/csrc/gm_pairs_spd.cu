@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128, MINB)
 spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __restrict__ xb,
                        const T* __restrict__ gout, T coef, T* __restrict__ ga, T* __restrict__ gb,
                        T* __restrict__ out_d2, TargetSpec tg, LossCfg lc, T scale_sp, double* __restrict__ acc,
-                       long long chunk) {
+                       long long chunk, const ShardTab sh) {
   constexpr int E = Op::E;
   constexpr int N = GM_N;
   constexpr int EU = N * (N + 1) / 2;  // gradients are symmetric: the run-length accumulator keeps the upper triangle
@@ -224,8 +224,24 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   const int tid = threadIdx.x, lane = tid & 31;
   const unsigned full = 0xffffffffu;
   const long long warp_id = (long long)blockIdx.x * 4 + (tid >> 5);
-  const long long k0 = warp_id * chunk;
-  const long long kend = (k0 + chunk < ps.P) ? k0 + chunk : ps.P;
+  // A warp owns `chunk` consecutive pairs of every segment of the list (one segment unless the caller cut a LIST into
+  // ps.nseg parts that the whole grid should walk one after another -- see gm_pairs_t.segments): position t of its
+  // walk, t = 0, 32, 64, ..., is pair (t / chunk) * seg_len + warp_id * chunk + t % chunk + lane.
+  const long long wbase = warp_id * chunk + lane;
+  const int nseg = ps.nseg;
+  auto locate = [&](int t, long long& k) -> bool {
+    int s = 0, o = t;
+    if (nseg > 1) {
+      s = t / (int)chunk;
+      o = t - s * (int)chunk;
+      if (s >= nseg) return false;
+    } else if (t >= chunk) {
+      return false;
+    }
+    const long long in_seg = wbase + o;
+    k = (long long)s * ps.seg_len + in_seg;
+    return in_seg < ps.seg_len && k < ps.P;
+  };
   const bool hopsP = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_PACKED;  // hop count in the top byte of idx_j
   const bool hops8 = (KMODE == K_FUSED) && (tg.mode == GM_TGT_HOPS_U8 || hopsP);
   const bool hops16 = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_U16;
@@ -238,9 +254,21 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   // ---- pipeline registers -------------------------------------------------------------------------------------
   using row_t = typename RowId<E * (int)sizeof(T)>::type;
   const row_t kNoRow = (row_t)-1;
-  long long kc = k0 + lane;  // pair computed in this iteration (rows staged in `stage`)
-  PairCursor ahead;          // TRIU position of the furthest pair whose indices have been loaded
-  // queue of pairs kc + 32 q: q = 0 is computed now, q = 1..D-1 have their rows in flight, q = D has its indices (rows
+  // Row-sharded tables (gm_row_shards_t, sh.log2w >= 0): global row v is row v >> log2w of rank (v & mask)'s shard --
+  // local memory or a peer's, mapped over NVLink -- for the point gathers and the gradient reductions alike.
+  const bool sharded = sh.log2w >= 0;
+  auto xrow = [&](const T* base, row_t r) -> const T* {
+    if (sharded) return (const T*)sh.x[(unsigned)r & sh.mask] + (size_t)((unsigned long long)r >> sh.log2w) * E;
+    return base + (size_t)r * E;
+  };
+  auto grow = [&](T* base, row_t r, long long& lr) -> T* {
+    lr = (long long)r;
+    if (sharded) { base = (T*)sh.g[(unsigned)r & sh.mask]; lr = (long long)((unsigned long long)r >> sh.log2w); }
+    return base;
+  };
+  int tc = 0;         // position (in the warp's walk) of the pair computed in this iteration (rows staged in `stage`)
+  PairCursor ahead;   // TRIU position of the furthest pair whose indices have been loaded
+  // queue of the pairs at positions tc + 32 q: q = 0 is computed now, q = 1..D-1 have their rows in flight, q = D has its indices (rows
   // are issued this iteration), q = D + 1 is the pair whose indices are being loaded
   row_t ra[D + 2], rb[D + 2];
   raw_t tgq[D + 1];    // target (K_FUSED) or upstream gradient (K_BWD) of the pair, raw
@@ -277,22 +305,26 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     ra = (row_t)a; rb = (row_t)b;
   };
 
-  ahead.init(ps, kc);
+  ahead.init(ps, wbase);
   GM_UNROLL for (int q = 0; q < D; ++q) {
-    v[q] = kc + 32 * q < kend;
+    long long kq = 0;
+    v[q] = locate(32 * q, kq);
     if (v[q]) {
       unsigned hop = 0;
-      load_rows(kc + 32 * q, ra[q], rb[q], hop);
-      tgq[q] = (sampled && hopsP) ? (raw_t)hop : fetch_scalar(kc + 32 * q, ra[q], rb[q]);
+      load_rows(kq, ra[q], rb[q], hop);
+      tgq[q] = (sampled && hopsP) ? (raw_t)hop : fetch_scalar(kq, ra[q], rb[q]);
       if (rawj) rb[q] &= (row_t)0x00ffffffu;
-      Stage::issue(stage_mem, q, 0, tid, xa + (size_t)ra[q] * E);
-      Stage::issue(stage_mem, q, 1, tid, xb + (size_t)rb[q] * E);
+      Stage::issue(stage_mem, q, 0, tid, xrow(xa, ra[q]));
+      Stage::issue(stage_mem, q, 1, tid, xrow(xb, rb[q]));
     }
     cp_async_commit();
     ahead.advance(ps);
   }
-  v[D] = kc + 32 * D < kend;
-  if (v[D]) load_rows(kc + 32 * D, ra[D], rb[D], hopn);
+  {
+    long long kq = 0;
+    v[D] = locate(32 * D, kq);
+    if (v[D]) load_rows(kq, ra[D], rb[D], hopn);
+  }
 
   // ---- per-lane running state -------------------------------------------------------------------------------------
   double loss_v = 0.0, gd2_v = 0.0;
@@ -312,14 +344,19 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
             gfull[i * N + j] = gacc[i * N - i * (i - 1) / 2 + (j - i)];
             gfull[j * N + i] = gfull[i * N + j];
           }
-        atomic_add_row<T, E>(ga, (long long)acc_row, gfull);
+        long long lr;
+        T* gbase = grow(ga, acc_row, lr);
+        atomic_add_row<T, E>(gbase, lr, gfull);
       }
       GM_UNROLL for (int e = 0; e < EU; ++e) gacc[e] = (T)0;
       acc_row = kNoRow;
     }
   };
 
-  while (__any_sync(full, v[0])) {
+  // one segment: the walk ends at the first position nobody holds a pair at.  Several: the warp that straddles the end
+  // of a segment idles through the rest of its chunk and resumes in the next segment, so the walk runs to its end.
+  const int t_end = (nseg > 1 && wbase - lane < ps.seg_len) ? nseg * (int)chunk : 0;
+  while (nseg > 1 ? tc < t_end : __any_sync(full, v[0])) {
     // (1) rows of the current pair have landed in my slots (the D - 1 younger groups may still be in flight)
     cp_async_wait_group<D - 1>();
     const bool v0 = v[0];
@@ -333,19 +370,22 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     // (2) issue the rows of pair q = D: rows via LDGSTS, scalar via LDG; (3) indices of the pair after it
     tgq[D] = 0;
     if (v[D]) {
-      tgq[D] = (sampled && hopsP) ? (raw_t)hopn : fetch_scalar(kc + 32 * D, ra[D], rb[D]);
+      long long kq = 0;
+      if (KMODE == K_BWD || !hopsP) locate(tc + 32 * D, kq);  // (a packed hop count needs no pair index)
+      tgq[D] = (sampled && hopsP) ? (raw_t)hopn : fetch_scalar(kq, ra[D], rb[D]);
       if (rawj) rb[D] &= (row_t)0x00ffffffu;
       int sn = stage + D;
       if (sn > D) sn -= D + 1;
-      Stage::issue(stage_mem, sn, 0, tid, xa + (size_t)ra[D] * E);
-      Stage::issue(stage_mem, sn, 1, tid, xb + (size_t)rb[D] * E);
+      Stage::issue(stage_mem, sn, 0, tid, xrow(xa, ra[D]));
+      Stage::issue(stage_mem, sn, 1, tid, xrow(xb, rb[D]));
     }
     cp_async_commit();
     ahead.advance(ps);
-    v[D + 1] = kc + 32 * (D + 1) < kend;
+    long long kh = 0;
+    v[D + 1] = locate(tc + 32 * (D + 1), kh);
     ra[D + 1] = kNoRow; rb[D + 1] = kNoRow;
     unsigned hop_next = 0;
-    if (v[D + 1]) load_rows(kc + 32 * (D + 1), ra[D + 1], rb[D + 1], hop_next);
+    if (v[D + 1]) load_rows(kh, ra[D + 1], rb[D + 1], hop_next);
 
     // (4) the math
     T gx[E], gy[E];
@@ -367,14 +407,20 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
         loss_v += (double)lv;
         gd2_v += (double)dm * (double)d2;
         w = dm * scale_sp;
-        if (out_d2) out_d2[kc] = d2;
+        if (out_d2) {
+          long long k0 = 0;
+          locate(tc, k0);
+          out_d2[k0] = d2;
+        }
       }
       if constexpr (Op::kCanPrep) {
         op.eig_backward(st, w, gx, gy);  // loss weight folded into the N eigen-coefficients
       } else {
         GM_UNROLL for (int e = 0; e < E; ++e) { gx[e] *= w; gy[e] *= w; }
       }
-      atomic_add_row<T, E>(gb, (long long)rb0, gy);
+      long long lrb;
+      T* gbb = grow(gb, rb0, lrb);
+      atomic_add_row<T, E>(gbb, lrb, gy);
     }
     // (5) first-endpoint gradient: run-length accumulation in registers
     {
@@ -390,12 +436,14 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
           GM_UNROLL for (int i = 0; i < N; ++i)
             GM_UNROLL for (int j = i; j < N; ++j) gacc[i * N - i * (i - 1) / 2 + (j - i)] = gx[i * N + j];
         } else if (v0) {
-          atomic_add_row<T, E>(ga, (long long)ra0, gx);
+          long long lra;
+          T* gba = grow(ga, ra0, lra);
+          atomic_add_row<T, E>(gba, lra, gx);
         }
       }
     }
     // (6) rotate the pipeline
-    kc += 32;
+    tc += 32;
     GM_UNROLL for (int q = 0; q < D + 1; ++q) { ra[q] = ra[q + 1]; rb[q] = rb[q + 1]; v[q] = v[q + 1]; }
     GM_UNROLL for (int q = 0; q < D; ++q) tgq[q] = tgq[q + 1];
     hopn = hop_next;
@@ -411,7 +459,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
 template <class Op, typename T>
 static int launch_op(const Op& op, const PairArgs& a) {
   if (a.ps.P <= 0) return 0;
-  if (a.px) return launch_product<SpdLead<Op>, T>(SpdLead<Op>{op}, a);
+  if (a.px) return a.sh.log2w >= 0 ? GM_EUNSUPPORTED : launch_product<SpdLead<Op>, T>(SpdLead<Op>{op}, a);
   const int threads = 128;
   long long blocks = (a.ps.P + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return GM_EINVAL;
@@ -422,7 +470,7 @@ static int launch_op(const Op& op, const PairArgs& a) {
 #define GM_MINB_F32 4
 #endif
 #ifndef GM_PF_DEPTH
-#define GM_PF_DEPTH 2
+#define GM_PF_DEPTH 1
 #endif
   constexpr int MINB = sizeof(T) == 4 ? GM_MINB_F32 : 2;
   // rows stay in flight for two iterations when MINB CTAs of three staging slots still fit one SM's shared memory
@@ -440,9 +488,13 @@ static int launch_op(const Op& op, const PairArgs& a) {
       long long want = (a.ps.P + threads - 1) / threads;
       long long nb = want < max_blocks ? want : max_blocks;
       long long warps = nb * (threads / 32);
-      long long chunk = ((a.ps.P + warps - 1) / warps + 31) / 32 * 32;
-      kern<<<(unsigned)nb, threads, Stage::BYTES, a.stream>>>(op, a.ps, xa, xb, gout, coef, (T*)a.ga, (T*)a.gb, out_d2,
-                                                             a.tg, a.lc, scale, acc, chunk);
+      PairSpec ps = a.ps;
+      if (ps.mode != GM_PAIRS_LIST || ps.nseg < 2 || ps.P < ps.nseg * 32LL * warps) ps.nseg = 1;  // (tiny lists: one walk)
+      ps.seg_len = (ps.P + ps.nseg - 1) / ps.nseg;
+      long long chunk = ((ps.seg_len + warps - 1) / warps + 31) / 32 * 32;
+      if (chunk * ps.nseg > 0x7fffffffLL) return GM_EINVAL;
+      kern<<<(unsigned)nb, threads, Stage::BYTES, a.stream>>>(op, ps, xa, xb, gout, coef, (T*)a.ga, (T*)a.gb, out_d2,
+                                                             a.tg, a.lc, scale, acc, chunk, a.sh);
       note_launch();
       return check_launch();
     };
@@ -452,6 +504,7 @@ static int launch_op(const Op& op, const PairArgs& a) {
     return launch_stream(spd_pair_stream_kernel<Op, T, K_FUSED, MINB, DEPTH>, nullptr, (T)0, (T*)a.out_d2, (T)a.scale_sp,
                          a.acc);
   }
+  if (a.sh.log2w >= 0) return GM_EUNSUPPORTED;  // row-sharded tables: the streaming (training) kernels only
   switch (a.kmode) {
     case K_FWD:
       spd_pair_kernel<Op, T, K_FWD><<<grid, block, 0, a.stream>>>(

@@ -40,7 +40,9 @@ class Pairs(ctypes.Structure):
                 ('nodes', ctypes.c_void_p), ('k0', ctypes.c_int64),
                 # GM_PAIRS_SAMPLED (zero otherwise)
                 ('levels', ctypes.c_void_p), ('slots', ctypes.c_void_p), ('n_nodes', ctypes.c_int64),
-                ('per_src', ctypes.c_int64), ('seed', ctypes.c_uint64)]
+                ('per_src', ctypes.c_int64), ('seed', ctypes.c_uint64),
+                # GM_PAIRS_LIST locality hint: the list is `segments` consecutive parts walked one after another
+                ('segments', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 class Loss(ctypes.Structure):
@@ -71,6 +73,13 @@ class Peers(ctypes.Structure):
                 ('grad', ctypes.c_void_p * GM_MAX_PEERS), ('flags', ctypes.c_void_p * GM_MAX_PEERS),
                 ('acc', ctypes.c_void_p * GM_MAX_PEERS), ('acc_out', ctypes.c_void_p), ('n_acc', ctypes.c_int32),
                 ('reserved', ctypes.c_int32), ('gsum', ctypes.c_void_p)]
+
+
+
+
+class RowShards(ctypes.Structure):
+    _fields_ = [('world', ctypes.c_int32), ('reserved', ctypes.c_int32), ('x', ctypes.c_void_p * GM_MAX_PEERS),
+                ('grad', ctypes.c_void_p * GM_MAX_PEERS)]
 
 
 _vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
@@ -105,6 +114,10 @@ _PROTOTYPES = {
                                               ctypes.POINTER(_i64), _vp]),
     'gm_optim_step_peer': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(Optim), ctypes.POINTER(Peers), _vp,
                                           _vp, _i64, _vp]),
+    'gm_pairs_loss_fused_sharded': (ctypes.c_int, [ctypes.POINTER(Manifold), ctypes.POINTER(RowShards),
+                                                   ctypes.POINTER(Pairs), ctypes.POINTER(Targets), ctypes.POINTER(Loss),
+                                                   _dbl, _vp, _vp, _vp]),
+    'gm_peer_barrier': (ctypes.c_int, [ctypes.POINTER(Peers), _i32, _vp]),
     'gm_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     'gm_peer_free': (ctypes.c_int, [_vp]),
     'gm_peer_export': (ctypes.c_int, [_vp, ctypes.c_char_p]),

@@ -79,9 +79,10 @@ class PairSet:
     """Which pairs a launch covers (mirrors gm_pairs_t); keeps the index tensors alive."""
 
     def __init__(self, mode, P, idx_i=None, idx_j=None, B=0, nodes=None, idx64=0, k0=0, levels=None, slots=None,
-                 n_nodes=0, per_src=0, seed=0):
+                 n_nodes=0, per_src=0, seed=0, segments=0):
         self.mode, self.P, self.idx_i, self.idx_j, self.B, self.nodes, self.idx64 = mode, P, idx_i, idx_j, B, nodes, idx64
         self.k0 = k0
+        self.segments = int(segments)
         self.levels, self.slots, self.n_nodes, self.per_src, self.seed = levels, slots, n_nodes, per_src, seed
 
     @staticmethod
@@ -106,14 +107,19 @@ class PairSet:
         return PairSet(L.GM_PAIRS_ELEMENTWISE, P)
 
     @staticmethod
-    def from_lists(idx_i, idx_j, device):
+    def from_lists(idx_i, idx_j, device, segments=0):
+        """Explicit pair lists.  `segments` (optional locality hint, gm_pairs_t.segments): the lists are that many
+        consecutive parts of ceil(P / segments) pairs which the training kernels walk one after another with the whole
+        grid -- for batches ordered by (window of the target row, source), see engine.window_order."""
+        if not 0 <= int(segments) <= 64:
+            raise ValueError('segments must be in [0, 64]')
         i, f64 = _index_tensor(idx_i, device)
         j, g64 = _index_tensor(idx_j, device)
         if f64 != g64:
             i, j, f64 = i.long(), j.long(), 1
         if i.shape != j.shape or i.ndim != 1:
             raise ValueError('pair index lists must be 1-D tensors of the same length')
-        return PairSet(L.GM_PAIRS_LIST, i.numel(), idx_i=i, idx_j=j, idx64=f64)
+        return PairSet(L.GM_PAIRS_LIST, i.numel(), idx_i=i, idx_j=j, idx64=f64, segments=segments)
 
     @staticmethod
     def triu(B, nodes=None, device=None, k0=0, P=None):
@@ -150,7 +156,7 @@ class PairSet:
                        nodes=None if self.nodes is None else self.nodes.data_ptr(), k0=self.k0,
                        levels=None if self.levels is None else self.levels.data_ptr(),
                        slots=None if self.slots is None else self.slots.data_ptr(), n_nodes=self.n_nodes,
-                       per_src=self.per_src, seed=self.seed)
+                       per_src=self.per_src, seed=self.seed, segments=self.segments, reserved=0)
 
 
 @_no_function_modes
@@ -241,6 +247,36 @@ def pairs_loss_fused(spec, x, pairs, targets, loss, scale_sp, grad, acc=None, wa
                                          L.stream_ptr(x.device))
     L.check(rc, 'gm_pairs_loss_fused')
     return acc, d2
+
+
+@_no_function_modes
+def pairs_loss_fused_sharded(spec, x_ptrs, grad_ptrs, dtype, device, pairs, targets, loss, scale_sp, acc, want_d2=False):
+    """gm_pairs_loss_fused_sharded: the fused training kernel over ROW-SHARDED tables.  x_ptrs / grad_ptrs: device
+    addresses (ints) of every rank's point / gradient shard as mapped into this process, in rank order (a power-of-two
+    count); global row v is row v // world of shard v % world.  Gradient rows are added into the owning shards; acc
+    (2 float64) is accumulated into.  Returns (acc, d2 or None)."""
+    W = len(x_ptrs)
+    if W != len(grad_ptrs) or W < 1 or W > L.GM_MAX_PEERS or W & (W - 1):
+        raise ValueError('row shards: a power-of-two number of ranks, at most %d' % L.GM_MAX_PEERS)
+    sh = L.RowShards()
+    sh.world = W
+    for r in range(W):
+        sh.x[r], sh.grad[r] = int(x_ptrs[r]), int(grad_ptrs[r])
+    d2 = torch.empty(pairs.P, dtype=dtype, device=device) if want_d2 else None
+    m, p, t, l = spec.c_struct(dtype, device), pairs.c_struct(), targets.c_struct(), loss.c_struct()
+    with torch.cuda.device(device):
+        rc = L.lib().gm_pairs_loss_fused_sharded(ctypes.byref(m), ctypes.byref(sh), ctypes.byref(p), ctypes.byref(t),
+                                                 ctypes.byref(l), float(scale_sp), L.ptr(d2), L.ptr(acc),
+                                                 L.stream_ptr(device))
+    L.check(rc, 'gm_pairs_loss_fused_sharded')
+    return acc, d2
+
+
+def peer_barrier(table, phase, device):
+    """gm_peer_barrier over the flag blocks of a peer table (graphembed.parallel.ShardedArena.next_table())."""
+    with torch.cuda.device(device):
+        rc = L.lib().gm_peer_barrier(ctypes.byref(table), int(phase), L.stream_ptr(device))
+    L.check(rc, 'gm_peer_barrier')
 
 
 FUSABLE_VECTOR_KINDS = (L.GM_LORENTZ, L.GM_SPHERE, L.GM_EUCLIDEAN)

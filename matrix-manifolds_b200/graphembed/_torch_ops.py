@@ -26,7 +26,7 @@ _lib.define('pair_dist2(Tensor x, Tensor idx_i, Tensor idx_j, int kind, int n, i
             'float wmax) -> Tensor')
 _lib.define('pairs_loss_fused(Tensor x, Tensor idx_i, Tensor idx_j, Tensor? hops, int kind, int n, int p, int flags, '
             'float wmin, float wmax, int loss_kind, bool inc_l1, bool inc_l2, float alpha, float eps, float max_hops_sq, '
-            'float scale_sp, Tensor(a!) grad, Tensor(b!) acc) -> ()')
+            'float scale_sp, Tensor(a!) grad, Tensor(b!) acc, int segments=0) -> ()')
 _lib.define('optim_step(Tensor(a!) x, Tensor grad, Tensor(b!)? buf1, Tensor(c!)? buf2, int kind, int n, int p, int flags, '
             'float wmin, float wmax, int opt_kind, bool exact, bool has_clip, int step, bool has_momentum, '
             'bool first_step, bool retr_qr, bool zero_grad, float lr, float beta1, float beta2, float momentum, '
@@ -52,8 +52,8 @@ def _pair_dist2(x, idx_i, idx_j, kind, n, p, flags, wmin, wmax):
 
 
 def _pairs_loss_fused(x, idx_i, idx_j, hops, kind, n, p, flags, wmin, wmax, loss_kind, inc_l1, inc_l2, alpha, eps,
-                      max_hops_sq, scale_sp, grad, acc):
-    pairs = _ops.PairSet.from_lists(idx_i, idx_j, x.device)
+                      max_hops_sq, scale_sp, grad, acc, segments=0):
+    pairs = _ops.PairSet.from_lists(idx_i, idx_j, x.device, segments=segments)
     tg = _ops.TargetSpec.hops_packed(max_hops_sq) if hops is None else _ops.TargetSpec.hops(hops, max_hops_sq)
     loss = _ops.LossSpec(loss_kind, inc_l1, inc_l2, alpha=alpha, eps=eps)
     _ops.pairs_loss_fused(_spec(kind, n, p, flags, wmin, wmax, x), x, pairs, tg, loss, scale_sp, grad, acc)

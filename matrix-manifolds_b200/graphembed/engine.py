@@ -20,7 +20,8 @@ from . import _lib as L
 from . import _ops
 from . import _torch_ops
 from .modules import ManifoldParameter, _softplus_value
-from .parallel import RowShards, allreduce_step_buffers, try_peer_arena
+from .parallel import (RowShards, ShardedArena, allreduce_step_buffers, cyclic_shard, cyclic_unshard,
+                       try_peer_arena)
 
 
 def pack_hops(idx_j, hops):
@@ -78,6 +79,7 @@ class PairTrainer:
         self.emb, self.opt, self.obj = embedding, optimizer, objective
         self.max_hops_sq, self.alpha, self.pg = float(max_hops_sq), alpha, process_group
         self.x = embedding.xs[0]
+        self.n_points = self.x.shape[0]
         self.man = embedding.manifolds[0]
         self.grad = torch.zeros_like(self.x, memory_format=torch.contiguous_format)
         self.x.grad = self.grad
@@ -128,11 +130,12 @@ class PairTrainer:
             self._fold_zero_grad = True
 
     # ---- device-resident inputs ---------------------------------------------------------------------------------
-    def step(self, idx_i, idx_j, hops, epoch=1):
-        """One training step on device tensors; returns the (device, float64) loss of the batch."""
-        pairs = _ops.PairSet.from_lists(idx_i, idx_j, self.x.device)
+    def step(self, idx_i, idx_j, hops, epoch=1, segments=0):
+        """One training step on device tensors; returns the (device, float64) loss of the batch.  `segments`: the
+        batch is in window_order(..., segments) (gm_pairs_t.segments: the kernel walks the windows one after another)."""
+        pairs = _ops.PairSet.from_lists(idx_i, idx_j, self.x.device, segments=segments)
         if hops is None:  # hop counts packed into the top byte of idx_j (pack_hops)
-            if self.x.shape[0] > (1 << 24) or pairs.idx64:
+            if self.n_points > (1 << 24) or pairs.idx64:
                 raise ValueError('packed hop counts need int32 indices and fewer than 2^24 points')
             targets = _ops.TargetSpec.hops_packed(self.max_hops_sq)
         else:
@@ -146,7 +149,7 @@ class PairTrainer:
         is uploaded, stored or read: the step's input is the list of sources.  The draw is stated in include/gm_kernels.h
         and can be reproduced on the host bit for bit, so `step(I, pack_hops(J, H), None)` on such lists is the same step."""
         pairs = _ops.PairSet.sampled(sources, levels, per_src, seed, slots=slots)
-        if levels.shape[1] != self.x.shape[0]:
+        if levels.shape[1] != self.n_points:
             raise ValueError('the level matrix must have one column per embedded point')
         return self._step_pairs(pairs, _ops.TargetSpec.hops_packed(self.max_hops_sq), epoch)
 
@@ -184,7 +187,7 @@ class PairTrainer:
             torch.ops.graphembed_b200.pairs_loss_fused(
                 self.x.detach(), pairs.idx_i, pairs.idx_j, targets.data, *_torch_ops.manifold_args(self.man.spec),
                 loss_spec.kind, bool(loss_spec.inc_l1), bool(loss_spec.inc_l2), float(loss_spec.alpha),
-                float(loss_spec.eps), float(targets.max_sq), float(sp), self.grad, self.acc)
+                float(loss_spec.eps), float(targets.max_sq), float(sp), self.grad, self.acc, pairs.segments)
         else:
             _ops.pairs_loss_fused(self.man.spec, self.x.detach(), pairs, targets, loss_spec, sp, self.grad, self.acc)
         if self.peer is not None:
@@ -276,7 +279,8 @@ class PairTrainer:
         self._loss_slot = 1 - s
         return float(self._loss_host[s][0])
 
-    def step_host_grouped(self, sources, offsets, idx_j, hops, epoch=1, next_batch=None, defer_loss=False):
+    def step_host_grouped(self, sources, offsets, idx_j, hops, epoch=1, next_batch=None, defer_loss=False,
+                          segments=0):
         """One step from PINNED host tensors in source-grouped (CSR-like) form, the natural output of a sampler that
         draws targets per BFS source: pairs offsets[g] <= k < offsets[g+1] are (sources[g], idx_j[k]) with hop count
         hops[k].  sources int32 (G,), offsets int64 (G+1,), idx_j int32 (P,), hops uint8/int16 (P,).  Uploads 5 bytes
@@ -330,10 +334,108 @@ class PairTrainer:
         _ops.expand_groups(ds[:G], do[:G + 1], di[:P])
         if packed3:
             _ops.unpack_pairs3(self._staging3[slot], P, dj)
-        loss = self.step(di[:P], dj[:P], None if packed else dh[:P], epoch=epoch)
+        loss = self.step(di[:P], dj[:P], None if packed else dh[:P], epoch=epoch, segments=segments)
         if defer_loss:  # read this step's loss back asynchronously, hand out the previous step's
             return self._queue_loss_read()
         return loss.item()
+
+
+class ShardedPairTrainer(PairTrainer):
+    """PairTrainer over ROW-SHARDED embeddings (SURVEY 8(e) second scheme, BASELINE config 5 "embeddings row-sharded over
+    NVLink"): every rank keeps only the rows v with v % world == rank of the point table, their gradient rows and
+    their optimizer state; the pair batch is sharded over the ranks as before (every rank passes ITS pairs, with
+    GLOBAL row ids).  One step is
+
+        fused pair kernel   rows gathered from whichever shard holds them (16-byte cp.async over NVLink for remote
+                            ones), gradient rows added into the owning shard (red.global.add over NVLink)
+        barrier 0           every rank's reductions into my shard are final; loss summed over the ranks
+        optimizer kernel    local shard only (gradient rows handed back zeroed)
+        barrier 1           every shard updated
+
+    -- no replicated table, no reduce-scatter / all-gather phase, no NCCL call on the step path; the NVLink traffic
+    (about 2 x 64 B per remote pair endpoint for SPD 4x4 fp32) rides inside the pair kernel instead of following it.
+    Same trajectory as PairTrainer on one GPU up to floating-point summation order.  Needs CUDA IPC between the ranks
+    (one NVLink domain), a power-of-two world size dividing the number of points, and an SPD manifold; raises
+    otherwise (use PairTrainer's replicated owner update then).
+
+    embedding : every rank passes the same full ManifoldEmbedding (same initial points); after construction the full
+        table is released (`keep_full=True` keeps it, stale) and `gather()` rebuilds it from the shards.
+    """
+
+    def __init__(self, embedding, optimizer, objective, max_hops_sq, process_group, alpha=1.0, keep_full=False):
+        if embedding.n_components != 1:
+            raise ValueError('ShardedPairTrainer drives a single-manifold embedding')
+        dist = torch.distributed
+        self.emb, self.opt, self.obj = embedding, optimizer, objective
+        self.max_hops_sq, self.alpha, self.pg = float(max_hops_sq), alpha, process_group
+        self.man = embedding.manifolds[0]
+        if self.man.spec.kind not in (L.GM_SPD_AI, L.GM_SPD_STEIN):
+            raise ValueError('row-sharded training is built for the SPD pair kernels')
+        full = embedding.xs[0]
+        self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        self.n_points = full.shape[0]
+        if self.n_points % self.world:
+            raise ValueError(f'{self.n_points} points do not split evenly over {self.world} ranks')
+        arena = try_peer_arena(cyclic_shard(full.data, self.rank, self.world), 2, process_group, cls=ShardedArena)
+        if arena is None:
+            raise RuntimeError('row-sharded training needs CUDA IPC peer memory between all ranks (one NVLink domain, '
+                               'NCCL process group, GM_PEER_UPDATE != 0)')
+        self.peer = arena
+        self.x, self.grad, self.acc = arena.x, arena.grad, arena.acc
+        own = ManifoldParameter(arena.x, manifold=self.man)
+        own.grad = arena.grad
+        own._gm_zero_grad_after_step = True  # the local optimizer kernel hands every gradient row back zeroed
+        self._own = own
+        replaced = False
+        for g in optimizer.param_groups:
+            for k, prm in enumerate(g['params']):
+                if prm is full:
+                    g['params'][k] = own
+                    replaced = True
+        if not replaced:
+            raise ValueError('optimizer does not hold the embedding parameter')
+        self._full = full
+        if not keep_full:
+            full.data = full.data.new_empty((0,) + tuple(full.shape[1:]))
+        self._staging = None
+        self._copy_stream = None
+        self.shards = None
+        self._grad_is_clean = True
+        self._fold_zero_grad = True
+
+    def _step_pairs(self, pairs, targets, epoch):
+        loss_spec = self.obj.loss_spec(epoch=epoch, alpha=self.alpha)
+        self.acc.zero_()
+        sp = _softplus_value(self.emb.scales[0])
+        a = self.peer
+        _ops.pairs_loss_fused_sharded(self.man.spec, a.x_ptrs, a.grad_ptrs, self.x.dtype, self.x.device, pairs, targets,
+                                      loss_spec, sp, self.acc)
+        table = a.next_table()
+        _ops.peer_barrier(table, 0, self.x.device)
+        self.opt.step()
+        _ops.peer_barrier(table, 1, self.x.device)
+        return a.acc_out[0]
+
+    def gather(self):
+        """The full (N, ...) point table, rebuilt from every rank's shard (an all-gather; for validation / snapshots)."""
+        buf = self.x.new_empty((self.world,) + tuple(self.x.shape))
+        torch.distributed.all_gather_into_tensor(buf, self.x.contiguous(), group=self.pg)
+        full = cyclic_unshard(list(buf.unbind(0)))
+        self._full.data = full
+        return full
+
+
+def window_order(idx_j, n_points, segments):
+    """Permutation that puts a pair batch into (window of the target row, original position) order: window w holds the
+    pairs whose target j lies in rows [w n / segments, (w + 1) n / segments).  Applied to a source-grouped batch it
+    keeps every source's pairs consecutive inside each window.  Launch the reordered lists with `segments=segments`
+    (gm_pairs_t.segments): the pair kernel then walks window after window with its whole grid, so the gradient rows it
+    scatters into and the point rows it gathers stay inside one L2-sized window at a time (measured on B200: the fused
+    SPD 4x4 kernel leaves its 3.3 GB-per-launch random DRAM traffic bound and becomes issue bound).  idx_j: int tensor
+    (a packed hop count in the top byte is ignored)."""
+    j = idx_j.long() & 0x00ffffff if idx_j.dtype == torch.int32 else idx_j.long()
+    window = (j * int(segments)) // int(n_points)
+    return torch.sort(window, stable=True).indices
 
 
 class ProductPairTrainer:

@@ -90,6 +90,8 @@ class PeerArena:
     x : the (N, ...) CUDA tensor holding the points (its values are copied into the arena); N must divide evenly.
     """
 
+    _need_even = True  # the (N, ...) table is cut into `world` equal row blocks
+
     def __init__(self, x, n_acc, group):
         """Runs all three construction phases back to back (every rank must succeed).  `try_peer_arena` drives the
         phases one at a time with a status vote in between, so that a failure on ONE rank makes ALL ranks fall back
@@ -116,7 +118,7 @@ class PeerArena:
         """Phase 1 (local, no collective): allocate the arena, export its IPC handle, move the points in."""
         if self.world > L.GM_MAX_PEERS:
             raise RuntimeError(f'peer update supports up to {L.GM_MAX_PEERS} ranks (one NVLink domain)')
-        if x.shape[0] % self.world != 0:
+        if self._need_even and x.shape[0] % self.world != 0:
             raise RuntimeError(f'{x.shape[0]} rows do not split evenly over {self.world} ranks')
         lib = L.lib()
         base = ctypes.c_void_p()
@@ -168,7 +170,7 @@ class PeerArena:
         # already overlap pulls and pushes, and the extra launches cost more than they buy.  Default: pipelined for 2 ranks.
         self.gsum = None
         mode = os.environ.get('GM_PEER_PIPELINE', 'auto')
-        if mode == '1' or (mode == 'auto' and self.world == 2):
+        if self._need_even and (mode == '1' or (mode == 'auto' and self.world == 2)):
             self.gsum = torch.empty_like(self.x[self.lo:self.hi])
             self.table.gsum = self.gsum.data_ptr()
         for r, b in enumerate(self.peer_base):
@@ -202,6 +204,45 @@ class PeerArena:
             self.base = None
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Row-sharded embeddings: every rank holds ONLY the rows it owns (cyclic ownership, include/gm_kernels.h
+# gm_row_shards_t); the pair kernel gathers remote rows and reduces remote gradient rows over NVLink peer memory.
+# ---------------------------------------------------------------------------------------------------------------------
+def cyclic_shard(t, rank, world):
+    """Rows rank, rank + world, rank + 2 world, ... of the (N, ...) tensor `t` (a contiguous copy)."""
+    return t[rank::world].contiguous()
+
+
+def cyclic_unshard(shards):
+    """Inverse of cyclic_shard: shards[r] holds rows r, r + world, ...; the row counts may differ by one."""
+    world = len(shards)
+    n = sum(s.shape[0] for s in shards)
+    full = shards[0].new_empty((n,) + tuple(shards[0].shape[1:]))
+    for r, s in enumerate(shards):
+        full[r::world] = s
+    return full
+
+
+class ShardedArena(PeerArena):
+    """Per-rank arena [point shard | gradient shard | step accumulator | accumulator sum | flag block] of a
+    ROW-SHARDED embedding, mapped by every other rank through CUDA IPC.  `x` is this rank's shard (cyclic_shard of the
+    full table; every rank must pass the same number of rows -- N divisible by the world size).  x_ptrs / grad_ptrs
+    are the tables gm_pairs_loss_fused_sharded takes; next_table() the flag / accumulator table of gm_peer_barrier."""
+    _need_even = False
+
+    def _init_fields(self, x, n_acc, group):
+        super()._init_fields(x, n_acc, group)
+        if self.world & (self.world - 1):
+            raise RuntimeError('row-sharded embeddings need a power-of-two number of ranks (cyclic ownership)')
+        self.rows, self.lo, self.hi = x.shape[0], 0, x.shape[0]
+
+    def phase_open(self, handles):
+        super().phase_open(handles)
+        self.table.row_lo = 0
+        self.x_ptrs = [b + self.off_x for b in self.peer_base]
+        self.grad_ptrs = [b + self.off_g for b in self.peer_base]
+
+
 def run_phases(group, device, phases):
     """Runs `phases` = [(local_fn, collective_fn or None), ...] in lock step over the ranks of `group`: after every
     local_fn a MIN all-reduce of a status flag decides whether ALL ranks continue (then collective_fn, if any, runs on
@@ -223,8 +264,8 @@ def run_phases(group, device, phases):
     return True, None
 
 
-def try_peer_arena(x, n_acc, group):
-    """PeerArena if EVERY rank of `group` could allocate, export and map the arenas (NCCL backend, CUDA IPC between
+def try_peer_arena(x, n_acc, group, cls=None):
+    """PeerArena (or `cls`, a subclass) if EVERY rank of `group` could allocate, export and map the arenas (NCCL backend, CUDA IPC between
     the processes, at most GM_MAX_PEERS ranks); otherwise None on every rank, and the caller keeps the NCCL
     reduce-scatter / all-gather owner update.  GM_PEER_UPDATE=0 disables the attempt."""
     if group is None or not x.is_cuda or dist.get_backend(group) != 'nccl':
@@ -232,7 +273,8 @@ def try_peer_arena(x, n_acc, group):
     world = dist.get_world_size(group)
     if world < 2 or os.environ.get('GM_PEER_UPDATE', '1') == '0':
         return None
-    arena = PeerArena.__new__(PeerArena)
+    cls = cls or PeerArena
+    arena = cls.__new__(cls)
     arena._init_fields(x, n_acc, group)
     box = {}
     ok, err = run_phases(group, x.device, [

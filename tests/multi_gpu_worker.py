@@ -4,7 +4,9 @@ Every rank trains the same embedding on its own shard of a pair batch for a few 
   peer   : owner update as ONE kernel over NVLink peer memory (gm_optim_step_peer)
   nccl   : ncclReduceScatter + owner update + ncclAllGather (GM_PEER_UPDATE=0)
   single : all shards concatenated on one GPU, no process group (rank 0 only)
-and checks that the three trajectories agree (summation order differs: 2e-5 fp32 / 1e-10 fp64 relative).
+  sharded: ROW-SHARDED embeddings (engine.ShardedPairTrainer: no replicated table, remote rows gathered / reduced over
+           NVLink inside the pair kernel, local optimizer), SPD cases
+and checks that the trajectories agree (summation order differs: 2e-5 fp32 / 1e-10 fp64 relative).
 
 With the smooth StressLoss EVERY row must agree (zero excluded rows).  QuotientLoss has kinks (|m/t - 1| at m == t):
 a pair sitting within rounding of one gets the opposite gradient sign under a different summation order, in the
@@ -64,8 +66,8 @@ def kink_margin(kind, x_prev, rows, parts, dev, epoch):
     return float(torch.minimum(q1, q2).min().item())
 
 
-def run(kind, dtype, opt_name, n_nodes, P, steps, dev, pg, ranks, loss_name='quotient'):
-    from graphembed.engine import PairTrainer
+def run(kind, dtype, opt_name, n_nodes, P, steps, dev, pg, ranks, loss_name='quotient', sharded=False):
+    from graphembed.engine import PairTrainer, ShardedPairTrainer
     from graphembed.objectives import QuotientLoss, StressLoss
     from graphembed.optim import RiemannianAdam, RiemannianSGD
     emb = make(kind, dtype, n_nodes, dev)
@@ -74,15 +76,20 @@ def run(kind, dtype, opt_name, n_nodes, P, steps, dev, pg, ranks, loss_name='quo
     else:
         opt = RiemannianSGD(emb.xs, lr=0.001, momentum=0.9, max_grad_norm=100)
     obj = QuotientLoss() if loss_name == 'quotient' else StressLoss()
-    tr = PairTrainer(emb, opt, obj, max_hops_sq=64.0, process_group=pg)
+    if sharded:
+        tr = ShardedPairTrainer(emb, opt, obj, max_hops_sq=64.0, process_group=pg)
+        assert emb.xs[0].shape[0] == 0 and tr.x.shape[0] == n_nodes // dist.get_world_size(pg)
+    else:
+        tr = PairTrainer(emb, opt, obj, max_hops_sq=64.0, process_group=pg)
     parts = [shard_pairs(n_nodes, P, r) for r in ranks]
     I, J, H = (torch.cat([p[k] for p in parts]).to(dev) for k in range(3))
-    losses, traj = [], [emb.xs[0].detach().clone()]
+    current = (lambda: tr.gather().clone()) if sharded else (lambda: emb.xs[0].detach().clone())
+    losses, traj = [], [current()]
     for s in range(steps):
         losses.append(float(tr.step(I, J, H, epoch=s + 1).item()))
-        traj.append(emb.xs[0].detach().clone())
+        traj.append(current())
     tr.traj = traj
-    return emb.xs[0].detach().clone(), losses, tr
+    return traj[-1].clone(), losses, tr
 
 
 def main():
@@ -115,6 +122,14 @@ def main():
         msg = f'[rank {rank}] {kind} {dtype} {opt_name} {loss_name}: peer={used_peer} replicas_identical={same} ' \
               f'peer-vs-nccl x {d_pn:.2e} ({k_pn} kinked rows) loss {d_l:.2e}'
         ok = used_peer and same and d_pn < tol and k_pn <= max_kinked and d_l < tol
+        if kind == 'spd4' and world & (world - 1) == 0:  # row-sharded embeddings against the replicated peer run
+            os.environ['GM_PEER_UPDATE'] = '1'
+            x_sh, l_sh, tr3 = run(kind, dtype, opt_name, n_nodes, P, steps, dev, pg, [rank], loss_name, sharded=True)
+            d_sh, k_sh = row_diff(x_sh, x_peer, tol)
+            d_lsh = max(abs(a - b) / abs(b) for a, b in zip(l_sh, l_peer))
+            msg += f' | sharded-vs-peer x {d_sh:.2e} ({k_sh} kinked rows) loss {d_lsh:.2e}'
+            ok = ok and d_sh < tol and k_sh <= max_kinked and d_lsh < tol
+            tr3.peer.close()
         if rank == 0:
             x_one, l_one, tr1 = run(kind, dtype, opt_name, n_nodes, P, steps, dev, None, list(range(world)), loss_name)
             d_p1, k_p1 = row_diff(x_peer, x_one, tol)

@@ -173,3 +173,35 @@ def test_custom_ops_are_registered_and_have_no_cpu_kernel():
     with pytest.raises(NotImplementedError):
         ns.bfs_levels(torch.zeros(3, dtype=torch.int32), torch.zeros(2, dtype=torch.int32),
                       torch.zeros(1, dtype=torch.int32))
+
+
+def test_cyclic_row_shards_round_trip():
+    """graphembed.parallel.cyclic_shard / cyclic_unshard: rank r of `world` holds rows r, r + world, ... (the ownership
+    rule of gm_row_shards_t: global row v = row v // world of shard v % world)."""
+    import torch
+    from graphembed.parallel import cyclic_shard, cyclic_unshard
+    x = torch.arange(22 * 3, dtype=torch.float64).reshape(22, 3)
+    for world in (1, 2, 4, 8):
+        shards = [cyclic_shard(x, r, world) for r in range(world)]
+        for r, s in enumerate(shards):
+            assert s.is_contiguous()
+            for k in range(s.shape[0]):
+                v = k * world + r
+                assert torch.equal(s[k], x[v]) and v % world == r and v // world == k
+        assert torch.equal(cyclic_unshard(shards), x)
+
+
+def test_window_order_groups_by_target_window():
+    import torch
+    from graphembed.engine import window_order
+    g = torch.Generator().manual_seed(0)
+    n, P, W = 1000, 5000, 4
+    j = torch.randint(n, (P,), generator=g, dtype=torch.int32)
+    packed = j | (torch.randint(1, 9, (P,), generator=g, dtype=torch.int32) << 24)
+    order = window_order(packed, n, W)
+    assert torch.equal(order, window_order(j, n, W))  # a packed hop count is ignored
+    w = (j[order].long() * W) // n
+    assert bool((w[1:] >= w[:-1]).all())
+    for k in range(W):  # stable: original order inside a window
+        pos = order[w == k]
+        assert bool((pos[1:] > pos[:-1]).all())

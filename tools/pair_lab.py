@@ -42,7 +42,7 @@ def make(path, nodes, log2_pairs, trained_steps):
     print('workload written:', path)
 
 
-def run(path, iters, which):
+def run(path, iters, which, sort_j=0):
     from graphembed import _lib as L, _ops
     from graphembed.manifolds import SymmetricPositiveDefinite
     dev = torch.device('cuda', 0)
@@ -51,6 +51,12 @@ def run(path, iters, which):
     man = SymmetricPositiveDefinite(4)
     Is = [t.to(dev) for t in wl['I']]
     Js = [t.to(dev) for t in wl['JP']]
+    if sort_j:  # order every group of `sort_j` consecutive pairs (one source's pairs, or a slice of them) by target row
+        def by_target(jp):
+            g = jp.view(-1, sort_j)
+            order = (g & 0x00ffffff).argsort(dim=1)
+            return g.gather(1, order).reshape(-1).contiguous()
+        Js = [by_target(j) for j in Js]
     tg = _ops.TargetSpec.hops_packed(wl['max_sq'])
     spec = _ops.LossSpec(L.GM_LOSS_QUOTIENT, True, True, alpha=1.0, eps=0.5)
     grad = torch.zeros_like(x)
@@ -68,7 +74,7 @@ def run(path, iters, which):
         if k >= 3:
             times.append(e0.elapsed_time(e1))
     env = {k: v for k, v in os.environ.items() if k.startswith('GM_')}
-    print(json.dumps({'env': env, 'points': which, 'ms_mean': sum(times) / len(times), 'ms_min': min(times),
+    print(json.dumps({'env': env, 'points': which, 'sort_j': sort_j, 'ms_mean': sum(times) / len(times), 'ms_min': min(times),
                       'loss': acc[0].item(), 'sum_ld2': acc[1].item(), 'grad_abs_sum': grad.double().abs().sum().item(),
                       'grad_sq': grad.double().pow(2).sum().item(), 'finite': bool(torch.isfinite(grad).all())}))
 
@@ -82,8 +88,9 @@ if __name__ == '__main__':
     ap.add_argument('--trained-steps', type=int, default=30)
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--points', default='x0', choices=['x0', 'x1'])
+    ap.add_argument('--sort-j', type=int, default=0, help='sort the targets inside every group of this many pairs')
     a = ap.parse_args()
     if a.make:
         make(a.make, a.nodes, a.pairs_log2, a.trained_steps)
     else:
-        run(a.run, a.iters, a.points)
+        run(a.run, a.iters, a.points, a.sort_j)
