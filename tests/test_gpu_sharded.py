@@ -19,7 +19,7 @@ def _shards(t, world):
 
 
 @pytest.mark.parametrize('n,dtype,world', [(4, torch.float32, 1), (4, torch.float32, 2), (4, torch.float32, 8),
-                                           (3, torch.float64, 4), (6, torch.float32, 4), (2, torch.float64, 2)])
+                                           (3, torch.float64, 4), (5, torch.float32, 4), (4, torch.float64, 2)])
 def test_sharded_launch_is_the_unsharded_sum(n, dtype, world):
     from graphembed import _ops, _lib as L
     from graphembed.engine import pack_hops
@@ -102,6 +102,11 @@ def test_sharded_launch_validation():
     xl = lor.rand(64, out=torch.empty(0, device=DEV, dtype=torch.float32)).contiguous()
     with pytest.raises(RuntimeError, match='UNSUPPORTED'):  # vector manifolds: not built
         _ops.pairs_loss_fused_sharded(lor.spec, [xl.data_ptr()], [torch.zeros_like(xl).data_ptr()], torch.float32, DEV,
+                                      pairs, tg, spec, 1.0, acc)
+    big = SymmetricPositiveDefinite(6)  # rows too large for the streaming kernel's staging: declined, not mis-run
+    xb = big.rand(64, out=torch.empty(0, device=DEV, dtype=torch.float32)).contiguous()
+    with pytest.raises(RuntimeError, match='UNSUPPORTED'):
+        _ops.pairs_loss_fused_sharded(big.spec, [xb.data_ptr()], [torch.zeros_like(xb).data_ptr()], torch.float32, DEV,
                                       pairs, tg, spec, 1.0, acc)
     with pytest.raises(RuntimeError, match='EINVAL'):  # node-batch enumeration is not a sharded mode
         _ops.pairs_loss_fused_sharded(man.spec, [x.data_ptr()], [g.data_ptr()], torch.float32, DEV, _ops.PairSet.triu(16, device=DEV),
