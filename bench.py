@@ -256,8 +256,10 @@ def cpu_step_rate(log2_pairs, steps, warmup, seed=0, device='cpu'):
     """The reference's implementation of the step (oracle port: the same torch / LAPACK calls) on a bounded sample.
     device='cpu': the host cores (the reference arm).  device='cuda': the same torch-op path on the same B200 -- the
     "second comparator" of SURVEY 8(d): what the reference's own PyTorch code does when its tensors live on the GPU
-    (run.py:33-35), except that torch.linalg.eigh stays on the device instead of round-tripping through the host as
-    linalg/torch_batch.py:94-135 does (cpu_offload=True), which only flatters the comparator."""
+    (run.py:33-35): every op on the device except the symmetric eigendecomposition, which the reference's wrapper
+    round-trips through the host (linalg/torch_batch.py:94-135, cpu_offload=True by default) -- reproduced here as is.
+    (Keeping eigh on the device is not an option on this stack anyway: torch 2.11's batched cuSOLVER syevBatched path
+    rejects a 2^17 x 4 x 4 fp32 batch with CUSOLVER_STATUS_INVALID_VALUE.)"""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import manifolds_oracle as O
     cores = os.cpu_count() or 1
@@ -266,6 +268,9 @@ def cpu_step_rate(log2_pairs, steps, warmup, seed=0, device='cpu'):
     n = max(64, P // 8)  # same pairs-per-node ratio as the full workload (2^24 pairs / 2M nodes)
     gen = torch.Generator().manual_seed(seed)
     orc = O.SpdOracle(4)
+    eigh_saved = O._eigh
+    if device != 'cpu':  # tb.symeig's cpu_offload=True: eigh on the host, results back on the device (differentiable)
+        O._eigh = lambda m: tuple(r.to(m.device) for r in torch.linalg.eigh(m.cpu(), UPLO='U'))
     x = orc.rand(n, ir=0.1, dtype=torch.float32, generator=gen).to(device)
     I = torch.randint(n, (P,), generator=gen).to(device)
     J = ((I.cpu() + 1 + torch.randint(n - 1, (P,), generator=gen)) % n).to(device)
@@ -290,6 +295,7 @@ def cpu_step_rate(log2_pairs, steps, warmup, seed=0, device='cpu'):
         dt = time.perf_counter() - t0
         if k >= warmup:
             times.append(dt)
+    O._eigh = eigh_saved
     med = float(np.median(times))
     return P / med, med, cores, f'2^{log2_pairs} pairs over {n} points per step (pairs:points = 8:1 as the full workload), ' \
                                 f'fwd+bwd+RAdam step, median of {steps}'
@@ -802,8 +808,10 @@ def main():
                 rate_g, med_g, _, sample_g = cpu_step_rate(args.cpu_pairs_log2, 3, 1, device='cuda')
                 line['cpu_baseline']['torch_ops_on_this_gpu'] = {
                     'value': rate_g, 'unit': UNIT, 'sample': sample_g,
-                    'what': "the reference's PyTorch-op implementation (oracle port: batched torch.linalg.cholesky / "
-                            'eigh, autograd, index_put_ scatter) with every tensor on the B200'}
+                    'what': "the reference's PyTorch-op implementation (oracle port: batched torch.linalg.cholesky, "
+                            'autograd, index_put_ scatter) with every tensor on the B200 and, as the reference does '
+                            '(linalg/torch_batch.py:94-135 cpu_offload=True), the batched eigh round-tripped through '
+                            'the host'}
             except Exception as e:  # noqa: BLE001 -- a comparator must not take the bench line down
                 line['cpu_baseline']['torch_ops_on_this_gpu'] = {'unavailable': repr(e)[:200]}
     if world == 1 and not args.no_secondary:
