@@ -350,6 +350,16 @@ int gm_pairs_loss_fused_sharded(const gm_manifold_t* man, const gm_row_shards_t*
  * Phase 0 additionally sums acc[r][0..n_acc) over the ranks into acc_out. */
 int gm_peer_barrier(const gm_peers_t* peers, int32_t phase, gm_stream_t stream);
 
+/* ---- deterministic gradient accumulation ------------------------------------------------------- */
+/* out[dst[c]] (row of E elements; dst == NULL: row c) = sum, left to right, of src[order[k]] (order == NULL: row k) for
+ * chunk_start[c] <= k < chunk_end[c].  Plain stores, no atomics: bit-reproducible.  The autograd scatter it can stand
+ * in for is index_put_(accumulate=True) behind x[m[0]], x[m[1]] (manifolds/base.py:62-63), which adds in whatever
+ * order the device schedules.  graphembed.engine.PairTrainer(deterministic=True) builds a step from per-pair gradient
+ * rows (gm_pairs_grad, GM_PAIRS_ELEMENTWISE) and two calls of this (fixed-size chunks of each row's sorted incidence
+ * list, then the chunk sums of each row). */
+int gm_segment_sum(int32_t dtype, int32_t E, const void* src, const int64_t* order, const int64_t* chunk_start,
+                   const int64_t* chunk_end, const int64_t* dst, int64_t n_chunks, void* out, gm_stream_t stream);
+
 /* ---- per-point manifold operations (Manifold API, manifolds/base.py:7-81) ----------------------------------- */
 enum gm_point_op {
   GM_OP_EXP = 0,         /* out = exp_x(u)                      */

@@ -118,6 +118,7 @@ _PROTOTYPES = {
                                                    ctypes.POINTER(Pairs), ctypes.POINTER(Targets), ctypes.POINTER(Loss),
                                                    _dbl, _vp, _vp, _vp]),
     'gm_peer_barrier': (ctypes.c_int, [ctypes.POINTER(Peers), _i32, _vp]),
+    'gm_segment_sum': (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'gm_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     'gm_peer_free': (ctypes.c_int, [_vp]),
     'gm_peer_export': (ctypes.c_int, [_vp, ctypes.c_char_p]),

@@ -279,6 +279,50 @@ def peer_barrier(table, phase, device):
     L.check(rc, 'gm_peer_barrier')
 
 
+@_no_function_modes
+def segment_sum(src, chunk_start, chunk_end, out, order=None, dst=None):
+    """gm_segment_sum: out[dst[c]] = sum (left to right) of src[order[k]] for chunk_start[c] <= k < chunk_end[c]; rows of
+    E = src.shape[1:].numel() elements, int64 index tensors, plain stores (bit-reproducible)."""
+    L.require_cuda(src, chunk_start, chunk_end, out, order, dst)
+    src = _prep(src)
+    if out.dtype != src.dtype or not out.is_contiguous():
+        raise RuntimeError('segment_sum: out must be a contiguous tensor of the dtype of src')
+    for t in (chunk_start, chunk_end, order, dst):
+        if t is not None and (t.dtype != torch.int64 or not t.is_contiguous()):
+            raise RuntimeError('segment_sum: index tensors must be contiguous int64')
+    E = 1
+    for d in src.shape[1:]:
+        E *= d
+    n = chunk_start.numel()
+    if chunk_end.numel() != n or (dst is not None and dst.numel() != n):
+        raise ValueError('segment_sum: chunk_start, chunk_end and dst must have one entry per chunk')
+    with torch.cuda.device(src.device):
+        rc = L.lib().gm_segment_sum(L.dtype_code(src.dtype), E, L.ptr(src), L.ptr(order), L.ptr(chunk_start),
+                                    L.ptr(chunk_end), L.ptr(dst), n, L.ptr(out), L.stream_ptr(src.device))
+    L.check(rc, 'gm_segment_sum')
+    return out
+
+
+def scatter_add_rows_deterministic(rows, index, out, chunk=128):
+    """out[index[k]] += rows[k] for all k, as a FIXED-ORDER sum (out must be zero on entry: rows of `out` that receive
+    something are overwritten with their sum, the others left alone).  Entries of a destination row are taken in
+    ascending k (stable sort), in chunks of `chunk` entries (level 1), then the chunk sums in order (level 2)."""
+    index = index.reshape(-1).long()
+    order = torch.sort(index, stable=True).indices.contiguous()
+    dest, counts = torch.unique_consecutive(index[order], return_counts=True)
+    seg_start = torch.cumsum(counts, 0) - counts
+    n_ch = (counts + (chunk - 1)) // chunk
+    ch_first = torch.cumsum(n_ch, 0) - n_ch              # first chunk of every segment
+    seg_of = torch.repeat_interleave(torch.arange(dest.numel(), device=index.device), n_ch)
+    within = torch.arange(seg_of.numel(), device=index.device) - ch_first[seg_of]
+    c_start = (seg_start[seg_of] + within * chunk).contiguous()
+    c_end = torch.minimum(c_start + chunk, (seg_start + counts)[seg_of]).contiguous()
+    partial = torch.empty((seg_of.numel(),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    segment_sum(rows, c_start, c_end, partial, order=order)
+    segment_sum(partial, ch_first.contiguous(), (ch_first + n_ch).contiguous(), out, dst=dest.contiguous())
+    return out
+
+
 FUSABLE_VECTOR_KINDS = (L.GM_LORENTZ, L.GM_SPHERE, L.GM_EUCLIDEAN)
 MAX_FUSED_VECTOR_FACTORS = 3
 

@@ -73,9 +73,11 @@ class PairTrainer:
         (`self.peer` is then the PeerArena; GM_PEER_UPDATE=0 forces the NCCL collectives).
     """
 
-    def __init__(self, embedding, optimizer, objective, max_hops_sq, alpha=1.0, process_group=None, owner_update=None):
+    def __init__(self, embedding, optimizer, objective, max_hops_sq, alpha=1.0, process_group=None, owner_update=None,
+                 deterministic=False):
         if embedding.n_components != 1:
             raise ValueError('PairTrainer drives a single-manifold embedding; use BatchedObjective for products')
+        self.deterministic = bool(deterministic)
         self.emb, self.opt, self.obj = embedding, optimizer, objective
         self.max_hops_sq, self.alpha, self.pg = float(max_hops_sq), alpha, process_group
         self.x = embedding.xs[0]
@@ -173,11 +175,42 @@ class PairTrainer:
             return self._queue_loss_read()
         return loss.item()
 
+    def _pairs_deterministic(self, pairs, targets, loss_spec, sp):
+        """The fused kernel's job with a fixed summation order: grad (zero on entry) and acc are filled."""
+        if pairs.mode != L.GM_PAIRS_LIST:
+            raise ValueError('deterministic accumulation takes explicit pair lists')
+        x = self.x.detach()
+        I = pairs.idx_i
+        J = pairs.idx_j
+        if targets.mode == L.GM_TGT_HOPS_PACKED:  # split the packed word: row id | hop count << 24
+            hops = ((J >> 24) & 0xff).to(torch.uint8)
+            J = (J & 0x00ffffff).contiguous()
+            targets = _ops.TargetSpec.hops(hops, targets.max_sq)
+        plain = _ops.PairSet.from_lists(I, J, x.device)
+        d2 = _ops.pairs_dist2(self.man.spec, x, x, plain)
+        acc, g = _ops.product_loss([d2], [sp], targets, loss_spec)
+        self.acc.copy_(acc[:2])
+        xi, xj = x.index_select(0, I.long()), x.index_select(0, J.long())
+        gi, gj = torch.empty_like(xi), torch.empty_like(xj)
+        _ops.pairs_grad(self.man.spec, xi, xj, _ops.PairSet.elementwise(plain.P), g, gi, gj, coef=sp)
+        _ops.scatter_add_rows_deterministic(torch.cat([gi, gj]), torch.cat([I.long(), J.long()]), self.grad)
+
     def _step_pairs(self, pairs, targets, epoch):
         loss_spec = self.obj.loss_spec(epoch=epoch, alpha=self.alpha)
         if not self._grad_is_clean:
             self.grad.zero_()
         self.acc.zero_()
+        if self.deterministic:
+            self._pairs_deterministic(pairs, targets, loss_spec, _softplus_value(self.emb.scales[0]))
+            if self.peer is not None:
+                self.opt.step()
+                return self.peer.acc_out[0]
+            if self.shards is not None or (self.pg is not None and torch.distributed.get_world_size(self.pg) > 1):
+                raise RuntimeError('deterministic accumulation: single GPU, or the peer-memory owner update (which '
+                                   'sums the ranks in rank order)')
+            self.opt.step()
+            self._grad_is_clean = self._fold_zero_grad
+            return self.acc[0]
         # softplus(scale) is re-read every step (cached on the parameter until somebody steps it or loads a snapshot);
         # the trainer itself does not train the scale: acc[1] (sum l' d2) is there for a caller who does
         sp = _softplus_value(self.emb.scales[0])
