@@ -74,6 +74,12 @@ def parse():
     ap.add_argument('--lists3', action='store_true', help='--e2e lists: upload 3-byte pair words (pack_hops3) instead of '
                     '4-byte ones; measured on one B200 it is NOT faster (1.339 vs 1.31 ms per step: the step is not PCIe '
                     'bound at 4 B/pair and the extra expansion kernel costs 0.03 ms)')
+    ap.add_argument('--lists-format', default='auto', choices=['auto', '2', '4'], help='--e2e lists: bytes per pair on '
+                    'the host->device link.  4: int32 j | hops << 24.  2: the gap format (pack_hops2: every source\'s '
+                    'targets sorted by row, 13-bit gap + 3 bits of hop count, expanded on the device by '
+                    'gm_unpack_pairs2).  auto: 4 on one GPU (measured: the step is then bound by the device, 1.324 ms '
+                    'with 4-byte words vs 1.354 ms with the 64 us expansion kernel of the 2-byte ones), 2 when several '
+                    'GPUs share the host\'s links')
     ap.add_argument('--layout', default='replicated', choices=['replicated', 'sharded'], help='N>1: `replicated` = every '
                     'rank holds the whole point table, partial gradients exchanged by the peer-memory owner update after '
                     'the pair kernel; `sharded` = ROW-SHARDED embeddings (engine.ShardedPairTrainer): every rank holds '
@@ -120,7 +126,7 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, 
     row, source) order (graphembed.engine.window_order) -- the groups are then the (window, source) runs -- for a launch
     with gm_pairs_t.segments = windows."""
     from graphembed.data import bfs_levels, edges_to_csr
-    from graphembed.engine import pack_hops, pack_hops3, window_order
+    from graphembed.engine import pack_hops, pack_hops2, pack_hops3, window_order
     from graphembed import _lib as L
     P = 1 << log2_pairs
     per_src = max(1, P // N_SOURCES)
@@ -159,9 +165,11 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, 
         else:
             src_groups = src
         three = n_nodes <= (1 << 21) and int(hops_h.max()) <= 8  # (j, hops - 1) fit 21 + 3 bits: 3 bytes per pair
+        two = pack_hops2(offsets, J, hops_h)  # every group's targets sorted by row, 2-byte gap words (None: no fit)
         batches.append((I.pin_memory(), J.pin_memory(), hops_h.pin_memory(), src_groups.contiguous().pin_memory(),
                         offsets.pin_memory(), pack_hops(J, hops_h).pin_memory(),
-                        pack_hops3(J, hops_h).pin_memory() if three else None))
+                        pack_hops3(J, hops_h).pin_memory() if three else None,
+                        None if two is None else (two[0].pin_memory(), two[1].pin_memory())))
         if keep_levels:
             kept.append(levels)  # (n_src, N) uint8, resident: the hop counts of this batch's landmark sources
         del levels
@@ -709,19 +717,25 @@ def main():
         # source-grouped upload (sources, offsets, j, hops): 4-5 B/pair over PCIe; the next batch is uploaded on a
         # second stream while this one computes; every step ends with a device->host read of the loss
         use3 = args.lists3 and not args.unpacked and all(b[6] is not None for b in batches)
+        use2 = ((args.lists_format == '2' or (args.lists_format == 'auto' and world > 1)) and not args.lists3
+                and not args.unpacked and seg == 0 and all(b[7] is not None for b in batches))
 
         def grouped(b):
+            if use2:
+                return (b[3], b[4], b[7][0], None, b[7][1])
             if use3:
-                return (b[3], b[4], b[6], None)
-            return (b[3], b[4], b[1], b[2]) if args.unpacked else (b[3], b[4], b[5], None)
+                return (b[3], b[4], b[6], None, None)
+            return (b[3], b[4], b[1], b[2], None) if args.unpacked else (b[3], b[4], b[5], None, None)
 
         def e2e_step(k):
-            return trainer.step_host_grouped(*grouped(batches[k % nb]), epoch=1,
-                                             next_batch=grouped(batches[(k + 1) % nb]), defer_loss=True,
-                                             segments=seg)
+            cur = grouped(batches[k % nb])
+            return trainer.step_host_grouped(*cur[:4], epoch=1, next_batch=grouped(batches[(k + 1) % nb]),
+                                             defer_loss=True, segments=seg, bases=cur[4])
         h2d_bytes = sum(t.numel() * t.element_size() for t in grouped(batches[0]) if t is not None)
         e2e_api = ('graphembed.engine.PairTrainer.step_host_grouped (pinned host int32 sources, int64 offsets, '
                    + ('int32 j, uint8 hops' if args.unpacked else
+                      '2-byte words (every source\'s targets sorted by row: 13-bit gap | (hops - 1) << 13, + one int32 '
+                      'base per source), expanded on the device by gm_unpack_pairs2' if use2 else
                       '3-byte words j | (hops - 1) << 21, expanded on the device' if use3 else 'int32 j | hops << 24')
                    + '; per rank); next batch '
                    'uploaded on a second stream, loss read back through pinned memory one step late')

@@ -417,6 +417,18 @@ int gm_expand_groups(const int32_t* group_row, const int64_t* offsets, int32_t G
  * (readable up to the next multiple of 4); out: 16-byte aligned, P words. */
 int gm_unpack_pairs3(const void* src3, int64_t P, int32_t* out, gm_stream_t stream);
 
+/* Upload format of source-grouped sampled pair batches, 2 bytes per pair.  A sampler that draws its targets per BFS
+ * source can hand every source's targets over SORTED by row; consecutive targets of a group are then close (2^24 pairs
+ * over 1024 sources and 2 M rows: mean gap 122 rows), and a pair fits a 16-bit word: bits 0-12 = j_k - j_{k-1}
+ * (0 .. 8191; j_{-1} := base[g], so the first word of a group is usually 0), bits 13-15 = hop count - 1
+ * (1 <= hops <= 8).  A batch with a larger gap or hop count is not representable -- the host packer
+ * (graphembed.engine.pack_hops2) then declines and the caller uploads the 4-byte words.  offsets (G + 1 entries) are the
+ * same group offsets gm_expand_groups takes.  Expands to the 4-byte words of GM_TGT_HOPS_PACKED,
+ * out[k] = (hops << 24) | j_k, with a segmented prefix sum per group (one block per group).  Half the bytes of the
+ * 4-byte form over PCIe: 33.5 MB instead of 67 MB per 2^24-pair step. */
+int gm_unpack_pairs2(const void* words, const int32_t* base, const int64_t* offsets, int32_t G, int32_t* out,
+                     gm_stream_t stream);
+
 /* ---- ranking metrics (evaluation) ------------------------------------------------------------------------------
  * FastPrecision on the GPU (graphembed/pyx/impl/precision.cpp:249-291 mean average precision, :321-446 per-layer F1
  * scores; bound to Python in graphembed/pyx/precision.pyx:48-127).  For every shortest-path-tree root u in

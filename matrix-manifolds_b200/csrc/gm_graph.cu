@@ -640,6 +640,52 @@ __global__ void unpack_pairs3_kernel(const unsigned* __restrict__ src, long long
   }
 }
 
+// 2-byte pair words (gm_unpack_pairs2): group g's targets arrive sorted, word k = (j_k - j_{k-1}) | (hops - 1) << 13 with
+// j_{-1} := base[g].  One block per group walks it in tiles of 256 x 8 words: per-thread sum of 8 deltas, block-wide
+// exclusive scan (shuffles + one shared-memory hop), running carry across tiles; out[k] = j_k | hops << 24.
+__global__ void __launch_bounds__(256)
+unpack_pairs2_kernel(const unsigned short* __restrict__ words, const int* __restrict__ base,
+                     const long long* __restrict__ offsets, int* __restrict__ out) {
+  __shared__ unsigned warp_tot[8];
+  __shared__ unsigned tile_tot;
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long lo = offsets[g], hi = offsets[g + 1];
+  unsigned carry = (unsigned)base[g];
+  for (long long t0 = lo; t0 < hi; t0 += 256 * 8) {
+    const long long k0 = t0 + (long long)tid * 8;
+    unsigned w[8];
+    unsigned sum = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      w[e] = (k0 + e < hi) ? (unsigned)words[k0 + e] : 0u;
+      sum += w[e] & 0x1FFFu;
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    unsigned before = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q < wid) before += warp_tot[q];
+    }
+    if (tid == 255) tile_tot = before + incl;
+    unsigned j = carry + before + incl - sum;  // row id reached before this thread's first word
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      j += w[e] & 0x1FFFu;
+      if (k0 + e < hi) out[k0 + e] = (int)(j | (((w[e] >> 13) + 1u) << 24));
+    }
+    __syncthreads();
+    carry += tile_tot;
+    __syncthreads();
+  }
+}
+
 template <typename L>
 __global__ void gather_levels_kernel(const L* __restrict__ levels, int N, const int* __restrict__ slot,
                                      const int* __restrict__ col, long long P, L* __restrict__ out) {
@@ -750,6 +796,18 @@ int gm_unpack_pairs3(const void* src3, int64_t P, int32_t* out, gm_stream_t stre
   long long blocks = ((P + 3) / 4 + 255) / 256;
   if (blocks > 0x7fffffffLL) return GM_EINVAL;
   unpack_pairs3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned*)src3, P, out);
+  note_launch();
+  return check_launch();
+}
+
+int gm_unpack_pairs2(const void* words, const int32_t* base, const int64_t* offsets, int32_t G, int32_t* out,
+                     gm_stream_t stream) {
+  if (G < 0) return GM_EINVAL;
+  if (G == 0) return GM_OK;
+  if (!words || !base || !offsets || !out) return GM_ENULL;
+  if (reinterpret_cast<size_t>(words) & 1) return GM_EINVAL;
+  unpack_pairs2_kernel<<<(unsigned)G, 256, 0, (cudaStream_t)stream>>>((const unsigned short*)words, base,
+                                                                    (const long long*)offsets, out);
   note_launch();
   return check_launch();
 }

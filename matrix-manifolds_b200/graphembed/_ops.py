@@ -548,6 +548,20 @@ def dist2_indexed(spec, x, pairs, c=None, wmin=None):
     return _Dist2Indexed.apply(x, spec, pairs, c, wmin)
 
 
+@_no_function_modes
+def unpack_pairs2(words, base, offsets, out):
+    """gm_unpack_pairs2: 2-byte delta words (engine.pack_hops2) of a source-grouped batch -> out[k] = j | hops << 24.
+    words int16 (P,), base int32 (G,), offsets int64 (G + 1,), out int32 (>= P,), all on one CUDA device."""
+    L.require_cuda(words, base, offsets, out)
+    G = base.numel()
+    if (words.dtype != torch.int16 or base.dtype != torch.int32 or offsets.dtype != torch.int64
+            or out.dtype != torch.int32 or offsets.numel() != G + 1 or out.numel() < words.numel()):
+        raise ValueError('unpack_pairs2: int16 words, int32 base (G,), int64 offsets (G + 1,), int32 output of P words')
+    with torch.cuda.device(out.device):
+        rc = L.lib().gm_unpack_pairs2(L.ptr(words), L.ptr(base), L.ptr(offsets), G, L.ptr(out), L.stream_ptr(out.device))
+    L.check(rc, 'gm_unpack_pairs2')
+
+
 def unpack_pairs3(src3, P, out):
     """3-byte pair words (engine.pack_hops3) -> out[k] = (hops << 24) | j, the GM_TGT_HOPS_PACKED form (all CUDA)."""
     L.require_cuda(src3, out)

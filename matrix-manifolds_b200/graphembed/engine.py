@@ -55,6 +55,41 @@ def pack_hops3(idx_j, hops):
     return b.contiguous()
 
 
+def pack_hops2(offsets, idx_j, hops):
+    """Source-grouped batch -> the TWO-byte-per-pair upload format of gm_unpack_pairs2.  offsets int64 (G + 1,): group
+    g is pairs offsets[g] <= k < offsets[g + 1]; idx_j int32 (P,), hops uint8 (P,).  Every group's targets are put in
+    ascending row order (the returned permutation `order` says how: pair k of the packed batch is pair order[k] of the
+    input) and stored as gaps: word k = (j_k - j_{k-1}) | (hops_k - 1) << 13, the first gap of a group taken from
+    bases[g] = the group's smallest row.  Returns (words int16 (P,), bases int32 (G,), order int64 (P,)), or None when
+    the batch does not fit (a gap above 8191 rows or a hop count outside 1..8): the caller then uploads 4-byte words."""
+    if idx_j.dtype != torch.int32 or hops.dtype != torch.uint8 or offsets.dtype != torch.int64:
+        raise ValueError('pack_hops2: int64 offsets, int32 indices, uint8 hop counts')
+    P, G = idx_j.numel(), offsets.numel() - 1
+    if P == 0:
+        return torch.empty(0, dtype=torch.int16), torch.zeros(G, dtype=torch.int32), torch.empty(0, dtype=torch.int64)
+    if int(hops.min()) < 1 or int(hops.max()) > 8 or int(idx_j.min()) < 0:
+        return None
+    counts = offsets[1:] - offsets[:-1]
+    group = torch.repeat_interleave(torch.arange(G, dtype=torch.int64), counts)
+    # sort by (group, row): one stable sort of the rows, then a stable sort of the groups
+    o1 = torch.sort(idx_j.long(), stable=True).indices
+    order = o1[torch.sort(group[o1], stable=True).indices]
+    j = idx_j.long()[order]
+    first = torch.zeros(P, dtype=torch.bool)
+    nonempty = counts > 0
+    first[offsets[:-1][nonempty]] = True
+    gap = torch.zeros(P, dtype=torch.int64)
+    gap[1:] = j[1:] - j[:-1]
+    gap[first] = 0
+    if int(gap.max()) > 0x1FFF:
+        return None
+    bases = torch.zeros(G, dtype=torch.int32)
+    bases[nonempty] = j[offsets[:-1][nonempty]].to(torch.int32)
+    words = gap | ((hops.long()[order] - 1) << 13)
+    words = torch.where(words >= 0x8000, words - 0x10000, words).to(torch.int16)  # the 16 bits, as torch's signed type
+    return words.contiguous(), bases.contiguous(), order
+
+
 class PairTrainer:
     """Drives (I, J, hops) pair batches through a single-manifold embedding.
 
@@ -313,7 +348,7 @@ class PairTrainer:
         return float(self._loss_host[s][0])
 
     def step_host_grouped(self, sources, offsets, idx_j, hops, epoch=1, next_batch=None, defer_loss=False,
-                          segments=0):
+                          segments=0, bases=None):
         """One step from PINNED host tensors in source-grouped (CSR-like) form, the natural output of a sampler that
         draws targets per BFS source: pairs offsets[g] <= k < offsets[g+1] are (sources[g], idx_j[k]) with hop count
         hops[k].  sources int32 (G,), offsets int64 (G+1,), idx_j int32 (P,), hops uint8/int16 (P,).  Uploads 5 bytes
@@ -322,18 +357,36 @@ class PairTrainer:
         `next_batch` = the next step's (sources, offsets, idx_j, hops), uploaded on a second stream meanwhile.
         defer_loss=True returns the loss of the previous deferred step instead of blocking on this one (its own loss
         is copied to pinned host memory asynchronously; `flush_loss()` returns the last one), so that the host can
-        enqueue step k+1 while the GPU runs step k."""
+        enqueue step k+1 while the GPU runs step k.
+        Two bytes per pair: idx_j = the int16 words of pack_hops2 (every group's targets sorted by row, stored as
+        gaps), hops=None, bases = its int32 (G,) vector; `next_batch` then carries the bases as a fifth entry."""
         packed3 = hops is None and idx_j.dtype == torch.uint8  # pack_hops3: 3 bytes per pair over PCIe
+        packed2 = hops is None and idx_j.dtype == torch.int16  # pack_hops2: 2 bytes per pair
+        if packed2 and bases is None:
+            raise ValueError('2-byte pair words need the bases vector of pack_hops2')
         P, G = (int(offsets[-1]) if packed3 else idx_j.numel()), sources.numel()
         packed = hops is None  # idx_j carries the hop counts (pack_hops / pack_hops3)
         self._ensure_staging(P, torch.uint8 if packed else hops.dtype, G)
         if packed3 and (getattr(self, '_staging3', None) is None or self._staging3[0].numel() < idx_j.numel()):
             self._staging3 = [torch.empty(idx_j.numel(), dtype=torch.uint8, device=self.x.device) for _ in range(2)]
+        if packed2 and (getattr(self, '_staging2', None) is None or self._staging2[0][0].numel() < P
+                        or self._staging2[0][1].numel() < G):
+            self._staging2 = [(torch.empty(P, dtype=torch.int16, device=self.x.device),
+                               torch.empty(max(G, 1), dtype=torch.int32, device=self.x.device)) for _ in range(2)]
         cur = torch.cuda.current_stream(self.x.device)
 
         def upload(slot, batch):
             di, dj, dh, ds, do = self._staging[slot]
-            s_, o_, j_, h_ = batch
+            s_, o_, j_, h_ = batch[:4]
+            if j_.dtype == torch.int16:  # 2-byte words + bases: staged raw, expanded on the device before the step
+                w2, b2 = self._staging2[slot]
+                if s_.numel() > ds.numel() or j_.numel() > w2.numel() or len(batch) < 5 or batch[4].numel() > b2.numel():
+                    raise ValueError('batch does not fit the staging buffers of the first batch of this call')
+                ds[:s_.numel()].copy_(s_, non_blocking=True)
+                do[:o_.numel()].copy_(o_, non_blocking=True)
+                w2[:j_.numel()].copy_(j_, non_blocking=True)
+                b2[:batch[4].numel()].copy_(batch[4], non_blocking=True)
+                return
             jcap = self._staging3[slot].numel() if j_.dtype == torch.uint8 else dj.numel()
             if s_.numel() > ds.numel() or j_.numel() > jcap or (h_ is not None and h_.dtype != dh.dtype):
                 raise ValueError('batch does not fit the staging buffers (more sources / pairs, or another hop dtype, '
@@ -352,7 +405,7 @@ class PairTrainer:
             cur.wait_event(ev)
         else:
             slot = self._slot
-            upload(slot, (sources, offsets, idx_j, hops))
+            upload(slot, (sources, offsets, idx_j, hops, bases))
         di, dj, dh, ds, do = self._staging[slot]
         self._pending = None
         if next_batch is not None:
@@ -367,6 +420,9 @@ class PairTrainer:
         _ops.expand_groups(ds[:G], do[:G + 1], di[:P])
         if packed3:
             _ops.unpack_pairs3(self._staging3[slot], P, dj)
+        if packed2:
+            w2, b2 = self._staging2[slot]
+            _ops.unpack_pairs2(w2[:P], b2[:G], do[:G + 1], dj)
         loss = self.step(di[:P], dj[:P], None if packed else dh[:P], epoch=epoch, segments=segments)
         if defer_loss:  # read this step's loss back asynchronously, hand out the previous step's
             return self._queue_loss_read()

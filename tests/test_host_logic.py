@@ -205,3 +205,26 @@ def test_window_order_groups_by_target_window():
     for k in range(W):  # stable: original order inside a window
         pos = order[w == k]
         assert bool((pos[1:] > pos[:-1]).all())
+
+
+def test_pack_hops2_round_trip_on_the_host():
+    """engine.pack_hops2: every group's targets sorted by row and stored as 13-bit gaps + 3 bits of hop count; decoding
+    the words as include/gm_kernels.h states the format gives back the sorted batch."""
+    import torch
+    from graphembed.engine import pack_hops2
+    g = torch.Generator().manual_seed(0)
+    offs = torch.tensor([0, 400, 400, 900, 1300, 2000], dtype=torch.int64)
+    J = torch.randint(20000, (2000,), generator=g, dtype=torch.int32)
+    H = torch.randint(1, 9, (2000,), generator=g, dtype=torch.uint8)
+    words, bases, order = pack_hops2(offs, J, H)
+    assert words.dtype == torch.int16 and bases.dtype == torch.int32 and words.numel() == 2000
+    wu = words.long() & 0xFFFF
+    for gi in range(5):
+        j = int(bases[gi])
+        for k in range(int(offs[gi]), int(offs[gi + 1])):
+            j += int(wu[k] & 0x1FFF)
+            assert j == int(J[order[k]]) and (int(wu[k]) >> 13) + 1 == int(H[order[k]])
+            assert int(offs[gi]) <= int(order[k]) < int(offs[gi + 1])
+    J2 = J.clone()
+    J2[0], J2[1:400] = 0, 19999
+    assert pack_hops2(offs, J2, H) is None  # a gap that does not fit 13 bits
