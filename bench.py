@@ -712,7 +712,10 @@ def main():
 
     # ---- end-to-end timing from pinned host buffers ----------------------------------------------------------------
     nb = len(batches)
-    e2e_mode = args.e2e if args.e2e != 'auto' else ('lists' if world <= 2 else 'sampled')
+    # auto: explicit lists at every GPU count -- 4-byte words on one GPU, the 2-byte gap words when several GPUs share the
+    # host (measured end to end, ms per step lists2 / sampled: 4 GPUs 1.556 / 1.722, 8 GPUs 1.740 / 1.778; 4-byte lists
+    # at 4 GPUs: 1.909)
+    e2e_mode = args.e2e if args.e2e != 'auto' else 'lists'
     if e2e_mode == 'lists':
         # source-grouped upload (sources, offsets, j, hops): 4-5 B/pair over PCIe; the next batch is uploaded on a
         # second stream while this one computes; every step ends with a device->host read of the loss
