@@ -205,7 +205,12 @@ template <> struct RawScalar<double> {
   __device__ __forceinline__ static double unpack(unsigned long long r) { return __longlong_as_double((long long)r); }
 };
 
-template <class Op, typename T, int KMODE, int MINB, int DEPTH>
+// SPEC = 1: the launch is known to be explicit int32 lists in window order (gm_pairs_t.segments > 1) with the hop count
+// packed into the top byte of idx_j and plain (not row-sharded) tables -- the BASELINE config 5 training step as
+// bench.py runs it.  Every mode test folds away at compile time and the walk position is carried as (segment, offset)
+// instead of being divided out: measured 0.957 vs 1.040 ms for the general instantiation on the same window-ordered
+// batch (profiles/r02_pair_kernel_ab.txt run 10); with resident rows the kernel is issue bound and these count.
+template <class Op, typename T, int KMODE, int MINB, int DEPTH, int SPEC = 0>
 __global__ void __launch_bounds__(128, MINB)
 spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __restrict__ xb,
                        const T* __restrict__ gout, T coef, T* __restrict__ ga, T* __restrict__ gb,
@@ -242,10 +247,16 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     k = (long long)s * ps.seg_len + in_seg;
     return in_seg < ps.seg_len && k < ps.P;
   };
-  const bool hopsP = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_PACKED;  // hop count in the top byte of idx_j
-  const bool hops8 = (KMODE == K_FUSED) && (tg.mode == GM_TGT_HOPS_U8 || hopsP);
-  const bool hops16 = (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_U16;
-  const bool rawj = hopsP || ps.mode == GM_PAIRS_SAMPLED;  // j arrives with a hop count in its top byte
+  [[maybe_unused]] auto locate_so = [&](int s, int o, long long& k) -> bool {  // SPEC: position given as (segment, offset)
+    if (s >= nseg) return false;
+    const long long in_seg = wbase + o;
+    k = (long long)s * ps.seg_len + in_seg;
+    return in_seg < ps.seg_len && k < ps.P;
+  };
+  const bool hopsP = SPEC ? true : (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_PACKED;  // hop count in the top byte of idx_j
+  const bool hops8 = SPEC ? true : (KMODE == K_FUSED) && (tg.mode == GM_TGT_HOPS_U8 || hopsP);
+  const bool hops16 = SPEC ? false : (KMODE == K_FUSED) && tg.mode == GM_TGT_HOPS_U16;
+  const bool rawj = SPEC ? true : hopsP || ps.mode == GM_PAIRS_SAMPLED;  // j arrives with a hop count in its top byte
   if (hops8) {
     for (int h = tid; h < 256; h += 128) hop_lut[h] = ((T)h * (T)h) / (T)tg.max_sq;
     __syncthreads();
@@ -256,7 +267,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   const row_t kNoRow = (row_t)-1;
   // Row-sharded tables (gm_row_shards_t, sh.log2w >= 0): global row v is row v >> log2w of rank (v & mask)'s shard --
   // local memory or a peer's, mapped over NVLink -- for the point gathers and the gradient reductions alike.
-  const bool sharded = sh.log2w >= 0;
+  const bool sharded = SPEC ? false : sh.log2w >= 0;
   auto xrow = [&](const T* base, row_t r) -> const T* {
     if (sharded) return (const T*)sh.x[(unsigned)r & sh.mask] + (size_t)((unsigned long long)r >> sh.log2w) * E;
     return base + (size_t)r * E;
@@ -276,7 +287,7 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
   unsigned hopn = 0;   // SAMPLED: hop count of pair q = D (load in flight since the previous iteration)
   GM_UNROLL for (int q = 0; q < D + 2; ++q) { ra[q] = kNoRow; rb[q] = kNoRow; v[q] = false; }
   GM_UNROLL for (int q = 0; q < D + 1; ++q) tgq[q] = 0;
-  const bool sampled = ps.mode == GM_PAIRS_SAMPLED;
+  const bool sampled = SPEC ? false : ps.mode == GM_PAIRS_SAMPLED;
   int stage = 0;
 
   auto fetch_scalar = [&](long long k, row_t ra, row_t rb) -> raw_t {
@@ -299,6 +310,11 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     }
   };
   auto load_rows = [&](long long k, row_t& ra, row_t& rb, unsigned& hop) {
+    if constexpr (SPEC != 0) {
+      ra = (row_t)((const int*)ps.idx_i)[k];
+      rb = (row_t)(unsigned)((const int*)ps.idx_j)[k];
+      return;
+    }
     long long a, b;
     if (sampled) ahead.rows_sampled(ps, k, a, b, hop);
     else ahead.rows(ps, k, a, b);
@@ -325,6 +341,9 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     v[D] = locate(32 * D, kq);
     if (v[D]) load_rows(kq, ra[D], rb[D], hopn);
   }
+  // SPEC: (segment, offset) of the walk position whose indices are loaded next, tc + 32 (D + 1)
+  [[maybe_unused]] int hs = SPEC ? (32 * (D + 1)) / (int)chunk : 0;
+  [[maybe_unused]] int ho = SPEC ? 32 * (D + 1) - hs * (int)chunk : 0;
 
   // ---- per-lane running state -------------------------------------------------------------------------------------
   double loss_v = 0.0, gd2_v = 0.0;
@@ -382,7 +401,13 @@ spd_pair_stream_kernel(Op op, PairSpec ps, const T* __restrict__ xa, const T* __
     cp_async_commit();
     ahead.advance(ps);
     long long kh = 0;
-    v[D + 1] = locate(tc + 32 * (D + 1), kh);
+    if constexpr (SPEC != 0) {
+      v[D + 1] = locate_so(hs, ho, kh);
+      ho += 32;
+      if (ho >= (int)chunk) { ho -= (int)chunk; ++hs; }
+    } else {
+      v[D + 1] = locate(tc + 32 * (D + 1), kh);
+    }
     ra[D + 1] = kNoRow; rb[D + 1] = kNoRow;
     unsigned hop_next = 0;
     if (v[D + 1]) load_rows(kh, ra[D + 1], rb[D + 1], hop_next);
@@ -480,7 +505,7 @@ static int launch_op(const Op& op, const PairArgs& a) {
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto launch_stream = [&](auto kern, const T* gout, T coef, T* out_d2, T scale, double* acc) -> int {
+    auto launch_stream = [&](auto kern, auto spec_kern, const T* gout, T coef, T* out_d2, T scale, double* acc) -> int {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Stage::BYTES);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, Stage::BYTES);
       if (occ < 1) occ = 1;
@@ -493,16 +518,30 @@ static int launch_op(const Op& op, const PairArgs& a) {
       ps.seg_len = (ps.P + ps.nseg - 1) / ps.nseg;
       long long chunk = ((ps.seg_len + warps - 1) / warps + 31) / 32 * 32;
       if (chunk * ps.nseg > 0x7fffffffLL) return GM_EINVAL;
+#ifndef GM_NO_SPEC
+      if constexpr (GM_N == 4 && sizeof(T) == 4 && Op::kCanPrep) {  // the window-ordered config 5 step: see SPEC
+        if (spec_kern && ps.nseg > 1 && !ps.idx64 && a.tg.mode == GM_TGT_HOPS_PACKED && a.sh.log2w < 0) {
+          cudaFuncSetAttribute(spec_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Stage::BYTES);
+          spec_kern<<<(unsigned)nb, threads, Stage::BYTES, a.stream>>>(op, ps, xa, xb, gout, coef, (T*)a.ga, (T*)a.gb,
+                                                                    out_d2, a.tg, a.lc, scale, acc, chunk, a.sh);
+          note_launch();
+          return check_launch();
+        }
+      }
+#endif
       kern<<<(unsigned)nb, threads, Stage::BYTES, a.stream>>>(op, ps, xa, xb, gout, coef, (T*)a.ga, (T*)a.gb, out_d2,
                                                              a.tg, a.lc, scale, acc, chunk, a.sh);
       note_launch();
       return check_launch();
     };
+    using kern_t = decltype(&spd_pair_stream_kernel<Op, T, K_FUSED, MINB, DEPTH>);
     if (a.kmode == K_BWD)
-      return launch_stream(spd_pair_stream_kernel<Op, T, K_BWD, MINB, DEPTH>, (const T*)a.gout, (T)a.coef, nullptr, (T)0,
-                           nullptr);
-    return launch_stream(spd_pair_stream_kernel<Op, T, K_FUSED, MINB, DEPTH>, nullptr, (T)0, (T*)a.out_d2, (T)a.scale_sp,
-                         a.acc);
+      return launch_stream(spd_pair_stream_kernel<Op, T, K_BWD, MINB, DEPTH>, (kern_t) nullptr, (const T*)a.gout,
+                           (T)a.coef, nullptr, (T)0, nullptr);
+    kern_t spec = nullptr;
+    if constexpr (GM_N == 4 && sizeof(T) == 4 && Op::kCanPrep) spec = spd_pair_stream_kernel<Op, T, K_FUSED, MINB, DEPTH, 1>;
+    return launch_stream(spd_pair_stream_kernel<Op, T, K_FUSED, MINB, DEPTH>, spec, nullptr, (T)0, (T*)a.out_d2,
+                         (T)a.scale_sp, a.acc);
   }
   if (a.sh.log2w >= 0) return GM_EUNSUPPORTED;  // row-sharded tables: the streaming (training) kernels only
   switch (a.kmode) {
