@@ -425,9 +425,10 @@ int gm_unpack_pairs3(const void* src3, int64_t P, int32_t* out, gm_stream_t stre
  * (graphembed.engine.pack_hops2) then declines and the caller uploads the 4-byte words.  offsets (G + 1 entries) are the
  * same group offsets gm_expand_groups takes.  Expands to the 4-byte words of GM_TGT_HOPS_PACKED,
  * out[k] = (hops << 24) | j_k, with a segmented prefix sum per group (one block per group).  Half the bytes of the
- * 4-byte form over PCIe: 33.5 MB instead of 67 MB per 2^24-pair step. */
+ * 4-byte form over PCIe: 33.5 MB instead of 67 MB per 2^24-pair step.  group_row / out_i (both or neither): also write
+ * the first-endpoint vector out_i[k] = group_row[g] in the same pass (gm_expand_groups folded in). */
 int gm_unpack_pairs2(const void* words, const int32_t* base, const int64_t* offsets, int32_t G, int32_t* out,
-                     gm_stream_t stream);
+                     const int32_t* group_row, int32_t* out_i, gm_stream_t stream);
 
 /* ---- ranking metrics (evaluation) ------------------------------------------------------------------------------
  * FastPrecision on the GPU (graphembed/pyx/impl/precision.cpp:249-291 mean average precision, :321-446 per-layer F1

@@ -645,12 +645,14 @@ __global__ void unpack_pairs3_kernel(const unsigned* __restrict__ src, long long
 // exclusive scan (shuffles + one shared-memory hop), running carry across tiles; out[k] = j_k | hops << 24.
 __global__ void __launch_bounds__(256)
 unpack_pairs2_kernel(const unsigned short* __restrict__ words, const int* __restrict__ base,
-                     const long long* __restrict__ offsets, int* __restrict__ out) {
+                     const long long* __restrict__ offsets, int* __restrict__ out, const int* __restrict__ group_row,
+                     int* __restrict__ out_i) {
   __shared__ unsigned warp_tot[8];
   __shared__ unsigned tile_tot;
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long lo = offsets[g], hi = offsets[g + 1];
   unsigned carry = (unsigned)base[g];
+  const int row_i = out_i ? group_row[g] : 0;  // gm_expand_groups folded in: the group's first endpoint
   for (long long t0 = lo; t0 < hi; t0 += 256 * 8) {
     const long long k0 = t0 + (long long)tid * 8;
     unsigned w[8];
@@ -678,7 +680,10 @@ unpack_pairs2_kernel(const unsigned short* __restrict__ words, const int* __rest
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       j += w[e] & 0x1FFFu;
-      if (k0 + e < hi) out[k0 + e] = (int)(j | (((w[e] >> 13) + 1u) << 24));
+      if (k0 + e < hi) {
+        out[k0 + e] = (int)(j | (((w[e] >> 13) + 1u) << 24));
+        if (out_i) out_i[k0 + e] = row_i;
+      }
     }
     __syncthreads();
     carry += tile_tot;
@@ -801,13 +806,14 @@ int gm_unpack_pairs3(const void* src3, int64_t P, int32_t* out, gm_stream_t stre
 }
 
 int gm_unpack_pairs2(const void* words, const int32_t* base, const int64_t* offsets, int32_t G, int32_t* out,
-                     gm_stream_t stream) {
+                     const int32_t* group_row, int32_t* out_i, gm_stream_t stream) {
   if (G < 0) return GM_EINVAL;
   if (G == 0) return GM_OK;
   if (!words || !base || !offsets || !out) return GM_ENULL;
+  if ((group_row == nullptr) != (out_i == nullptr)) return GM_ENULL;
   if (reinterpret_cast<size_t>(words) & 1) return GM_EINVAL;
   unpack_pairs2_kernel<<<(unsigned)G, 256, 0, (cudaStream_t)stream>>>((const unsigned short*)words, base,
-                                                                    (const long long*)offsets, out);
+                                                                    (const long long*)offsets, out, group_row, out_i);
   note_launch();
   return check_launch();
 }

@@ -321,8 +321,23 @@ GM_HD void matmul(const T (&a)[N * N], const T (&b)[N * N], T (&c)[N * N]) {
 // permutation/sign-invariant combinations (sum f(w), v f(w) v^T).
 // ---------------------------------------------------------------------------
 template <typename T> struct JacobiCfg;
-template <> struct JacobiCfg<float> { static constexpr int max_sweeps = 10; };
-template <> struct JacobiCfg<double> { static constexpr int max_sweeps = 16; };
+// off_factor: the iteration stops when ||off(A)||_F^2 <= eps^2 * off_factor * ||diag(A)||_F^2.  fp64: off-diagonal mass
+// a quarter of an ulp of the diagonal (1e-10 parity with LAPACK's eigenvectors).  fp32: 4 ulp (GM_JACOBI_F32_OFF = 16)
+// -- the error a residual off-diagonal E leaves in V f(Lambda) V^T is |E| max|f'| (the eigenvalue gaps cancel for a
+// smooth matrix function), i.e. 5e-7 relative, below the 2e-6 mean / 2e-5 worst-case error the fp32 Cholesky +
+// congruence in front of the solver already carry (tools/eig_lab.cu: accuracy against fp64 unchanged from 1/4 ulp up
+// to 4 ulp, while the share of 4x4 pair matrices done after 3 sweeps goes 95.2 -> 98.5 %).
+#ifndef GM_JACOBI_F32_OFF
+#define GM_JACOBI_F32_OFF 16.0f
+#endif
+template <> struct JacobiCfg<float> {
+  static constexpr int max_sweeps = 10;
+  static constexpr float off_factor = GM_JACOBI_F32_OFF;
+};
+template <> struct JacobiCfg<double> {
+  static constexpr int max_sweeps = 16;
+  static constexpr double off_factor = 0.0625;
+};
 
 // Rotation schedule of one sweep (inside jacobi_eigh).  N == 4 uses the round-robin ("tournament") order (0,1)(2,3) (0,2)(1,3)
 // (0,3)(1,2): the two rotations of a round touch disjoint rows/columns, so their parameter chains are independent
@@ -380,7 +395,7 @@ GM_HD bool jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N], int max_sweeps =
         GM_UNROLL for (int j = i + 1; j < N; ++j) off += a[i * N + j] * a[i * N + j];
       }
       // converged when the off-diagonal mass is below rounding level of the diagonal
-      converged = off <= (Num<T>::eps * Num<T>::eps * (T)0.0625) * dia || off < Num<T>::tiny;
+      converged = off <= (Num<T>::eps * Num<T>::eps * JacobiCfg<T>::off_factor) * dia || off < Num<T>::tiny;
       if (converged || sweep >= max_sweeps) break;
     }
     if constexpr (N == 4) {

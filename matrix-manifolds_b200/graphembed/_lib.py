@@ -132,7 +132,7 @@ _PROTOTYPES = {
     'gm_gather_levels': (ctypes.c_int, [_i32, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     'gm_expand_groups': (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _vp]),
     'gm_unpack_pairs3': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
-    'gm_unpack_pairs2': (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    'gm_unpack_pairs2': (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     'gm_rank_metrics': (ctypes.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _vp]),
 }

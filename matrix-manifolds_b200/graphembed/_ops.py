@@ -549,16 +549,24 @@ def dist2_indexed(spec, x, pairs, c=None, wmin=None):
 
 
 @_no_function_modes
-def unpack_pairs2(words, base, offsets, out):
+def unpack_pairs2(words, base, offsets, out, group_rows=None, out_i=None):
     """gm_unpack_pairs2: 2-byte delta words (engine.pack_hops2) of a source-grouped batch -> out[k] = j | hops << 24.
-    words int16 (P,), base int32 (G,), offsets int64 (G + 1,), out int32 (>= P,), all on one CUDA device."""
-    L.require_cuda(words, base, offsets, out)
+    words int16 (P,), base int32 (G,), offsets int64 (G + 1,), out int32 (>= P,), all on one CUDA device.  With
+    group_rows int32 (G,) and out_i int32 (>= P,) the first-endpoint vector out_i[k] = group_rows[g] is written in the
+    same pass (expand_groups folded in)."""
+    L.require_cuda(words, base, offsets, out, group_rows, out_i)
     G = base.numel()
     if (words.dtype != torch.int16 or base.dtype != torch.int32 or offsets.dtype != torch.int64
             or out.dtype != torch.int32 or offsets.numel() != G + 1 or out.numel() < words.numel()):
         raise ValueError('unpack_pairs2: int16 words, int32 base (G,), int64 offsets (G + 1,), int32 output of P words')
+    if (group_rows is None) != (out_i is None):
+        raise ValueError('unpack_pairs2: group_rows and out_i go together')
+    if group_rows is not None and (group_rows.dtype != torch.int32 or out_i.dtype != torch.int32
+                                   or group_rows.numel() != G or out_i.numel() < words.numel()):
+        raise ValueError('unpack_pairs2: int32 group_rows (G,) and int32 out_i of P words')
     with torch.cuda.device(out.device):
-        rc = L.lib().gm_unpack_pairs2(L.ptr(words), L.ptr(base), L.ptr(offsets), G, L.ptr(out), L.stream_ptr(out.device))
+        rc = L.lib().gm_unpack_pairs2(L.ptr(words), L.ptr(base), L.ptr(offsets), G, L.ptr(out), L.ptr(group_rows),
+                                      L.ptr(out_i), L.stream_ptr(out.device))
     L.check(rc, 'gm_unpack_pairs2')
 
 

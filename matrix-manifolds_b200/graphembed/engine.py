@@ -417,12 +417,13 @@ class PairTrainer:
                 ev.record(self._copy_stream)
             self._pending = (next_batch[2], nslot, ev)
         self._slot = 1 - slot
-        _ops.expand_groups(ds[:G], do[:G + 1], di[:P])
+        if packed2:  # one kernel: gaps -> rows (segmented scan per group) and the group's first endpoint per pair
+            w2, b2 = self._staging2[slot]
+            _ops.unpack_pairs2(w2[:P], b2[:G], do[:G + 1], dj, group_rows=ds[:G], out_i=di)
+        else:
+            _ops.expand_groups(ds[:G], do[:G + 1], di[:P])
         if packed3:
             _ops.unpack_pairs3(self._staging3[slot], P, dj)
-        if packed2:
-            w2, b2 = self._staging2[slot]
-            _ops.unpack_pairs2(w2[:P], b2[:G], do[:G + 1], dj)
         loss = self.step(di[:P], dj[:P], None if packed else dh[:P], epoch=epoch, segments=segments)
         if defer_loss:  # read this step's loss back asynchronously, hand out the previous step's
             return self._queue_loss_read()

@@ -36,6 +36,14 @@ def test_unpack_pairs2_bit_exact():
     want = pack_hops(J[order].contiguous(), H[order].contiguous())
     assert torch.equal(out[:P].cpu(), want)
     assert bool((out[P:] == -1).all())  # nothing written past the batch
+    # the same pass can write the first-endpoint vector (gm_expand_groups folded in)
+    rows = torch.arange(100, 100 + counts.numel(), dtype=torch.int32)
+    out2 = torch.full((P,), -1, dtype=torch.int32, device=DEV)
+    out_i = torch.full((P + 2,), -7, dtype=torch.int32, device=DEV)
+    _ops.unpack_pairs2(words.to(DEV), bases.to(DEV), offsets.to(DEV), out2, group_rows=rows.to(DEV), out_i=out_i)
+    assert torch.equal(out2.cpu(), want)
+    assert torch.equal(out_i[:P].cpu(), torch.repeat_interleave(rows, counts))
+    assert bool((out_i[P:] == -7).all())
     # every group keeps its pairs (a permutation inside the group), sorted by row
     for gi in range(counts.numel()):
         a, b = int(offsets[gi]), int(offsets[gi + 1])
