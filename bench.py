@@ -75,11 +75,11 @@ def parse():
                     '4-byte ones; measured on one B200 it is NOT faster (1.339 vs 1.31 ms per step: the step is not PCIe '
                     'bound at 4 B/pair and the extra expansion kernel costs 0.03 ms)')
     ap.add_argument('--lists-format', default='auto', choices=['auto', '2', '4'], help='--e2e lists: bytes per pair on '
-                    'the host->device link.  4: int32 j | hops << 24.  2: the gap format (pack_hops2: every source\'s '
-                    'targets sorted by row, 13-bit gap + 3 bits of hop count, expanded on the device by '
-                    'gm_unpack_pairs2).  auto: 4 on one GPU (measured: the step is then bound by the device, 1.324 ms '
-                    'with 4-byte words vs 1.354 ms with the 64 us expansion kernel of the 2-byte ones), 2 when several '
-                    'GPUs share the host\'s links')
+                    'the host->device link.  4: int32 j | hops << 24.  2 (= auto whenever the batch fits): the gap format '
+                    '(pack_hops2: every group\'s targets sorted by row, 13-bit gap + 3 bits of hop count, expanded on the '
+                    'device by gm_unpack_pairs2 together with the first-endpoint vector, 53 us per 2^24 pairs).  Measured '
+                    'end to end on one GPU: 1.197 ms per step with 2-byte words (device bound), 1.285 ms with 4-byte '
+                    'words (PCIe bound: 67 MB per step at 52 GB/s)')
     ap.add_argument('--layout', default='replicated', choices=['replicated', 'sharded'], help='N>1: `replicated` = every '
                     'rank holds the whole point table, partial gradients exchanged by the peer-memory owner update after '
                     'the pair kernel; `sharded` = ROW-SHARDED embeddings (engine.ShardedPairTrainer): every rank holds '
@@ -713,15 +713,14 @@ def main():
 
     # ---- end-to-end timing from pinned host buffers ----------------------------------------------------------------
     nb = len(batches)
-    # auto: explicit lists at every GPU count -- 4-byte words on one GPU, the 2-byte gap words when several GPUs share the
-    # host (measured end to end, ms per step lists2 / sampled: 4 GPUs 1.556 / 1.722, 8 GPUs 1.740 / 1.778; 4-byte lists
-    # at 4 GPUs: 1.909)
+    # auto: explicit lists at every GPU count, as 2-byte gap words (measured end to end, ms per step lists2 / sampled: 4 GPUs
+    # 1.556 / 1.722, 8 GPUs 1.740 / 1.778 before the expansion kernel was vectorised; 4-byte lists at 4 GPUs: 1.909)
     e2e_mode = args.e2e if args.e2e != 'auto' else 'lists'
     if e2e_mode == 'lists':
         # source-grouped upload (sources, offsets, j, hops): 4-5 B/pair over PCIe; the next batch is uploaded on a
         # second stream while this one computes; every step ends with a device->host read of the loss
         use3 = args.lists3 and not args.unpacked and all(b[6] is not None for b in batches)
-        use2 = ((args.lists_format == '2' or (args.lists_format == 'auto' and world > 1)) and not args.lists3
+        use2 = (args.lists_format in ('2', 'auto') and not args.lists3
                 and not args.unpacked and all(b[7] is not None for b in batches))
 
         def grouped(b):

@@ -641,25 +641,36 @@ __global__ void unpack_pairs3_kernel(const unsigned* __restrict__ src, long long
 }
 
 // 2-byte pair words (gm_unpack_pairs2): group g's targets arrive sorted, word k = (j_k - j_{k-1}) | (hops - 1) << 13 with
-// j_{-1} := base[g].  One block per group walks it in tiles of 256 x 8 words: per-thread sum of 8 deltas, block-wide
-// exclusive scan (shuffles + one shared-memory hop), running carry across tiles; out[k] = j_k | hops << 24.
+// j_{-1} := base[g].  One block per group walks it in tiles of 256 x 8 words that start at a multiple of 8 words, so that
+// a thread's 8 words are one 16-byte load and its 8 results two 16-byte stores (words outside the group are masked):
+// per-thread sum of 8 gaps, block-wide exclusive scan (shuffles + one shared-memory hop), running carry across tiles;
+// out[k] = j_k | hops << 24 and, optionally, out_i[k] = group_row[g] (gm_expand_groups folded in).
 __global__ void __launch_bounds__(256)
 unpack_pairs2_kernel(const unsigned short* __restrict__ words, const int* __restrict__ base,
                      const long long* __restrict__ offsets, int* __restrict__ out, const int* __restrict__ group_row,
-                     int* __restrict__ out_i) {
+                     int* __restrict__ out_i, int vec_ok) {
   __shared__ unsigned warp_tot[8];
   __shared__ unsigned tile_tot;
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const long long lo = offsets[g], hi = offsets[g + 1];
+  const long long lo = offsets[g], hi = offsets[g + 1], P = offsets[gridDim.x];
   unsigned carry = (unsigned)base[g];
-  const int row_i = out_i ? group_row[g] : 0;  // gm_expand_groups folded in: the group's first endpoint
-  for (long long t0 = lo; t0 < hi; t0 += 256 * 8) {
+  const int row_i = out_i ? group_row[g] : 0;
+  for (long long t0 = lo & ~7LL; t0 < hi; t0 += 256 * 8) {
     const long long k0 = t0 + (long long)tid * 8;
     unsigned w[8];
+    const bool inside = k0 >= lo && k0 + 8 <= hi;  // all 8 words belong to this group
+    if (vec_ok && k0 < hi && k0 + 8 > lo && k0 + 8 <= P) {
+      const uint4 v = *reinterpret_cast<const uint4*>(words + k0);
+      w[0] = v.x & 0xFFFFu; w[1] = v.x >> 16; w[2] = v.y & 0xFFFFu; w[3] = v.y >> 16;
+      w[4] = v.z & 0xFFFFu; w[5] = v.z >> 16; w[6] = v.w & 0xFFFFu; w[7] = v.w >> 16;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = (k0 + e >= lo && k0 + e < hi) ? (unsigned)words[k0 + e] : 0u;
+    }
     unsigned sum = 0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      w[e] = (k0 + e < hi) ? (unsigned)words[k0 + e] : 0u;
+      if (!inside && !(k0 + e >= lo && k0 + e < hi)) w[e] = 0u;  // a neighbouring group's word
       sum += w[e] & 0x1FFFu;
     }
     unsigned incl = sum;
@@ -677,12 +688,28 @@ unpack_pairs2_kernel(const unsigned short* __restrict__ words, const int* __rest
     }
     if (tid == 255) tile_tot = before + incl;
     unsigned j = carry + before + incl - sum;  // row id reached before this thread's first word
+    int r[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       j += w[e] & 0x1FFFu;
-      if (k0 + e < hi) {
-        out[k0 + e] = (int)(j | (((w[e] >> 13) + 1u) << 24));
-        if (out_i) out_i[k0 + e] = row_i;
+      r[e] = (int)(j | (((w[e] >> 13) + 1u) << 24));
+    }
+    if (inside && vec_ok) {
+      int4* o4 = reinterpret_cast<int4*>(out + k0);
+      o4[0] = make_int4(r[0], r[1], r[2], r[3]);
+      o4[1] = make_int4(r[4], r[5], r[6], r[7]);
+      if (out_i) {
+        int4* i4 = reinterpret_cast<int4*>(out_i + k0);
+        i4[0] = make_int4(row_i, row_i, row_i, row_i);
+        i4[1] = make_int4(row_i, row_i, row_i, row_i);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (k0 + e >= lo && k0 + e < hi) {
+          out[k0 + e] = r[e];
+          if (out_i) out_i[k0 + e] = row_i;
+        }
       }
     }
     __syncthreads();
@@ -812,8 +839,12 @@ int gm_unpack_pairs2(const void* words, const int32_t* base, const int64_t* offs
   if (!words || !base || !offsets || !out) return GM_ENULL;
   if ((group_row == nullptr) != (out_i == nullptr)) return GM_ENULL;
   if (reinterpret_cast<size_t>(words) & 1) return GM_EINVAL;
+  // 16-byte accesses when every table starts on a 16-byte boundary (device allocations do); scalar otherwise
+  const int vec_ok = ((reinterpret_cast<size_t>(words) | reinterpret_cast<size_t>(out) |
+                       reinterpret_cast<size_t>(out_i)) & 15) == 0;
   unpack_pairs2_kernel<<<(unsigned)G, 256, 0, (cudaStream_t)stream>>>((const unsigned short*)words, base,
-                                                                    (const long long*)offsets, out, group_row, out_i);
+                                                                    (const long long*)offsets, out, group_row, out_i,
+                                                                    vec_ok);
   note_launch();
   return check_launch();
 }

@@ -44,6 +44,11 @@ def test_unpack_pairs2_bit_exact():
     assert torch.equal(out2.cpu(), want)
     assert torch.equal(out_i[:P].cpu(), torch.repeat_interleave(rows, counts))
     assert bool((out_i[P:] == -7).all())
+    # tables that do not start on a 16-byte boundary take the scalar path: same words
+    w_off = torch.cat([torch.zeros(1, dtype=torch.int16), words]).to(DEV)[1:]
+    out3 = torch.full((P + 1,), -1, dtype=torch.int32, device=DEV)[1:]
+    _ops.unpack_pairs2(w_off, bases.to(DEV), offsets.to(DEV), out3)
+    assert torch.equal(out3.cpu(), want)
     # every group keeps its pairs (a permutation inside the group), sorted by row
     for gi in range(counts.numel()):
         a, b = int(offsets[gi]), int(offsets[gi + 1])
