@@ -780,7 +780,7 @@ def main():
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
     tpath = os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json')
     if os.path.isfile(tpath) and P == (1 << 24) and N == 2_000_000:
-        traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+        traffic = json.load(open(tpath)).get('dram_bytes_per_launch' if seg == 8 else 'dram_bytes_per_launch_windows0' if seg == 0 else 'none')
     total_pairs = P * world * args.steps
     line = {
         'metric': METRIC, 'value': total_pairs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -819,7 +819,13 @@ def main():
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'kernel': 'spd_pair_stream_kernel<SpdAI<float,4>,K_FUSED>',
-                     'kernel_ms': pair_ms, 'bytes_per_pair': BYTES_PER_PAIR, 'peak_source': peak_src},
+                     'kernel_ms': pair_ms, 'bytes_per_pair': BYTES_PER_PAIR, 'peak_source': peak_src,
+                     'note': ('achieved = algorithmic bytes (268 B per pair: two 64-B rows read, two 64-B gradient rows '
+                              'read-modify-written, index + hop word) / kernel time, as SURVEY 8(d) defines it.  With '
+                              'window-ordered batches most of those bytes are served by L2 (traffic = measured DRAM '
+                              'bytes per launch, far below the algorithmic figure) and the kernel is bound by '
+                              'instruction issue (ncu: issue-active 74 %, profiles/r02_pairs_final_full.txt), not by HBM')
+                     if seg else None},
         'clocks': clock_info,
     }
     if not args.no_cpu_baseline:

@@ -327,8 +327,14 @@ template <typename T> struct JacobiCfg;
 // smooth matrix function), i.e. 5e-7 relative, below the 2e-6 mean / 2e-5 worst-case error the fp32 Cholesky +
 // congruence in front of the solver already carry (tools/eig_lab.cu: accuracy against fp64 unchanged from 1/4 ulp up
 // to 4 ulp, while the share of 4x4 pair matrices done after 3 sweeps goes 95.2 -> 98.5 %).
+// Applied to n <= 4 only (GM_JACOBI_F32_OFF_MAX_N): there the solver runs inside warps that stop together, and the
+// looser test lets most warps stop after 3 sweeps (pair kernel 0.962 -> 0.902 ms).  For n = 6 the same change measured
+// 9 % SLOWER (BASELINE config 4: 57.6 -> 62.5 ms per epoch, profiles/r02_pair_kernel_ab.txt run 12), so n >= 5 keep 1/4 ulp.
 #ifndef GM_JACOBI_F32_OFF
 #define GM_JACOBI_F32_OFF 16.0f
+#endif
+#ifndef GM_JACOBI_F32_OFF_MAX_N
+#define GM_JACOBI_F32_OFF_MAX_N 4
 #endif
 template <> struct JacobiCfg<float> {
   static constexpr int max_sweeps = 10;
@@ -395,7 +401,9 @@ GM_HD bool jacobi_eigh(T (&a)[N * N], T (&v)[N * N], T (&w)[N], int max_sweeps =
         GM_UNROLL for (int j = i + 1; j < N; ++j) off += a[i * N + j] * a[i * N + j];
       }
       // converged when the off-diagonal mass is below rounding level of the diagonal
-      converged = off <= (Num<T>::eps * Num<T>::eps * JacobiCfg<T>::off_factor) * dia || off < Num<T>::tiny;
+      // (n <= 4 in fp32: 4 ulp; everything else 1/4 ulp -- see JacobiCfg)
+      constexpr T off_factor = (N <= GM_JACOBI_F32_OFF_MAX_N) ? JacobiCfg<T>::off_factor : (T)0.0625;
+      converged = off <= (Num<T>::eps * Num<T>::eps * off_factor) * dia || off < Num<T>::tiny;
       if (converged || sweep >= max_sweeps) break;
     }
     if constexpr (N == 4) {
