@@ -127,7 +127,7 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, 
     row, source) order (graphembed.engine.window_order) -- the groups are then the (window, source) runs -- for a launch
     with gm_pairs_t.segments = windows."""
     from graphembed.data import bfs_levels, edges_to_csr
-    from graphembed.engine import pack_hops, pack_hops2, pack_hops3, window_order
+    from graphembed.engine import pack_hops, pack_hops2, pack_hops3, window_groups
     from graphembed import _lib as L
     P = 1 << log2_pairs
     per_src = max(1, P // N_SOURCES)
@@ -157,12 +157,8 @@ def make_pair_batches(n_nodes, log2_pairs, n_batches, device, seed, n_src=None, 
         offsets = (torch.arange(n_src + 1, dtype=torch.int64) * per_src)
         hops_h = hops.cpu()
         if windows > 1:
-            order = window_order(J, n_nodes, windows)
+            order, src_groups, offsets = window_groups(src, offsets, J, n_nodes, windows)
             I, J, hops_h = I[order].contiguous(), J[order].contiguous(), hops_h[order].contiguous()
-            key = (J.long() * windows) // n_nodes * n_src + slot.long()[order]
-            counts = torch.bincount(key, minlength=windows * n_src)
-            offsets = torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)])
-            src_groups = src.repeat(windows)
         else:
             src_groups = src
         three = n_nodes <= (1 << 21) and int(hops_h.max()) <= 8  # (j, hops - 1) fit 21 + 3 bits: 3 bytes per pair

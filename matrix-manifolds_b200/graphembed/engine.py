@@ -528,6 +528,23 @@ def window_order(idx_j, n_points, segments):
     return torch.sort(window, stable=True).indices
 
 
+def window_groups(sources, offsets, idx_j, n_points, segments):
+    """A source-grouped batch (sources int32 (G,), offsets int64 (G + 1,), targets idx_j (P,)) in window order: returns
+    (order, group_rows, group_offsets) with `order` = window_order(idx_j, n_points, segments) and the (window, source)
+    groups of the reordered batch -- group w * G + g holds the pairs of source g whose target lies in window w (possibly
+    none), group_rows[w * G + g] = sources[g].  Feed `idx_j[order]` etc. with these to step_host_grouped(segments=...)
+    or pack_hops2."""
+    G = sources.numel()
+    counts = offsets[1:] - offsets[:-1]
+    group = torch.repeat_interleave(torch.arange(G, dtype=torch.int64), counts)
+    order = window_order(idx_j, n_points, segments)
+    j = idx_j.long() & 0x00ffffff if idx_j.dtype == torch.int32 else idx_j.long()
+    key = ((j[order] * int(segments)) // int(n_points)) * G + group[order]
+    group_counts = torch.bincount(key, minlength=int(segments) * G)
+    group_offsets = torch.cat([torch.zeros(1, dtype=torch.int64), group_counts.cumsum(0)])
+    return order, sources.repeat(int(segments)).contiguous(), group_offsets
+
+
 class ProductPairTrainer:
     """(I, J, hops) pair batches through a PRODUCT-manifold embedding -- BASELINE config 3 ("product SPD 3x3 x Lorentz 5,
     sampled pairs").  The distance of a pair is sum_f softplus(scale_f) * d_f^2 (modules.py:84-88); one step is

@@ -228,3 +228,28 @@ def test_pack_hops2_round_trip_on_the_host():
     J2 = J.clone()
     J2[0], J2[1:400] = 0, 19999
     assert pack_hops2(offs, J2, H) is None  # a gap that does not fit 13 bits
+
+
+def test_window_groups_are_the_runs_of_the_reordered_batch():
+    """engine.window_groups: after window_order the batch consists of (window, source) runs; the returned group rows and
+    offsets describe exactly those runs (empty groups included), so expand_groups / pack_hops2 can take them as is."""
+    import torch
+    from graphembed.engine import window_groups
+    g = torch.Generator().manual_seed(0)
+    n_points, G, W = 1000, 7, 4
+    counts = torch.tensor([50, 0, 13, 200, 1, 77, 64])
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)])
+    src = torch.randperm(n_points, generator=g)[:G].int()
+    P = int(offsets[-1])
+    I = torch.repeat_interleave(src, counts)
+    J = torch.randint(n_points, (P,), generator=g, dtype=torch.int32)
+    order, rows, offs = window_groups(src, offsets, J, n_points, W)
+    assert rows.numel() == W * G and offs.numel() == W * G + 1 and int(offs[-1]) == P
+    assert torch.equal(torch.repeat_interleave(rows, offs[1:] - offs[:-1]), I[order])
+    win = (J[order].long() * W) // n_points
+    for k in range(W * G):
+        a, b = int(offs[k]), int(offs[k + 1])
+        assert bool((win[a:b] == k // G).all())
+    packed = J | (torch.randint(1, 9, (P,), generator=g, dtype=torch.int32) << 24)  # a packed hop count is ignored
+    o2, r2, f2 = window_groups(src, offsets, packed, n_points, W)
+    assert torch.equal(o2, order) and torch.equal(f2, offs)
