@@ -20,7 +20,7 @@ from . import _lib as L
 from . import _ops
 from . import _torch_ops
 from .modules import ManifoldParameter, _softplus_value
-from .parallel import (RowShards, ShardedArena, allreduce_step_buffers, cyclic_shard, cyclic_unshard,
+from .parallel import (RowShards, ShardedArena, allreduce_step_buffers, cyclic_shard, gather_cyclic,
                        try_peer_arena)
 
 
@@ -508,9 +508,7 @@ class ShardedPairTrainer(PairTrainer):
 
     def gather(self):
         """The full (N, ...) point table, rebuilt from every rank's shard (an all-gather; for validation / snapshots)."""
-        buf = self.x.new_empty((self.world,) + tuple(self.x.shape))
-        torch.distributed.all_gather_into_tensor(buf, self.x.contiguous(), group=self.pg)
-        full = cyclic_unshard(list(buf.unbind(0)))
+        full = gather_cyclic(self.x, self.pg)
         self._full.data = full
         return full
 

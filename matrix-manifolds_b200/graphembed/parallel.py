@@ -223,6 +223,15 @@ def cyclic_unshard(shards):
     return full
 
 
+def gather_cyclic(shard, group=None):
+    """The full (N, ...) table from every rank's cyclic shard (equal row counts): an all-gather, then cyclic_unshard.
+    Works on any backend (NCCL on GPUs, gloo in the CPU tests); for validation / snapshots, not on the step path."""
+    world = dist.get_world_size(group)
+    shards = [torch.empty_like(shard) for _ in range(world)]
+    dist.all_gather(shards, shard.contiguous(), group=group)
+    return cyclic_unshard(shards)
+
+
 class ShardedArena(PeerArena):
     """Per-rank arena [point shard | gradient shard | step accumulator | accumulator sum | flag block] of a
     ROW-SHARDED embedding, mapped by every other rank through CUDA IPC.  `x` is this rank's shard (cyclic_shard of the

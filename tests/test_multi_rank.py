@@ -161,3 +161,59 @@ def test_phase_vote_keeps_ranks_in_lock_step_when_one_fails():
         assert (res[1][1] is not None) == (rank == 1)
         assert res[2][0] is False and res[2][2] == ['p1']                    # both ranks stop before c1
         assert (res[2][1] is not None) == (rank == 0)
+
+
+def _row_sharded_worker(rank, world, port, out):
+    """CPU analogue of engine.ShardedPairTrainer (the GPU path gathers / reduces the remote rows inside the pair kernel
+    over NVLink; here the same data movement is spelled out with gloo collectives and the oracle's autograd): every rank
+    keeps only its cyclic shard of the points and of the optimizer state, evaluates ITS slice of the pair batch, the
+    gradient rows travel to their owners, the optimizer update is local."""
+    sys.path.insert(0, os.path.join(ROOT, 'matrix-manifolds_b200'))
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import manifolds_oracle as O
+    from graphembed.parallel import cyclic_shard, cyclic_unshard, gather_cyclic, shard_range
+    torch.manual_seed(0)
+    orc = O.SpdOracle(3)
+    n, P = 24, 157
+    x0 = orc.rand(n, ir=1.0)
+    I = torch.randint(n, (P,))
+    J = (I + 1 + torch.randint(n - 1, (P,))) % n
+    t = torch.rand(P, dtype=torch.float64) + 0.2
+    shard = cyclic_shard(x0, rank, world)          # the only copy of the points this rank keeps
+    state = {}
+    lo, hi = shard_range(P, rank, world)
+    for step in range(3):
+        full = gather_cyclic(shard)                # (GPU: row gathers over NVLink inside the kernel)
+        xr = full.clone().requires_grad_()
+        O.quotient_loss(t[lo:hi], orc.dist2(xr[I[lo:hi]], xr[J[lo:hi]]), 1.0, step + 1).backward()
+        g = xr.grad.clone()
+        dist.all_reduce(g)                         # (GPU: red.global.add into the owning shard)
+        shard = O.radam_step(orc, shard, cyclic_shard(g, rank, world), state, lr=0.01, max_grad_norm=100,
+                             exact=True).detach()
+    result = gather_cyclic(shard)
+    if rank == 0:
+        x, st = x0.clone(), {}
+        for step in range(3):
+            xs = x.clone().requires_grad_()
+            O.quotient_loss(t, orc.dist2(xs[I], xs[J]), 1.0, step + 1).backward()
+            x = O.radam_step(orc, x, xs.grad, st, lr=0.01, max_grad_norm=100, exact=True).detach()
+        shards = [cyclic_shard(x, r, world) for r in range(world)]
+        out.put((float((result - x).abs().max() / x.abs().max()), bool(torch.equal(cyclic_unshard(shards), x)),
+                 tuple(shard.shape)))
+    dist.destroy_process_group()
+
+
+def test_row_sharded_step_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_row_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, round_trip, shape = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert err < 1e-12 and round_trip and shape == (12, 3, 3)
